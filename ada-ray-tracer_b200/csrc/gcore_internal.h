@@ -1,0 +1,59 @@
+// gcore_internal.h -- host-side launch interface between gcore_api.cu, render_kernels.cu and lbvh_build.cu.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gcore.h"
+
+namespace art { struct DeviceScene; struct BvhView; }
+
+namespace gcore_dev {
+
+#define GC_TILE 32                       // tile edge in pixels; one tile = 1024 accumulator slots
+
+struct RenderArgs {
+  int      width, height;
+  int      tiles_x, ntiles;              // tile grid of the whole image
+  int      rank, world;                  // this device renders tiles with (tile % world) == rank
+  int      nslots;                       // local tiles * 1024
+  int      anti_aliasing, max_depth, passes;
+  uint32_t seed;
+  int      first_sample;
+  float    bg[3];
+  float    zdir;                         // -float(width) / safe_tan(fov/2)   (ray_tracer.adb:67)
+  float    half_w, half_h;               // float(width)/2, float(height)/2
+  float4*  accum;                        // slot-major accumulator (rgb, unused)
+  unsigned long long* counters;          // [0] += scene queries, [1] += queries inside the mesh bbox, [2] += shaded bounces
+};
+
+cudaError_t upload_scene(const art::DeviceScene* host_copy, cudaStream_t s);
+// render_type: GCORE_PT_STUPID / GCORE_PT_SHADOW / GCORE_PT_MIS
+cudaError_t launch_render(int render_type, const RenderArgs& a, cudaStream_t s);
+// RT_DEBUG / RT_WHITTED: palette of the primary hit written into accum (ray_tracer.adb:208-238)
+cudaError_t launch_debug(const RenderArgs& a, cudaStream_t s);
+// primary hits, row-major hits[y*W+x]
+cudaError_t launch_primary_hits(const RenderArgs& a, gcore_hit* d_hits, cudaStream_t s);
+cudaError_t launch_closest_batch(int n, const gcore_ray* d_rays, gcore_hit* d_hits, cudaStream_t s);
+// pure triangle query on the committed LBVH (legacy gcore_closest_hit semantics)
+cudaError_t launch_bvh_batch(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, cudaStream_t s);
+// slot-major accumulator -> row-major outputs; either pointer may be null.
+// hdr4[y*W+x] = (r,g,b,spp), ldr[y*W+x] = R | G<<8 | B<<16 (ray_tracer.adb:281-291, 19-57)
+cudaError_t launch_resolve(const RenderArgs& a, int spp, float4* d_hdr4, uint32_t* d_ldr, cudaStream_t s);
+// gather variant for multi-GPU: `all` holds world slot-major buffers back to back (rank r at r*nslots)
+cudaError_t launch_resolve_gathered(const RenderArgs& a, const float4* d_all, int spp, float4* d_hdr4, uint32_t* d_ldr, cudaStream_t s);
+int render_kernel_regs(int render_type);
+
+// ---- lbvh_build.cu ----
+struct LbvhBuffers {                     // device allocations owned by the builder
+  float4* nodes = nullptr; float4* tris = nullptr; float* tri_normals = nullptr;
+  int ntris = 0, nnodes = 0, root = -1;
+  size_t bytes = 0;
+  float build_ms = 0.0f;
+};
+// verts: device float3 array (world space), tris: device int3 array, normals9: optional device per-triangle nA,nB,nC
+cudaError_t lbvh_build(const float* d_verts, int nverts, const int* d_tris, int ntris, const float* d_normals9,
+                       LbvhBuffers* out, cudaStream_t s);
+void lbvh_free(LbvhBuffers* b);
+
+}  // namespace gcore_dev

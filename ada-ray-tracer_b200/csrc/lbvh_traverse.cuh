@@ -1,0 +1,88 @@
+// lbvh_traverse.cuh -- closest-hit / any-hit traversal of the packed LBVH (replaces Embree's
+// BVHNIntersector1 reached through rtcIntersect1, cpp/embree_connect.cpp:218, and scales
+// geometry.adb:266-323 IntersectMeshBF beyond a handful of triangles).
+//
+// Node (64 B = 4 x float4, one 16-byte vector load each):
+//   n0 = (c0.min.x, c0.min.y, c0.min.z, c0.max.x)
+//   n1 = (c0.max.y, c0.max.z, c1.min.x, c1.min.y)
+//   n2 = (c1.min.z, c1.max.x, c1.max.y, c1.max.z)
+//   n3 = (bits child0, bits child1, -, -)      child >= 0: internal node, child < 0: leaf, ~child = first sorted slot,
+//                                              n3.z/w bits = triangle counts of leaf children
+// Triangle slot (48 B = 3 x float4): (A.xyz, bits prim id), (e1.xyz, 0), (e2.xyz, 0) with e1 = B - A, e2 = C - A.
+//
+// Semantics: nearest hit of the reference's one-sided Moeller-Trumbore test (geometry.adb:231-263) inside the
+// open window (t_min, t_max); exact ties go to the lowest ORIGINAL triangle index.  Box tests only cull: boxes
+// are padded at build time and the slab test is evaluated conservatively, so the result equals testing every
+// triangle.
+#pragma once
+
+namespace art {
+
+#define LBVH_STACK 96
+
+ART_D bool slab_hit(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz,
+                    f3 o, f3 inv, float t_lo, float t_hi, float& t_entry) {
+  float x0 = (bminx - o.x) * inv.x, x1 = (bmaxx - o.x) * inv.x;
+  float y0 = (bminy - o.y) * inv.y, y1 = (bmaxy - o.y) * inv.y;
+  float z0 = (bminz - o.z) * inv.z, z1 = (bmaxz - o.z) * inv.z;
+  // fminf/fmaxf drop NaNs (0 * inf on axis-parallel rays lying in a slab plane) -> never culls wrongly
+  float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_lo));
+  float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi));
+  t_entry = tn;
+  return tn <= tf * 1.00001f + 1.0e-6f;
+}
+
+ART_D void bvh_leaf_test(const BvhView& bv, int first, int count, f3 o, f3 d, float t_min,
+                         float& best_t, int& best_prim, float& best_u, float& best_v) {
+  for (int s = first; s < first + count; s++) {
+    float4 a  = __ldg(&bv.tris[3 * s + 0]);
+    float4 e1 = __ldg(&bv.tris[3 * s + 1]);
+    float4 e2 = __ldg(&bv.tris[3 * s + 2]);
+    int prim = __float_as_int(a.w);
+    float t, u, v;
+    // closed upper bound so that equal-t candidates reach the tie rule: test against nextafter(best_t)
+    if (intersect_triangle(o, d, mk3(a.x, a.y, a.z), mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z), t_min, ART_FLT_LAST, t, u, v)) {
+      if (t < best_t || (t == best_t && best_prim >= 0 && prim < best_prim)) { best_t = t; best_prim = prim; best_u = u; best_v = v; }
+    }
+  }
+}
+
+// closest hit; prim = -1 when nothing is hit inside (t_min, t_max)
+ART_D void bvh_closest(const BvhView& bv, f3 o, f3 d, float t_min, float t_max, int& prim_o, float& t_o, float& u_o, float& v_o) {
+  float best_t = t_max; int best_prim = -1; float best_u = 0.0f, best_v = 0.0f;
+  if (bv.ntris > 0) {
+    if (bv.root < 0) {
+      bvh_leaf_test(bv, 0, bv.ntris, o, d, t_min, best_t, best_prim, best_u, best_v);
+    } else {
+      f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+      int stack[LBVH_STACK];
+      int sp = 0;
+      int node = bv.root;
+      for (;;) {
+        float4 n0 = __ldg(&bv.nodes[4 * node + 0]);
+        float4 n1 = __ldg(&bv.nodes[4 * node + 1]);
+        float4 n2 = __ldg(&bv.nodes[4 * node + 2]);
+        float4 n3 = __ldg(&bv.nodes[4 * node + 3]);
+        int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+        float e0, e1;
+        bool h0 = slab_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, best_t, e0);
+        bool h1 = slab_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, best_t, e1);
+        if (h0 && c0 < 0) { bvh_leaf_test(bv, ~c0, __float_as_int(n3.z), o, d, t_min, best_t, best_prim, best_u, best_v); h0 = false; }
+        if (h1 && c1 < 0) { bvh_leaf_test(bv, ~c1, __float_as_int(n3.w), o, d, t_min, best_t, best_prim, best_u, best_v); h1 = false; }
+        if (h0 && h1) {
+          // near child first, far child on the stack
+          if (e1 < e0) { int t = c0; c0 = c1; c1 = t; }
+          if (sp < LBVH_STACK) stack[sp++] = c1;
+          node = c0;
+        } else if (h0) node = c0;
+        else if (h1) node = c1;
+        else { if (sp == 0) break; node = stack[--sp]; }
+      }
+    }
+  }
+  prim_o = (best_t < t_max || best_prim >= 0) ? best_prim : -1;
+  if (best_prim < 0) prim_o = -1;
+  t_o = best_t; u_o = best_u; v_o = best_v;
+}
+
+}  // namespace art

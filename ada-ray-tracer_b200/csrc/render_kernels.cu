@@ -1,0 +1,359 @@
+// render_kernels.cu -- the render hot path on the GPU (sm_100a).
+//
+// Built with -fmad=false -prec-div=true -prec-sqrt=true -ftz=false (see art_math.cuh): every result is bit-identical
+// to the reference arithmetic restated by the oracle.
+//
+// Kernels
+//   render_kernel<RT>   K1+K2+K4+K5+K6a  one thread per pixel slot; persistent per-pixel loop over all samples of the
+//                       call with path regeneration (a lane starts its next sample as soon as its path ends), fused
+//                       ray generation, scene query, NEE + shadow query, BSDF sampling, per-pass accumulation.
+//                       Replaces ray_tracer-integrators.adb:25-301, ray_tracer.adb:61-132.
+//   debug_kernel        RT_DEBUG / RT_WHITTED palette render, ray_tracer.adb:208-238.
+//   primary_kernel      primary hit records (config C2).
+//   closest_kernel      Scene.Find_Closest_Hit for a batch of rays.
+//   bvh_batch_kernel    triangle-only LBVH query (legacy gcore_closest_hit seam).
+//   resolve_kernel      K6b/K7: slot-major accumulator(s) -> row-major HDR float4 and LDR u32 (ray_tracer.adb:281-291).
+#include "gcore_internal.h"
+#include "art_shade.cuh"
+
+using namespace art;
+
+namespace {
+
+#define RENDER_BLOCK 128
+#define MAX_DEPTH_CAP 16
+
+struct PixelId { int x, y, active; };
+
+// slot -> pixel.  A tile is 32x32 pixels = 1024 slots = 32 warps; warp w of a tile covers the 8x4 pixel block
+// (w % 4, w / 4); lanes are row-major inside the block.  Slots of a warp are contiguous -> coalesced float4 I/O.
+__device__ __forceinline__ PixelId slot_to_pixel(const gcore_dev::RenderArgs& a, int slot, int rank) {
+  int tile_local = slot >> 10, q = slot & 1023;
+  int tile = tile_local * a.world + rank;
+  int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+  int w = q >> 5, l = q & 31;
+  PixelId p;
+  p.x = tx * GC_TILE + (w & 3) * 8 + (l & 7);
+  p.y = ty * GC_TILE + (w >> 2) * 4 + (l >> 3);
+  p.active = (tile < a.ntiles) && (p.x < a.width) && (p.y < a.height);
+  return p;
+}
+
+// pixel -> (rank, slot) for the resolve
+__device__ __forceinline__ void pixel_to_slot(const gcore_dev::RenderArgs& a, int x, int y, int& rank, int& slot) {
+  int tx = x / GC_TILE, ty = y / GC_TILE, lx = x % GC_TILE, ly = y % GC_TILE;
+  int tile = ty * a.tiles_x + tx;
+  rank = tile % a.world;
+  int tile_local = tile / a.world;
+  int w = (ly >> 2) * 4 + (lx >> 3), l = (ly & 3) * 8 + (lx & 7);
+  slot = (tile_local << 10) + (w << 5) + l;
+}
+
+// EyeRayDirection / Generate4RayDirections (ray_tracer.adb:61-97) + normalize(cam.matrix * dir) (integrators.adb:46,58)
+__device__ __forceinline__ f3 eye_ray_dir(const gcore_dev::RenderArgs& a, int x, int y, int sub) {
+  const float third = 1.0f / 3.0f, two_thirds = 2.0f / 3.0f;
+  float offx = (sub < 0) ? 0.5f : ((sub & 2) ? two_thirds : third);
+  float offy = (sub < 0) ? 0.5f : ((sub & 1) ? two_thirds : third);
+  f3 r;
+  r.x = (float)x + offx - a.half_w;
+  r.y = (float)y + offy - a.half_h;
+  r.z = a.zdir;
+  r = normalize(r);
+  f3 m;
+  m.x = g_scn.cam_m[0] * r.x + g_scn.cam_m[1] * r.y + g_scn.cam_m[2] * r.z + g_scn.cam_m[3];   // vector_math.adb:137-144
+  m.y = g_scn.cam_m[4] * r.x + g_scn.cam_m[5] * r.y + g_scn.cam_m[6] * r.z + g_scn.cam_m[7];
+  m.z = g_scn.cam_m[8] * r.x + g_scn.cam_m[9] * r.y + g_scn.cam_m[10] * r.z + g_scn.cam_m[11];
+  return normalize(m);
+}
+
+__device__ __forceinline__ void store_hit(gcore_hit* o, const DHit& h) {
+  o->is_hit = h.is_hit; o->prim_type = h.prim_type; o->prim_index = h.prim_index; o->matId = h.matId; o->mat = h.mat;
+  o->t = h.t; o->normal[0] = h.normal.x; o->normal[1] = h.normal.y; o->normal[2] = h.normal.z; o->tx = h.tx; o->ty = h.ty;
+}
+
+template <int RT>
+__global__ void __launch_bounds__(RENDER_BLOCK) render_kernel(const __grid_constant__ gcore_dev::RenderArgs a) {
+  const int slot = blockIdx.x * RENDER_BLOCK + threadIdx.x;
+  unsigned int nrays = 0, nmesh = 0, nbounce = 0;
+  const PixelId px = slot_to_pixel(a, slot < a.nslots ? slot : 0, a.rank);
+  if (slot < a.nslots && px.active) {
+    const float4 acc4 = a.accum[slot];
+    f3 acc = mk3(acc4.x, acc4.y, acc4.z);
+    const f3 bg = mk3(a.bg[0], a.bg[1], a.bg[2]);
+    const int aa = a.anti_aliasing;
+    const int total = a.passes * (aa ? 4 : 1);
+    const int max_depth = a.max_depth;
+    const uint32_t pixel = (uint32_t)(px.y * a.width + px.x);
+
+    f3 E[MAX_DEPTH_CAP], Wt[MAX_DEPTH_CAP];     // per-bounce explicit term and continuation weight (local memory)
+    f3 color = bg;
+    f3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f);
+    float prev_pdf = 1.0f;
+    bool  prev_spec = true;
+    int   s = 0, depth = 0;
+    bool  need_new = true;
+
+    for (;;) {
+      if (need_new) {
+        if (s == total) break;
+        const int sub = aa ? (s & 3) : -1;
+        o = ld3(g_scn.cam_pos);
+        d = eye_ray_dir(a, px.x, px.y, sub);
+        depth = 0; prev_pdf = 1.0f; prev_spec = true; need_new = false;      // StartSample, materials.ads:25
+        if (sub <= 0) color = bg;                                             // integrators.adb:42
+      }
+
+      DHit h;
+      find_closest_hit(o, d, h, nmesh);
+      nrays++;
+
+      f3   Lterm = mk3(0.f, 0.f, 0.f);
+      bool terminal = false;
+      if (!h.is_hit) {
+        terminal = true;                                                      // integrators.adb:98,151,218
+      } else {
+        const DMaterial& m = g_scn.mats[h.mat];
+        if (m.type == MAT_LIGHT) {
+          terminal = true;
+          if (RT == GCORE_PT_SHADOW) {
+            Lterm = mk3(0.f, 0.f, 0.f);                                       // :155-157
+          } else if (dot(neg(d), h.normal) < 0.0f) {
+            Lterm = mk3(0.f, 0.f, 0.f);                                       // :103, :224
+          } else {
+            f3 emit = (m.light < 0) ? mk3(0.f, 0.f, 0.f) : ld3(g_scn.l_intensity);   // materials.adb:147-156
+            if (RT == GCORE_PT_STUPID) Lterm = emit;                          // :106
+            else {                                                            // :230-243
+              float lgtPdf = light_eval_pdf(o, d, h.t);
+              float bsdfPdf = prev_pdf;
+              float misWeight = prev_spec ? 1.0f : (bsdfPdf * bsdfPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf));
+              Lterm = emit * misWeight;
+            }
+          }
+        } else {
+          nbounce++;
+          const BounceRand br = bounce_rand(a.seed, pixel, (uint32_t)(a.first_sample + s), (uint32_t)depth);
+          const f3 hpos = mk3(o.x + h.t * d.x, o.y + h.t * d.y, o.z + h.t * d.z);
+          f3 explicitColor = mk3(0.f, 0.f, 0.f);
+          if (RT != GCORE_PT_STUPID) {                                        // :161-178 / :251-287
+            LightSample ls = light_sample(br.u0, br.u1, hpos);
+            f3 sdir = normalize(ls.pos - hpos);
+            bool shadowed = compute_shadow(hpos, ls.pos, nmesh);
+            nrays++;
+            if (!shadowed) {
+              f3 bxdfVal; float bsdfPdf;
+              mat_eval(m, sdir, neg(d), h.normal, bxdfVal, bsdfPdf);
+              float cosTheta1 = max2(dot(sdir, h.normal), 0.0f);
+              if (RT == GCORE_PT_SHADOW) {
+                explicitColor = ls.intensity * (cosTheta1 * bxdfVal) * (1.0f / max2(ls.pdf, 1.0e-20f));
+              } else {
+                float lgtPdf = ls.pdf;
+                float misWeight = lgtPdf * lgtPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf);
+                explicitColor = ls.intensity * (1.0f / max2(lgtPdf, 1.0e-20f)) * (cosTheta1 * bxdfVal) * misWeight;
+              }
+            }
+          }
+          MatSampleD ms = mat_sample(m, br.u2, br.u3, d, h.normal);           // :116,183,291
+          f3 bxdfVal = ms.color * (1.0f / max2(ms.pdf, 1.0e-20f));
+          float cosTheta = dot(ms.direction, h.normal);
+          E[depth]  = explicitColor;
+          Wt[depth] = fabsf(cosTheta) * bxdfVal;
+          depth++;
+          f3 off = (sign_ada(cosTheta) * h.normal) * 1.0e-5f;                 // :122,189,297
+          o = hpos + off;
+          d = ms.direction;
+          prev_pdf = ms.pdf; prev_spec = ms.pureSpecular;
+          if (depth == max_depth) terminal = true;                            // recursion_level = 0 -> (0,0,0)
+        }
+      }
+
+      if (terminal) {
+        f3 L = Lterm;                                                         // unwind the recursion: :124,191,299
+        for (int k = depth - 1; k >= 0; k--) {
+          if (RT == GCORE_PT_STUPID) L = Wt[k] * L;
+          else L = E[k] + Wt[k] * L;
+        }
+        if (aa) {
+          color = color + L;                                                  // :47
+          if ((s & 3) == 3) acc = color + acc;                                // :51
+        } else {
+          acc = L + acc;                                                      // :60-63
+        }
+        s++;
+        need_new = true;
+      }
+    }
+    a.accum[slot] = make_float4(acc.x, acc.y, acc.z, acc4.w);
+  }
+  // statistics: one atomic per warp and counter
+  unsigned int total_rays = __reduce_add_sync(0xffffffffu, nrays);
+  unsigned int total_mesh = __reduce_add_sync(0xffffffffu, nmesh);
+  unsigned int total_bnc  = __reduce_add_sync(0xffffffffu, nbounce);
+  if ((threadIdx.x & 31) == 0 && total_rays) {
+    atomicAdd(&a.counters[0], (unsigned long long)total_rays);
+    atomicAdd(&a.counters[1], (unsigned long long)total_mesh);
+    atomicAdd(&a.counters[2], (unsigned long long)total_bnc);
+  }
+}
+
+__global__ void __launch_bounds__(RENDER_BLOCK) debug_kernel(const __grid_constant__ gcore_dev::RenderArgs a) {
+  const int slot = blockIdx.x * RENDER_BLOCK + threadIdx.x;
+  unsigned int nrays = 0;
+  const PixelId px = slot_to_pixel(a, slot < a.nslots ? slot : 0, a.rank);
+  if (slot < a.nslots && px.active) {
+    DHit h;
+    unsigned int nmesh = 0;
+    find_closest_hit(ld3(g_scn.cam_pos), eye_ray_dir(a, px.x, px.y, -1), h, nmesh);
+    nrays = 1;
+    float3 c = make_float3(0.f, 0.f, 0.f);
+    if (h.is_hit) {                                                           // palette, ray_tracer.adb:210-211
+      switch (h.matId % 8) {
+        case 0: c = make_float3(0.5f, 0.0f, 0.0f); break;
+        case 1: c = make_float3(0.0f, 0.5f, 0.0f); break;
+        case 2: c = make_float3(0.0f, 0.0f, 0.5f); break;
+        case 3: c = make_float3(0.5f, 0.5f, 0.5f); break;
+        case 4: c = make_float3(0.5f, 0.5f, 0.0f); break;
+        case 5: c = make_float3(0.5f, 0.0f, 0.5f); break;
+        case 6: c = make_float3(0.0f, 0.5f, 0.5f); break;
+        default: c = make_float3(0.75f, 0.75f, 0.75f); break;
+      }
+    }
+    a.accum[slot] = make_float4(c.x, c.y, c.z, 0.f);
+  }
+  unsigned int total_rays = __reduce_add_sync(0xffffffffu, nrays);
+  if ((threadIdx.x & 31) == 0 && total_rays) atomicAdd(&a.counters[0], (unsigned long long)total_rays);
+}
+
+__global__ void __launch_bounds__(RENDER_BLOCK) primary_kernel(const __grid_constant__ gcore_dev::RenderArgs a, gcore_hit* __restrict__ hits) {
+  const int slot = blockIdx.x * RENDER_BLOCK + threadIdx.x;
+  if (slot >= a.nslots) return;
+  const PixelId px = slot_to_pixel(a, slot, a.rank);
+  if (!px.active) return;
+  DHit h;
+  unsigned int nmesh = 0;
+  find_closest_hit(ld3(g_scn.cam_pos), eye_ray_dir(a, px.x, px.y, -1), h, nmesh);
+  store_hit(&hits[(size_t)px.y * a.width + px.x], h);
+}
+
+__global__ void __launch_bounds__(RENDER_BLOCK) closest_kernel(int n, const gcore_ray* __restrict__ rays, gcore_hit* __restrict__ hits) {
+  const int i = blockIdx.x * RENDER_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  DHit h;
+  unsigned int nmesh = 0;
+  find_closest_hit(ld3(rays[i].origin), ld3(rays[i].direction), h, nmesh);
+  store_hit(&hits[i], h);
+}
+
+__global__ void __launch_bounds__(RENDER_BLOCK) bvh_batch_kernel(int n, const gcore_ray* __restrict__ rays, float t_near, float t_far,
+                                                                 gcore_HitCpp* __restrict__ hits, int* __restrict__ found) {
+  const int i = blockIdx.x * RENDER_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  int prim; float t, u, v;
+  bvh_closest(g_scn.bvh_legacy, ld3(rays[i].origin), ld3(rays[i].direction), t_near, t_far, prim, t, u, v);
+  found[i] = (prim >= 0) ? 1 : 0;
+  if (prim >= 0) {
+    gcore_HitCpp hc;
+    hc.primIndex = prim; hc.geomIndex = 0; hc.instIndex = 0; hc.t = t;
+    hc.normal[0] = 0.f; hc.normal[1] = 0.f; hc.normal[2] = 0.f;
+    hc.texCoord[0] = v; hc.texCoord[1] = u;                 // reference v weighs B, u weighs C (geometry.adb:245-246, 301)
+    hits[i] = hc;
+  }
+}
+
+// Ada float -> Unsigned_32 conversion rounds to nearest, ties away from zero (ray_tracer.adb:51-53)
+__device__ __forceinline__ uint32_t to_u32_round(float v) {
+  float f = floorf(v);
+  float dlt = v - f;
+  if (dlt >= 0.5f) f = f + 1.0f;
+  if (!(f > 0.0f)) return 0u;
+  return (uint32_t)f;
+}
+
+__global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ gcore_dev::RenderArgs a, const float4* __restrict__ all,
+                                                      int gathered, int spp, float4* __restrict__ hdr4, uint32_t* __restrict__ ldr) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= a.width || y >= a.height) return;
+  int rank, slot;
+  pixel_to_slot(a, x, y, rank, slot);
+  const float4 v = gathered ? all[(size_t)rank * a.nslots + slot] : all[slot];
+  const size_t o = (size_t)y * a.width + x;
+  if (hdr4) hdr4[o] = make_float4(v.x, v.y, v.z, (float)spp);
+  if (ldr) {
+    float normC = 1.0f / (float)spp;                                          // ray_tracer.adb:281
+    float r = sqrtf(normC * v.x), g = sqrtf(normC * v.y), b = sqrtf(normC * v.z);   // ** (1.0/g_gamma) with g_gamma = 2.0
+    r = min2(r, 1.0f); g = min2(g, 1.0f); b = min2(b, 1.0f);                  // ToneMapping :19-38
+    ldr[o] = to_u32_round(r * 255.0f) | (to_u32_round(g * 255.0f) << 8) | (to_u32_round(b * 255.0f) << 16);
+  }
+}
+
+}  // namespace
+
+namespace gcore_dev {
+
+cudaError_t upload_scene(const art::DeviceScene* host_copy, cudaStream_t s) {
+  return cudaMemcpyToSymbolAsync(g_scn, host_copy, sizeof(art::DeviceScene), 0, cudaMemcpyHostToDevice, s);
+}
+
+static inline int blocks_for(int n, int b) { return (n + b - 1) / b; }
+
+cudaError_t launch_render(int render_type, const RenderArgs& a, cudaStream_t s) {
+  if (a.nslots <= 0) return cudaSuccess;
+  dim3 g(blocks_for(a.nslots, RENDER_BLOCK)), b(RENDER_BLOCK);
+  switch (render_type) {
+    case GCORE_PT_STUPID: render_kernel<GCORE_PT_STUPID><<<g, b, 0, s>>>(a); break;
+    case GCORE_PT_SHADOW: render_kernel<GCORE_PT_SHADOW><<<g, b, 0, s>>>(a); break;
+    case GCORE_PT_MIS:    render_kernel<GCORE_PT_MIS><<<g, b, 0, s>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_debug(const RenderArgs& a, cudaStream_t s) {
+  if (a.nslots <= 0) return cudaSuccess;
+  debug_kernel<<<blocks_for(a.nslots, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_primary_hits(const RenderArgs& a, gcore_hit* d_hits, cudaStream_t s) {
+  if (a.nslots <= 0) return cudaSuccess;
+  primary_kernel<<<blocks_for(a.nslots, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(a, d_hits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_closest_batch(int n, const gcore_ray* d_rays, gcore_hit* d_hits, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  closest_kernel<<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, d_hits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bvh_batch(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  bvh_batch_kernel<<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, d_hits, d_found);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resolve(const RenderArgs& a, int spp, float4* d_hdr4, uint32_t* d_ldr, cudaStream_t s) {
+  dim3 g(blocks_for(a.width, 32), blocks_for(a.height, 8)), b(256);
+  resolve_kernel<<<g, b, 0, s>>>(a, a.accum, 0, spp, d_hdr4, d_ldr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resolve_gathered(const RenderArgs& a, const float4* d_all, int spp, float4* d_hdr4, uint32_t* d_ldr, cudaStream_t s) {
+  dim3 g(blocks_for(a.width, 32), blocks_for(a.height, 8)), b(256);
+  resolve_kernel<<<g, b, 0, s>>>(a, d_all, 1, spp, d_hdr4, d_ldr);
+  return cudaGetLastError();
+}
+
+int render_kernel_regs(int render_type) {
+  cudaFuncAttributes at;
+  cudaError_t e;
+  switch (render_type) {
+    case GCORE_PT_STUPID: e = cudaFuncGetAttributes(&at, render_kernel<GCORE_PT_STUPID>); break;
+    case GCORE_PT_SHADOW: e = cudaFuncGetAttributes(&at, render_kernel<GCORE_PT_SHADOW>); break;
+    default:              e = cudaFuncGetAttributes(&at, render_kernel<GCORE_PT_MIS>); break;
+  }
+  if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+  return at.numRegs;
+}
+
+}  // namespace gcore_dev

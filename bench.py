@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the render hot path (see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload C4_1024|C2|C3|C4|C1]
+
+One "step" = one Render_Pass of the hot path (ray generation, scene queries, NEE + shadow rays, BSDF sampling, per-pixel
+accumulation) over the whole image: `units` DoPass units of 4 fixed sub-pixel samples each.  The default workload is the
+one BASELINE.json's metric is quoted on: pyramid2 Cornell scene, PT_MIS, depth 8, 1024x1024, 256 spp per step.
+
+Printed JSON line (rank 0):
+  value   Mrays/s, whole job, scene and accumulators resident in HBM, device-timed (CUDA events on the library's stream,
+          max over ranks); N>1: image tiles split round-robin over the ranks, slot-major accumulators gathered to rank 0
+          with NCCL and resolved there, inside the timed region.
+  e2e     same metric through the reference-facing C-ABI call gcore_render() with HOST buffers: scene description
+          re-sent (host->device) and the resolved frame read back (device->host) every step.
+  roofline / cpu_baseline as specified in the task; the CPU leg times the oracle (a C++ restatement of the Ada
+          renderer; neither GNAT nor Embree exists here) on the host cores with all threads.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+WORKLOADS = {
+    # name: (width, height, render_type, aa, max_depth, units per step, description)
+    "C4_1024": (1024, 1024, "PT_MIS", 1, 8, 64, "pyramid2 Cornell scene, PT_MIS depth 8, AA 4 fixed sub-pixels, 1024x1024, 256 spp per step"),
+    "C1": (1024, 768, "PT_MIS", 1, 8, 28, "reference default: 1024x768 PT_MIS depth 8, 28 units (112 spp) per Render_Pass"),
+    "C2": (1024, 1024, "PT_STUPID", 0, 1, 1, "primary rays only, 1024x1024, 1 spp (pixel centres)"),
+    "C3": (1024, 1024, "PT_SHADOW", 1, 1, 4, "direct lighting with shadow rays, 1024x1024, 16 spp"),
+    "C4": (2048, 2048, "PT_MIS", 1, 8, 64, "multi-bounce PT_MIS depth 8, 2048x2048, 256 spp per step"),
+}
+SEED = 0x5EED0004
+FLOP_QUERY_MESH, FLOP_QUERY_NOMESH, FLOP_BOUNCE = 564.0, 140.0, 200.0      # SURVEY 8d, counted from the reference source
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe's clocks line)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        self.p = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill(); out = ""
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_run(width, height, rtype, aa, depth, units, threads, seed=SEED, first_sample=0):
+    ob = ge.load_oracle()
+    global _ORACLE_SCENE
+    try:
+        _ORACLE_SCENE
+    except NameError:
+        _ORACLE_SCENE = ob.OracleScene()
+    p = ob.make_params(width, height, getattr(ob, rtype), aa=aa, max_depth=depth, passes=units, seed=seed,
+                       first_sample=first_sample, threads=threads)
+    t0 = time.perf_counter()
+    _, rays = _ORACLE_SCENE.render(p)
+    return rays, time.perf_counter() - t0
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (kind "port": the Ada sources
+    cannot be compiled here), all host threads, a bounded sample of the workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    width, height, rtype, aa, depth, units, desc = wl
+    cores = host_cores()
+    sample_units = 1                                    # 4 spp of the full image per step
+    for _ in range(max(args.warmup, 1)):
+        oracle_run(width, height, rtype, aa, depth, sample_units, cores)
+    rays_tot, t_tot = 0, 0.0
+    for k in range(args.steps):
+        rays, dt = oracle_run(width, height, rtype, aa, depth, sample_units, cores, first_sample=4 * k)
+        rays_tot += rays; t_tot += dt
+    v = rays_tot / t_tot / 1e6
+    sample = "%dx%d %s depth %d, %d unit(s) (%d spp) of the full image per step" % (width, height, rtype, depth, sample_units,
+                                                                                   sample_units * (4 if aa else 1))
+    line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "sample": sample, "note": "CPU oracle port of the Ada renderer (C++ -O2, no FMA); not GNAT, not Embree: neither exists in this image"},
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C4_1024", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+    width, height, rtype, aa, depth, units, desc = wl
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the render core has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pkg = ge.load_package()
+    L = pkg.lib()
+    pkg.set_device(local_rank)
+    pkg.set_partition(rank, world)
+    scene = pkg.Scene(); scene.Init()
+    rt = pkg.Ray_Tracer()
+    rt.Threads_Num = units; rt.Anti_Aliasing_On = bool(aa); rt.Max_Trace_Depth = depth; rt.seed = SEED
+    rt.Init_Render(getattr(pkg, rtype))
+    rt.Resize_Viewport(width, height)
+
+    # torch sees the library's stream: events, NCCL and the L2 flush are ordered with the kernels
+    stream = torch.cuda.ExternalStream(pkg.stream_handle(), device=torch.device("cuda", local_rank))
+    npx = width * height
+    acc_ptr, nslots = pkg.accum_device_ptr()
+    with torch.cuda.stream(stream):
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
+        d_ldr = torch.empty(npx, dtype=torch.int32, device="cuda")
+        local = torch.empty(nslots * 4, dtype=torch.float32, device="cuda")
+        gathered = [torch.empty(nslots * 4, dtype=torch.float32, device="cuda") for _ in range(world)] if (world > 1 and rank == 0) else None
+        allb = torch.empty(world * nslots * 4, dtype=torch.float32, device="cuda") if (world > 1 and rank == 0) else None
+    cudart = C.CDLL("libcudart.so")
+    cudart.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+
+    def device_step():
+        """one Render_Pass, everything resident on the device"""
+        rc = L.gcore_render_units(units, None)
+        if rc != 0:
+            raise RuntimeError(pkg.last_error())
+        if world == 1:
+            L.gcore_resolve_device(None, C.c_void_p(d_ldr.data_ptr()))
+            return 2
+        with torch.cuda.stream(stream):
+            cudart.cudaMemcpyAsync(C.c_void_p(local.data_ptr()), C.c_void_p(acc_ptr), C.c_size_t(nslots * 16), 3, C.c_void_p(stream.cuda_stream))
+            dist.gather(local, gathered, dst=0)
+            if rank == 0:
+                torch.cat(gathered, out=allb)
+                L.gcore_resolve_gathered_device(C.c_void_p(allb.data_ptr()), rt.GetSPP(), None, C.c_void_p(d_ldr.data_ptr()))
+        return 2 if rank == 0 else 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- value: device-resident, CUDA events
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            flush.fill_(1); device_step()
+    barrier()
+    c0 = pkg.get_counters()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    barrier()
+    wall0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for k in range(args.steps):
+            flush.fill_(k & 255)                         # L2 flush between timed iterations (outside the events)
+            ev[k][0].record(stream)
+            rc = L.gcore_render_units(units, None)
+            ev[k][1].record(stream)                      # render kernel alone: ev0..ev1
+            if world == 1:
+                L.gcore_resolve_device(None, C.c_void_p(d_ldr.data_ptr())); launches += 2
+            else:
+                cudart.cudaMemcpyAsync(C.c_void_p(local.data_ptr()), C.c_void_p(acc_ptr), C.c_size_t(nslots * 16), 3, C.c_void_p(stream.cuda_stream))
+                dist.gather(local, gathered, dst=0)
+                if rank == 0:
+                    torch.cat(gathered, out=allb)
+                    L.gcore_resolve_gathered_device(C.c_void_p(allb.data_ptr()), rt.GetSPP(), None, C.c_void_p(d_ldr.data_ptr()))
+                launches += 2 if rank == 0 else 1
+            ev[k][2].record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler else None
+    c1 = pkg.get_counters()
+    step_ms = sum(a.elapsed_time(c) for a, _, c in ev)
+    kern_ms = sum(a.elapsed_time(b) for a, b, _ in ev)
+    rays_local, mesh_local, bounce_local = (c1[i] - c0[i] for i in range(3))
+    t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([rays_local, mesh_local, bounce_local, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    step_ms, kern_ms = float(t[0]), float(t[1])
+    rays, mesh_q, bounces, launches_all = (float(x) for x in cnt)
+    value = rays / (step_ms * 1e-3) / 1e6
+
+    # ---------------------------------------------------------------- e2e: C-ABI call with host buffers
+    cfg = rt._cfg()
+    ldr_host = torch.empty(npx, dtype=torch.int32).pin_memory()
+    d = ge.load_package()
+    desc_scene = None
+    h2d = d2h = 0
+    e2e_rays = 0.0
+    e2e_s = 0.0
+    if world == 1:
+        st = pkg.RenderStats()
+        h2d = 12 * 1024                                 # sizeof(DeviceScene): the scene block is re-sent each step
+        d2h = 4 * npx + 24
+        for k in range(2 + args.steps):
+            barrier()
+            t0 = time.perf_counter()
+            scene.Init()                                # scene description from host data -> device (dirty => re-upload)
+            rc = L.gcore_render(C.byref(cfg), width, height, units, None, C.c_void_p(ldr_host.data_ptr()), C.byref(st))
+            if rc != 0:
+                raise RuntimeError(pkg.last_error())
+            dt = time.perf_counter() - t0
+            if k >= 2:
+                e2e_s += dt; e2e_rays += st.rays
+    else:
+        # N > 1: every rank renders its tiles from a fresh viewport, accumulators gathered with NCCL, rank 0 resolves and
+        # copies the frame to pinned host memory
+        h2d = 12 * 1024; d2h = 4 * npx
+        for k in range(2 + args.steps):
+            barrier()
+            t0 = time.perf_counter()
+            scene.Init()
+            rt.Resize_Viewport(width, height)
+            cc0 = pkg.get_counters()
+            with torch.cuda.stream(stream):
+                L.gcore_render_units(units, None)
+                cudart.cudaMemcpyAsync(C.c_void_p(local.data_ptr()), C.c_void_p(pkg.accum_device_ptr()[0]), C.c_size_t(nslots * 16), 3, C.c_void_p(stream.cuda_stream))
+                dist.gather(local, gathered, dst=0)
+                if rank == 0:
+                    torch.cat(gathered, out=allb)
+                    L.gcore_resolve_gathered_device(C.c_void_p(allb.data_ptr()), rt.GetSPP(), None, C.c_void_p(d_ldr.data_ptr()))
+                    ldr_host.copy_(d_ldr, non_blocking=True)
+            barrier()
+            dt = time.perf_counter() - t0
+            cc1 = pkg.get_counters()
+            r = torch.tensor([cc1[0] - cc0[0], dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(r[0:1], op=dist.ReduceOp.SUM); dist.all_reduce(r[1:2], op=dist.ReduceOp.MAX)
+            if k >= 2:
+                e2e_rays += float(r[0]); e2e_s += float(r[1])
+    e2e_value = e2e_rays / e2e_s / 1e6
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        # algorithmic FP32 work of the dominant kernel (render_kernel): per launch, this rank's share
+        flop = mesh_q * FLOP_QUERY_MESH + (rays - mesh_q) * FLOP_QUERY_NOMESH + bounces * FLOP_BOUNCE
+        flop_per_launch = flop / args.steps / world
+        kern_s = kern_ms * 1e-3 / args.steps
+        achieved = flop_per_launch / kern_s / 1e12
+        peak = sms * 128 * sm_mhz * 1e6 / 1e12          # one non-FMA FP32 op per lane per cycle at the clock seen under load
+        roofline = {"bound": "fp32_issue", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": None,
+                    "note": "analytic scene lives in constant memory: HBM traffic is the 16 B/pixel accumulator only, so the bound "
+                            "is FP32 instruction issue (SURVEY 8d), not hbm/tensor; peak = SMs x 128 lanes x SM clock sampled during "
+                            "the run (no measured FP32 peak in MEASURED_PEAKS.json; -fmad=false => 1 flop per lane-instruction)",
+                    "kernel": "render_kernel<PT_MIS>", "kernel_ms_per_launch": kern_ms / args.steps,
+                    "hbm_view": {"achieved_GBs": 2 * 16.0 * npx / world / kern_s / 1e9, "peak_GBs": peaks.get("hbm_gbs", 6650.0),
+                                 "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"}}
+        cpu_baseline = None
+        if not args.no_cpu_baseline and world == 1:
+            cores = host_cores()
+            r1, t1 = oracle_run(width, height, rtype, aa, depth, 1, cores)          # also warms the page cache
+            n_units = int(min(max(round(12.0 / max(t1, 1e-3)), 1), units))
+            r2, t2 = oracle_run(width, height, rtype, aa, depth, n_units, cores)
+            cpu_baseline = {"value": r2 / t2 / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                            "sample": "%d of the step's %d units (%d spp) of the full %dx%d image, %.1f s" % (n_units, units, n_units * (4 if aa else 1), width, height, t2)}
+        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "scene": "scene.adb Cornell box + 2 spheres + sphere light + data/pyramid2.vsgf",
+                           "seed": SEED, "parallelism": "tiles32x32_rr%d" % world,
+                           "l2": "256 MiB buffer written between timed steps (outside the per-step CUDA events); inputs are < L2",
+                           "numerics": "bit-exact mode (-fmad=false, IEEE div/sqrt), identical to the CPU oracle"},
+                "msamples_per_s": (npx * units * (4 if aa else 1)) / (step_ms / args.steps * 1e-3) / 1e6,
+                "rays_per_step": rays / args.steps, "wall_s": wall,
+                "clocks": clocks, "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                          "ms_per_step": 1e3 * e2e_s / args.steps},
+                "gpu_launches": int(launches_all), "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
