@@ -249,17 +249,4 @@ ART_D void mat_eval(const DMaterial& mat, f3 l, f3 v, f3 n, f3& bxdf, float& pdf
   }
 }
 
-// ---------------------------------------------------------------- ray_tracer.adb:100-132 Compute_Shadow
-ART_D bool compute_shadow(f3 hit_pos, f3 lpos, unsigned int& mesh_queries) {
-  float epsilon = max3(fabsf(hit_pos.x), fabsf(hit_pos.y), fabsf(hit_pos.z)) * 0.000000001f;
-  epsilon = max2(epsilon, 1.0e-30f);
-  f3 sdir = normalize(lpos - hit_pos);
-  f3 sorg = hit_pos + sdir * epsilon;
-  DHit h;
-  find_closest_hit(sorg, sdir, h, mesh_queries);
-  float maxDist  = length(hit_pos - lpos);
-  float epsilon2 = max2(maxDist * 0.000001f, 1.0e-30f);
-  return h.is_hit && (h.t < maxDist - epsilon2 && h.t > 10.0f * epsilon);
-}
-
 }  // namespace art

@@ -38,7 +38,8 @@ struct DeviceScene {
   float fl_min[3], fl_max[3];      // FlatLight boxMin/boxMax (geometry.ads:38-44)
   float l_boxMin[3], l_boxMax[3], l_normal[3], l_center[3], l_radius, l_intensity[3], l_area;
   float cam_pos[3], cam_m[12];
-  float mesh_bmin[3], mesh_bmax[3];
+  float mesh_bmin[3], mesh_bmax[3];            // the reference's bbox (folded from zeros, geometry.adb:593-603)
+  float mesh_tight_min[3], mesh_tight_max[3];  // padded bounds of the vertices: a pure culling device
   DMaterial mats[GC_MAX_MATERIALS];
   float triA[GC_MAX_BF_TRIS][3], triE1[GC_MAX_BF_TRIS][3], triE2[GC_MAX_BF_TRIS][3];
   float triN[GC_MAX_BF_TRIS][9];   // nA, nB, nC

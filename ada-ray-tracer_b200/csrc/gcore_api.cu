@@ -209,6 +209,15 @@ int install_mesh(int mesh_mode) {
   for (int k = 0; k < 3; k++) { s.hs.mesh_bmin[k] = s.mesh_bbox[k]; s.hs.mesh_bmax[k] = s.mesh_bbox[3 + k]; }
   s.scene_dirty = true;
   if (ntris == 0) return 0;
+  {  // padded tight bounds of the vertices (culling only; 1e-4 relative + 1e-5 absolute >> rounding error of the triangle test)
+    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (size_t i = 0; i + 2 < s.mesh_pos.size(); i += 3)
+      for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], s.mesh_pos[i + k]); mx[k] = fmaxf(mx[k], s.mesh_pos[i + k]); }
+    for (int k = 0; k < 3; k++) {
+      float pad = fmaxf(fabsf(mn[k]), fabsf(mx[k])) * 1.0e-4f + 1.0e-5f;
+      s.hs.mesh_tight_min[k] = mn[k] - pad; s.hs.mesh_tight_max[k] = mx[k] + pad;
+    }
+  }
   auto P = [&](int v, int k) { return s.mesh_pos[3 * (size_t)v + k]; };
   auto N = [&](int v, int k) { return s.mesh_nrm[3 * (size_t)v + k]; };
   if (ntris <= GC_MAX_BF_TRIS) {
@@ -270,11 +279,11 @@ int render_units_locked(int units, gcore_render_stats* stats) {
   uint64_t samples = 0;
   const uint64_t pixels = (uint64_t)s.width * s.height;
   if (s.cfg.render_type == GCORE_RT_DEBUG || s.cfg.render_type == GCORE_RT_WHITTED) {
-    CU(gcore_dev::launch_debug(a, s.stream), "debug_kernel");           // Debug_Ray_Tracing overwrites the buffer, spp stays
+    CU(gcore_dev::launch_debug(s.hs.mesh_kind, a, s.stream), "debug_kernel");           // Debug_Ray_Tracing overwrites the buffer, spp stays
     launches = 1; samples = pixels;
     if (s.spp == 0) s.spp = 1;
   } else if (units > 0) {
-    CU(gcore_dev::launch_render(s.cfg.render_type, a, s.stream), "render_kernel");
+    CU(gcore_dev::launch_render(s.cfg.render_type, s.hs.mesh_kind, a, s.stream), "render_kernel");
     launches = 1;
     const int per = s.cfg.anti_aliasing ? 4 : 1;
     s.spp += units * per;                                                // ray_tracer.adb:168-176
@@ -670,7 +679,7 @@ int gcore_closest_hit_batch(int n, const gcore_ray* rays, gcore_hit* hits) {
     cudaFree(d_r); cudaFree(d_h); return fail_cuda(e, "cudaMalloc batch");
   }
   cudaMemcpyAsync(d_r, rays, sizeof(gcore_ray) * (size_t)n, cudaMemcpyHostToDevice, s.stream);
-  e = gcore_dev::launch_closest_batch(n, d_r, d_h, s.stream);
+  e = gcore_dev::launch_closest_batch(s.hs.mesh_kind, n, d_r, d_h, s.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_h, sizeof(gcore_hit) * (size_t)n, cudaMemcpyDeviceToHost, s.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
   cudaFree(d_r); cudaFree(d_h);
@@ -765,7 +774,7 @@ int gcore_primary_hits(int width, int height, gcore_hit* hits) {
   gcore_hit* d_h = nullptr;
   size_t px = (size_t)width * height;
   CU(cudaMalloc(&d_h, sizeof(gcore_hit) * px), "cudaMalloc hits");
-  cudaError_t e = gcore_dev::launch_primary_hits(a, d_h, s.stream);
+  cudaError_t e = gcore_dev::launch_primary_hits(s.hs.mesh_kind, a, d_h, s.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_h, sizeof(gcore_hit) * px, cudaMemcpyDeviceToHost, s.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
   cudaFree(d_h);

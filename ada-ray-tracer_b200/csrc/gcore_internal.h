@@ -29,12 +29,12 @@ struct RenderArgs {
 
 cudaError_t upload_scene(const art::DeviceScene* host_copy, cudaStream_t s);
 // render_type: GCORE_PT_STUPID / GCORE_PT_SHADOW / GCORE_PT_MIS
-cudaError_t launch_render(int render_type, const RenderArgs& a, cudaStream_t s);
+cudaError_t launch_render(int render_type, int mesh_kind, const RenderArgs& a, cudaStream_t s);   // mesh_kind: DeviceScene::mesh_kind
 // RT_DEBUG / RT_WHITTED: palette of the primary hit written into accum (ray_tracer.adb:208-238)
-cudaError_t launch_debug(const RenderArgs& a, cudaStream_t s);
+cudaError_t launch_debug(int mesh_kind, const RenderArgs& a, cudaStream_t s);
 // primary hits, row-major hits[y*W+x]
-cudaError_t launch_primary_hits(const RenderArgs& a, gcore_hit* d_hits, cudaStream_t s);
-cudaError_t launch_closest_batch(int n, const gcore_ray* d_rays, gcore_hit* d_hits, cudaStream_t s);
+cudaError_t launch_primary_hits(int mesh_kind, const RenderArgs& a, gcore_hit* d_hits, cudaStream_t s);
+cudaError_t launch_closest_batch(int mesh_kind, int n, const gcore_ray* d_rays, gcore_hit* d_hits, cudaStream_t s);
 // pure triangle query on the committed LBVH (legacy gcore_closest_hit semantics)
 cudaError_t launch_bvh_batch(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, cudaStream_t s);
 // slot-major accumulator -> row-major outputs; either pointer may be null.

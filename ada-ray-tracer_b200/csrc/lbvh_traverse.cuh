@@ -34,6 +34,7 @@ ART_D bool slab_hit(float bminx, float bminy, float bminz, float bmaxx, float bm
 
 ART_D void bvh_leaf_test(const BvhView& bv, int first, int count, f3 o, f3 d, float t_min,
                          float& best_t, int& best_prim, float& best_u, float& best_v) {
+#pragma unroll 1
   for (int s = first; s < first + count; s++) {
     float4 a  = __ldg(&bv.tris[3 * s + 0]);
     float4 e1 = __ldg(&bv.tris[3 * s + 1]);
@@ -48,13 +49,12 @@ ART_D void bvh_leaf_test(const BvhView& bv, int first, int count, f3 o, f3 d, fl
 }
 
 // closest hit; prim = -1 when nothing is hit inside (t_min, t_max)
-ART_D void bvh_closest(const BvhView& bv, f3 o, f3 d, float t_min, float t_max, int& prim_o, float& t_o, float& u_o, float& v_o) {
+ART_D void bvh_closest(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, float t_max, int& prim_o, float& t_o, float& u_o, float& v_o) {
   float best_t = t_max; int best_prim = -1; float best_u = 0.0f, best_v = 0.0f;
   if (bv.ntris > 0) {
     if (bv.root < 0) {
       bvh_leaf_test(bv, 0, bv.ntris, o, d, t_min, best_t, best_prim, best_u, best_v);
     } else {
-      f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
       int stack[LBVH_STACK];
       int sp = 0;
       int node = bv.root;

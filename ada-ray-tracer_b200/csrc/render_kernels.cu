@@ -4,10 +4,13 @@
 // to the reference arithmetic restated by the oracle.
 //
 // Kernels
-//   render_kernel<RT>   K1+K2+K4+K5+K6a  one thread per pixel slot; persistent per-pixel loop over all samples of the
-//                       call with path regeneration (a lane starts its next sample as soon as its path ends), fused
-//                       ray generation, scene query, NEE + shadow query, BSDF sampling, per-pass accumulation.
-//                       Replaces ray_tracer-integrators.adb:25-301, ray_tracer.adb:61-132.
+//   render_kernel<RT,MESHK>  K1+K2+K4+K5+K6a.  One thread per pixel slot, persistent over all samples of the call.  The
+//                       per-lane state machine issues exactly ONE scene query per loop iteration -- a camera/bounce ray
+//                       (phase BOUNCE) or the shadow ray of the previous hit (phase SHADOW) -- so all lanes of a warp
+//                       meet at the single inlined copy of find_closest_hit whatever their phase, bounce or sample
+//                       index (path regeneration: a lane starts its next sample as soon as its path ends).  Fused: ray
+//                       generation, scene query, light sampling + shadow test, BSDF eval/sample, MIS, recursion unwind,
+//                       per-pass accumulation.  Replaces ray_tracer-integrators.adb:25-301, ray_tracer.adb:61-132.
 //   debug_kernel        RT_DEBUG / RT_WHITTED palette render, ray_tracer.adb:208-238.
 //   primary_kernel      primary hit records (config C2).
 //   closest_kernel      Scene.Find_Closest_Hit for a batch of rays.
@@ -71,7 +74,9 @@ __device__ __forceinline__ void store_hit(gcore_hit* o, const DHit& h) {
   o->t = h.t; o->normal[0] = h.normal.x; o->normal[1] = h.normal.y; o->normal[2] = h.normal.z; o->tx = h.tx; o->ty = h.ty;
 }
 
-template <int RT>
+enum { PH_NEW = 0, PH_BOUNCE = 1, PH_SHADOW = 2 };
+
+template <int RT, int MESHK>
 __global__ void __launch_bounds__(RENDER_BLOCK) render_kernel(const __grid_constant__ gcore_dev::RenderArgs a) {
   const int slot = blockIdx.x * RENDER_BLOCK + threadIdx.x;
   unsigned int nrays = 0, nmesh = 0, nbounce = 0;
@@ -87,87 +92,117 @@ __global__ void __launch_bounds__(RENDER_BLOCK) render_kernel(const __grid_const
 
     f3 E[MAX_DEPTH_CAP], Wt[MAX_DEPTH_CAP];     // per-bounce explicit term and continuation weight (local memory)
     f3 color = bg;
-    f3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f);
+    f3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f);   // the ray of the next scene query
+    // surface state carried from the BOUNCE query to the SHADOW query of the same bounce
+    f3 hpos = o, hn = d, din = d;
+    int hmat = 0;
+    float ls_pdf = 1.0f, sh_thi = 0.0f, sh_tlo = 0.0f, r1 = 0.0f, r2 = 0.0f;
     float prev_pdf = 1.0f;
     bool  prev_spec = true;
     int   s = 0, depth = 0;
-    bool  need_new = true;
+    int   phase = PH_NEW;
 
     for (;;) {
-      if (need_new) {
+      if (phase == PH_NEW) {
         if (s == total) break;
         const int sub = aa ? (s & 3) : -1;
         o = ld3(g_scn.cam_pos);
         d = eye_ray_dir(a, px.x, px.y, sub);
-        depth = 0; prev_pdf = 1.0f; prev_spec = true; need_new = false;      // StartSample, materials.ads:25
+        depth = 0; prev_pdf = 1.0f; prev_spec = true;                         // StartSample, materials.ads:25
         if (sub <= 0) color = bg;                                             // integrators.adb:42
+        phase = PH_BOUNCE;
       }
 
       DHit h;
-      find_closest_hit(o, d, h, nmesh);
+      find_closest_hit<MESHK>(o, d, phase == PH_BOUNCE, h, nmesh);
       nrays++;
 
       f3   Lterm = mk3(0.f, 0.f, 0.f);
-      bool terminal = false;
-      if (!h.is_hit) {
-        terminal = true;                                                      // integrators.adb:98,151,218
-      } else {
-        const DMaterial& m = g_scn.mats[h.mat];
-        if (m.type == MAT_LIGHT) {
-          terminal = true;
-          if (RT == GCORE_PT_SHADOW) {
-            Lterm = mk3(0.f, 0.f, 0.f);                                       // :155-157
-          } else if (dot(neg(d), h.normal) < 0.0f) {
-            Lterm = mk3(0.f, 0.f, 0.f);                                       // :103, :224
-          } else {
-            f3 emit = (m.light < 0) ? mk3(0.f, 0.f, 0.f) : ld3(g_scn.l_intensity);   // materials.adb:147-156
-            if (RT == GCORE_PT_STUPID) Lterm = emit;                          // :106
-            else {                                                            // :230-243
-              float lgtPdf = light_eval_pdf(o, d, h.t);
-              float bsdfPdf = prev_pdf;
-              float misWeight = prev_spec ? 1.0f : (bsdfPdf * bsdfPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf));
-              Lterm = emit * misWeight;
-            }
-          }
+      f3   explicitColor = mk3(0.f, 0.f, 0.f);
+      bool terminal = false, do_bsdf = false;
+
+      if (phase == PH_BOUNCE) {
+        if (!h.is_hit) {
+          terminal = true;                                                    // integrators.adb:98,151,218
         } else {
-          nbounce++;
-          const BounceRand br = bounce_rand(a.seed, pixel, (uint32_t)(a.first_sample + s), (uint32_t)depth);
-          const f3 hpos = mk3(o.x + h.t * d.x, o.y + h.t * d.y, o.z + h.t * d.z);
-          f3 explicitColor = mk3(0.f, 0.f, 0.f);
-          if (RT != GCORE_PT_STUPID) {                                        // :161-178 / :251-287
-            LightSample ls = light_sample(br.u0, br.u1, hpos);
-            f3 sdir = normalize(ls.pos - hpos);
-            bool shadowed = compute_shadow(hpos, ls.pos, nmesh);
-            nrays++;
-            if (!shadowed) {
-              f3 bxdfVal; float bsdfPdf;
-              mat_eval(m, sdir, neg(d), h.normal, bxdfVal, bsdfPdf);
-              float cosTheta1 = max2(dot(sdir, h.normal), 0.0f);
-              if (RT == GCORE_PT_SHADOW) {
-                explicitColor = ls.intensity * (cosTheta1 * bxdfVal) * (1.0f / max2(ls.pdf, 1.0e-20f));
-              } else {
-                float lgtPdf = ls.pdf;
-                float misWeight = lgtPdf * lgtPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf);
-                explicitColor = ls.intensity * (1.0f / max2(lgtPdf, 1.0e-20f)) * (cosTheta1 * bxdfVal) * misWeight;
+          const int mtype = g_scn.mats[h.mat].type;
+          if (mtype == MAT_LIGHT) {
+            terminal = true;
+            if (RT == GCORE_PT_SHADOW) {
+              Lterm = mk3(0.f, 0.f, 0.f);                                     // :155-157
+            } else if (dot(neg(d), h.normal) < 0.0f) {
+              Lterm = mk3(0.f, 0.f, 0.f);                                     // :103, :224
+            } else {
+              f3 emit = (g_scn.mats[h.mat].light < 0) ? mk3(0.f, 0.f, 0.f) : ld3(g_scn.l_intensity);   // materials.adb:147-156
+              if (RT == GCORE_PT_STUPID) Lterm = emit;                        // :106
+              else {                                                          // :230-243
+                float lgtPdf = light_eval_pdf(o, d, h.t);
+                float bsdfPdf = prev_pdf;
+                float misWeight = prev_spec ? 1.0f : (bsdfPdf * bsdfPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf));
+                Lterm = emit * misWeight;
               }
             }
+          } else {
+            nbounce++;
+            const BounceRand br = bounce_rand(a.seed, pixel, (uint32_t)(a.first_sample + s), (uint32_t)depth);
+            hpos = mk3(o.x + h.t * d.x, o.y + h.t * d.y, o.z + h.t * d.z);
+            hn = h.normal; hmat = h.mat; din = d;
+            r1 = br.u2; r2 = br.u3;
+            if (RT == GCORE_PT_STUPID) {
+              do_bsdf = true;
+            } else {                                                          // :161-178 / :251-287
+              LightSample ls = light_sample(br.u0, br.u1, hpos);
+              ls_pdf = ls.pdf;
+              // Compute_Shadow (ray_tracer.adb:100-132): the shadow ray becomes the next query
+              float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
+              epsilon = max2(epsilon, 1.0e-30f);
+              f3 sdir = normalize(ls.pos - hpos);                             // == normalize(lsam.pos - hpos) of :165/:268
+              o = hpos + sdir * epsilon;
+              d = sdir;
+              float maxDist  = length(hpos - ls.pos);
+              float epsilon2 = max2(maxDist * 0.000001f, 1.0e-30f);
+              sh_thi = maxDist - epsilon2;
+              sh_tlo = 10.0f * epsilon;
+              phase = PH_SHADOW;
+            }
           }
-          MatSampleD ms = mat_sample(m, br.u2, br.u3, d, h.normal);           // :116,183,291
-          f3 bxdfVal = ms.color * (1.0f / max2(ms.pdf, 1.0e-20f));
-          float cosTheta = dot(ms.direction, h.normal);
-          E[depth]  = explicitColor;
-          Wt[depth] = fabsf(cosTheta) * bxdfVal;
-          depth++;
-          f3 off = (sign_ada(cosTheta) * h.normal) * 1.0e-5f;                 // :122,189,297
-          o = hpos + off;
-          d = ms.direction;
-          prev_pdf = ms.pdf; prev_spec = ms.pureSpecular;
-          if (depth == max_depth) terminal = true;                            // recursion_level = 0 -> (0,0,0)
         }
+      } else {                                                                // PH_SHADOW
+        const bool shadowed = h.is_hit && (h.t < sh_thi && h.t > sh_tlo);     // ray_tracer.adb:122
+        if (!shadowed) {
+          f3 bxdfVal; float bsdfPdf;
+          mat_eval(g_scn.mats[hmat], d, neg(din), hn, bxdfVal, bsdfPdf);
+          float cosTheta1 = max2(dot(d, hn), 0.0f);
+          f3 intensity = ld3(g_scn.l_intensity);
+          if (RT == GCORE_PT_SHADOW) {
+            explicitColor = intensity * (cosTheta1 * bxdfVal) * (1.0f / max2(ls_pdf, 1.0e-20f));
+          } else {
+            float lgtPdf = ls_pdf;
+            float misWeight = lgtPdf * lgtPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf);
+            explicitColor = intensity * (1.0f / max2(lgtPdf, 1.0e-20f)) * (cosTheta1 * bxdfVal) * misWeight;
+          }
+        }
+        do_bsdf = true;
+      }
+
+      if (do_bsdf) {                                                          // pick up next ray, :116,183,291
+        MatSampleD ms = mat_sample(g_scn.mats[hmat], r1, r2, din, hn);
+        f3 bxdfVal = ms.color * (1.0f / max2(ms.pdf, 1.0e-20f));
+        float cosTheta = dot(ms.direction, hn);
+        E[depth]  = explicitColor;
+        Wt[depth] = fabsf(cosTheta) * bxdfVal;
+        depth++;
+        f3 off = (sign_ada(cosTheta) * hn) * 1.0e-5f;                         // :122,189,297
+        o = hpos + off;
+        d = ms.direction;
+        prev_pdf = ms.pdf; prev_spec = ms.pureSpecular;
+        phase = PH_BOUNCE;
+        if (depth == max_depth) terminal = true;                              // recursion_level = 0 -> (0,0,0)
       }
 
       if (terminal) {
         f3 L = Lterm;                                                         // unwind the recursion: :124,191,299
+#pragma unroll 1
         for (int k = depth - 1; k >= 0; k--) {
           if (RT == GCORE_PT_STUPID) L = Wt[k] * L;
           else L = E[k] + Wt[k] * L;
@@ -179,7 +214,7 @@ __global__ void __launch_bounds__(RENDER_BLOCK) render_kernel(const __grid_const
           acc = L + acc;                                                      // :60-63
         }
         s++;
-        need_new = true;
+        phase = PH_NEW;
       }
     }
     a.accum[slot] = make_float4(acc.x, acc.y, acc.z, acc4.w);
@@ -195,6 +230,7 @@ __global__ void __launch_bounds__(RENDER_BLOCK) render_kernel(const __grid_const
   }
 }
 
+template <int MESHK>
 __global__ void __launch_bounds__(RENDER_BLOCK) debug_kernel(const __grid_constant__ gcore_dev::RenderArgs a) {
   const int slot = blockIdx.x * RENDER_BLOCK + threadIdx.x;
   unsigned int nrays = 0;
@@ -202,7 +238,7 @@ __global__ void __launch_bounds__(RENDER_BLOCK) debug_kernel(const __grid_consta
   if (slot < a.nslots && px.active) {
     DHit h;
     unsigned int nmesh = 0;
-    find_closest_hit(ld3(g_scn.cam_pos), eye_ray_dir(a, px.x, px.y, -1), h, nmesh);
+    find_closest_hit<MESHK>(ld3(g_scn.cam_pos), eye_ray_dir(a, px.x, px.y, -1), true, h, nmesh);
     nrays = 1;
     float3 c = make_float3(0.f, 0.f, 0.f);
     if (h.is_hit) {                                                           // palette, ray_tracer.adb:210-211
@@ -223,6 +259,7 @@ __global__ void __launch_bounds__(RENDER_BLOCK) debug_kernel(const __grid_consta
   if ((threadIdx.x & 31) == 0 && total_rays) atomicAdd(&a.counters[0], (unsigned long long)total_rays);
 }
 
+template <int MESHK>
 __global__ void __launch_bounds__(RENDER_BLOCK) primary_kernel(const __grid_constant__ gcore_dev::RenderArgs a, gcore_hit* __restrict__ hits) {
   const int slot = blockIdx.x * RENDER_BLOCK + threadIdx.x;
   if (slot >= a.nslots) return;
@@ -230,16 +267,17 @@ __global__ void __launch_bounds__(RENDER_BLOCK) primary_kernel(const __grid_cons
   if (!px.active) return;
   DHit h;
   unsigned int nmesh = 0;
-  find_closest_hit(ld3(g_scn.cam_pos), eye_ray_dir(a, px.x, px.y, -1), h, nmesh);
+  find_closest_hit<MESHK>(ld3(g_scn.cam_pos), eye_ray_dir(a, px.x, px.y, -1), true, h, nmesh);
   store_hit(&hits[(size_t)px.y * a.width + px.x], h);
 }
 
+template <int MESHK>
 __global__ void __launch_bounds__(RENDER_BLOCK) closest_kernel(int n, const gcore_ray* __restrict__ rays, gcore_hit* __restrict__ hits) {
   const int i = blockIdx.x * RENDER_BLOCK + threadIdx.x;
   if (i >= n) return;
   DHit h;
   unsigned int nmesh = 0;
-  find_closest_hit(ld3(rays[i].origin), ld3(rays[i].direction), h, nmesh);
+  find_closest_hit<MESHK>(ld3(rays[i].origin), ld3(rays[i].direction), true, h, nmesh);
   store_hit(&hits[i], h);
 }
 
@@ -248,7 +286,8 @@ __global__ void __launch_bounds__(RENDER_BLOCK) bvh_batch_kernel(int n, const gc
   const int i = blockIdx.x * RENDER_BLOCK + threadIdx.x;
   if (i >= n) return;
   int prim; float t, u, v;
-  bvh_closest(g_scn.bvh_legacy, ld3(rays[i].origin), ld3(rays[i].direction), t_near, t_far, prim, t, u, v);
+  const f3 o = ld3(rays[i].origin), d = ld3(rays[i].direction);
+  bvh_closest(g_scn.bvh_legacy, o, d, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), t_near, t_far, prim, t, u, v);
   found[i] = (prim >= 0) ? 1 : 0;
   if (prim >= 0) {
     gcore_HitCpp hc;
@@ -296,33 +335,41 @@ cudaError_t upload_scene(const art::DeviceScene* host_copy, cudaStream_t s) {
 
 static inline int blocks_for(int n, int b) { return (n + b - 1) / b; }
 
-cudaError_t launch_render(int render_type, const RenderArgs& a, cudaStream_t s) {
-  if (a.nslots <= 0) return cudaSuccess;
+template <int MESHK>
+static cudaError_t launch_render_m(int render_type, const RenderArgs& a, cudaStream_t s) {
   dim3 g(blocks_for(a.nslots, RENDER_BLOCK)), b(RENDER_BLOCK);
   switch (render_type) {
-    case GCORE_PT_STUPID: render_kernel<GCORE_PT_STUPID><<<g, b, 0, s>>>(a); break;
-    case GCORE_PT_SHADOW: render_kernel<GCORE_PT_SHADOW><<<g, b, 0, s>>>(a); break;
-    case GCORE_PT_MIS:    render_kernel<GCORE_PT_MIS><<<g, b, 0, s>>>(a); break;
+    case GCORE_PT_STUPID: render_kernel<GCORE_PT_STUPID, MESHK><<<g, b, 0, s>>>(a); break;
+    case GCORE_PT_SHADOW: render_kernel<GCORE_PT_SHADOW, MESHK><<<g, b, 0, s>>>(a); break;
+    case GCORE_PT_MIS:    render_kernel<GCORE_PT_MIS, MESHK><<<g, b, 0, s>>>(a); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 
-cudaError_t launch_debug(const RenderArgs& a, cudaStream_t s) {
+cudaError_t launch_render(int render_type, int mesh_kind, const RenderArgs& a, cudaStream_t s) {
   if (a.nslots <= 0) return cudaSuccess;
-  debug_kernel<<<blocks_for(a.nslots, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(a);
+  return (mesh_kind == 2) ? launch_render_m<MESHK_BVH>(render_type, a, s) : launch_render_m<MESHK_CONST>(render_type, a, s);
+}
+
+cudaError_t launch_debug(int mesh_kind, const RenderArgs& a, cudaStream_t s) {
+  if (a.nslots <= 0) return cudaSuccess;
+  if (mesh_kind == 2) debug_kernel<MESHK_BVH><<<blocks_for(a.nslots, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(a);
+  else debug_kernel<MESHK_CONST><<<blocks_for(a.nslots, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(a);
   return cudaGetLastError();
 }
 
-cudaError_t launch_primary_hits(const RenderArgs& a, gcore_hit* d_hits, cudaStream_t s) {
+cudaError_t launch_primary_hits(int mesh_kind, const RenderArgs& a, gcore_hit* d_hits, cudaStream_t s) {
   if (a.nslots <= 0) return cudaSuccess;
-  primary_kernel<<<blocks_for(a.nslots, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(a, d_hits);
+  if (mesh_kind == 2) primary_kernel<MESHK_BVH><<<blocks_for(a.nslots, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(a, d_hits);
+  else primary_kernel<MESHK_CONST><<<blocks_for(a.nslots, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(a, d_hits);
   return cudaGetLastError();
 }
 
-cudaError_t launch_closest_batch(int n, const gcore_ray* d_rays, gcore_hit* d_hits, cudaStream_t s) {
+cudaError_t launch_closest_batch(int mesh_kind, int n, const gcore_ray* d_rays, gcore_hit* d_hits, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  closest_kernel<<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, d_hits);
+  if (mesh_kind == 2) closest_kernel<MESHK_BVH><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, d_hits);
+  else closest_kernel<MESHK_CONST><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, d_hits);
   return cudaGetLastError();
 }
 
@@ -348,9 +395,9 @@ int render_kernel_regs(int render_type) {
   cudaFuncAttributes at;
   cudaError_t e;
   switch (render_type) {
-    case GCORE_PT_STUPID: e = cudaFuncGetAttributes(&at, render_kernel<GCORE_PT_STUPID>); break;
-    case GCORE_PT_SHADOW: e = cudaFuncGetAttributes(&at, render_kernel<GCORE_PT_SHADOW>); break;
-    default:              e = cudaFuncGetAttributes(&at, render_kernel<GCORE_PT_MIS>); break;
+    case GCORE_PT_STUPID: e = cudaFuncGetAttributes(&at, render_kernel<GCORE_PT_STUPID, MESHK_CONST>); break;
+    case GCORE_PT_SHADOW: e = cudaFuncGetAttributes(&at, render_kernel<GCORE_PT_SHADOW, MESHK_CONST>); break;
+    default:              e = cudaFuncGetAttributes(&at, render_kernel<GCORE_PT_MIS, MESHK_CONST>); break;
   }
   if (e != cudaSuccess) { cudaGetLastError(); return -1; }
   return at.numRegs;

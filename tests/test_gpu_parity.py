@@ -10,7 +10,12 @@ pytestmark = pytest.mark.gpu
 
 
 def _bits(a):
-    return np.ascontiguousarray(a).view(np.uint32)
+    """binary32 bit patterns; NaNs are canonicalised: the NaN *payload/sign* is not part of the contract (x86 SSE produces
+    the default NaN 0xFFC00000, NVIDIA GPUs 0x7FFFFFFF) -- a NaN must still be a NaN on both sides."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = a.view(np.uint32).copy()
+    b[np.isnan(a)] = 0x7FC00000
+    return b
 
 
 def _assert_hits_equal(g, o):
@@ -68,7 +73,7 @@ def test_closest_hit_batch_random_rays(gscene, oscene, pkg):
     g = gscene.Find_Closest_Hit(rays)
     o = oscene.closest_hit_batch(rays)
     _assert_hits_equal(g, o)
-    assert 0.5 < g["is_hit"].mean() <= 1.0
+    assert 0.3 < g["is_hit"].mean() <= 1.0
 
 
 def test_closest_hit_rect_light_scene(pkg, ob):
