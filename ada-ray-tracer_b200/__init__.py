@@ -17,7 +17,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libgcore_b200.so")
+LIB_PATH = os.environ.get("GCORE_B200_LIB", os.path.join(_HERE, "libgcore_b200.so"))   # override: tuning experiments only
 DEFAULT_VSGF = os.path.join(ROOT, "data", "pyramid2.vsgf")
 
 # ---- POD layouts of include/gcore.h -------------------------------------------------------------------------------
@@ -47,7 +47,7 @@ class RenderConfig(C.Structure):
 
 
 class RenderStats(C.Structure):
-    _fields_ = [("rays", C.c_uint64), ("samples", C.c_uint64), ("mesh_queries", C.c_uint64), ("bounces", C.c_uint64),
+    _fields_ = [("rays", C.c_uint64), ("samples", C.c_uint64), ("mesh_queries", C.c_uint64), ("bounces", C.c_uint64), ("hoisted_rays", C.c_uint64),
                 ("kernel_ms", C.c_float), ("total_ms", C.c_float),
                 ("spp", C.c_int32), ("kernel_launches", C.c_int32)]
 
@@ -389,10 +389,10 @@ def stream_handle():
 
 
 def get_counters():
-    """(rays, mesh_queries, bounces) accumulated since the last Resize_Viewport"""
-    c = np.zeros(3, np.uint64)
+    """(rays traced, mesh_queries, bounces, hoisted camera rays) accumulated since the last Resize_Viewport"""
+    c = np.zeros(4, np.uint64)
     _ck(lib().gcore_get_counters(_p(c)))
-    return int(c[0]), int(c[1]), int(c[2])
+    return int(c[0]), int(c[1]), int(c[2]), int(c[3])
 
 
 def synchronize():

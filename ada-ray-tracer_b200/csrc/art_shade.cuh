@@ -117,25 +117,6 @@ ART_D f3 map_tail(f3 deviation, f3 direction, f3 normal) {                      
   return res;
 }
 
-ART_D f3 map_cosine(float r1, float r2, f3 direction, f3 normal, float power) {       // MapSampleToCosineDist :202-252
-  float sin_phi, cos_phi;
-  det_sincos(2.0f * r1 * ART_PI, sin_phi, cos_phi);
-  float cos_theta = ada_expon(1.0f - r2, 1.0f / (power + 1.0f));
-  float sin_theta = sqrt_clamped(1.0f - cos_theta * cos_theta);
-  return map_tail(mk3(sin_theta * cos_phi, sin_theta * sin_phi, cos_theta), direction, normal);
-}
-
-ART_D f3 map_cosine_fixed(float r1, float r2, f3 direction, f3 normal, float power) { // MapSampleToCosineDistFixed :255-312
-  float h = sqrt_clamped(1.0f - ada_expon(r1, 2.0f / (power + 1.0f)));
-  float s, c;
-  det_sincos(2.0f * ART_PI * r2, s, c);
-  f3 deviation;
-  deviation.x = h * c;
-  deviation.y = h * s;
-  deviation.z = ada_expon(r1, 1.0f / (power + 1.0f));
-  return map_tail(deviation, direction, normal);
-}
-
 // ---------------------------------------------------------------- materials.adb
 struct MatSampleD { f3 color; f3 direction; float pdf; bool pureSpecular; };          // materials.ads:18-23
 
@@ -153,99 +134,119 @@ ART_D float fresnel_ada(float cosTheta1, float a_etaExt, float a_etaInt) {      
   return (Rs * Rs + Rp * Rp) / 2.0f;
 }
 
-ART_D MatSampleD mat_sample(const DMaterial& mat, float r1, float r2, f3 ray_dir, f3 normal) {
+// "**" with a run-time exponent, kept out of line: one copy of the exp/log kernels serves every call site
+__device__ __noinline__ float ada_expon_call(float left, float right) { return ada_expon(left, right); }
+
+// function pow (vector_math.adb:24-47) through the out-of-line "**"
+ART_D float pow_ada_call(float left, float right) {
+  if (left == 0.0f && right == 0.0f) return 1.0f;
+  else if (left < 0.0f) return 0.0f;
+  else if (right == 0.0f) return 1.0f;
+  else if (left == 0.0f) { return (right < 0.0f) ? __int_as_float(0x7f800000) : 0.0f; }
+  else if (left == 1.0f) return 1.0f;
+  else if (right == 1.0f) return left;
+  else return ada_expon_call(left, right);
+}
+
+// SampleAndEvalBxDF of every material type (materials.adb:163-166, 197-215, 247-254, 295-331, 363-387) in one pass whose
+// expensive common pieces are executed once, with the lanes of all types that need them converged:
+//   refl = reflect(ray_dir, normal)                  mirror :251, glass :313/:322, Phong :371  (passed in by the caller)
+//   sin/cos of the azimuth                           Lambert vector_math.adb:210-211, Phong :265-266
+//   tangent frame + under-surface fix-up (map_tail)  Lambert :218-250, Phong :278-310
+// Every value is produced by the same operation sequence as in the per-type functions of the reference.
+ART_D MatSampleD mat_sample(const DMaterial& mat, float r1, float r2, f3 ray_dir, f3 normal, f3 refl) {
   MatSampleD ms;
-  f3 refl_c = ld3(mat.color);
-  switch (mat.type) {
-    case MAT_LAMBERT: {                                                               // :197-215
-      f3 newDir = map_cosine(r1, r2, normal, normal, 1.0f);
-      float cosTheta = dot(newDir, normal);
+  ms.color = mk3(0.0f, 0.0f, 0.0f); ms.direction = mk3(0.0f, 0.0f, 0.0f); ms.pdf = 1.0f; ms.pureSpecular = false;   // MaterialLight / null
+  const int type = mat.type;
+  const f3 refl_c = ld3(mat.color);
+  const float param = mat.param;
+
+  if (type == MAT_LAMBERT || type == MAT_PHONG) {
+    const bool lam = (type == MAT_LAMBERT);
+    // azimuth: Lambert sin/cos(2.0*r1*M_PI), Phong cos/sin(2.0*M_PI*r2)
+    const float angle = lam ? (2.0f * r1 * ART_PI) : (2.0f * ART_PI * r2);
+    float sn, cs;
+    det_sincos(angle, sn, cs);
+    f3 deviation;
+    if (lam) {
+      float cos_theta = ada_expon(1.0f - r2, 1.0f / (1.0f + 1.0f));          // (1.0-r2) ** (1.0/(e+1.0)), e = 1.0
+      float sin_theta = sqrt_clamped(1.0f - cos_theta * cos_theta);
+      deviation = mk3(sin_theta * cs, sin_theta * sn, cos_theta);
+    } else {
+      float hh = sqrt_clamped(1.0f - ada_expon_call(r1, 2.0f / (param + 1.0f)));
+      deviation.x = hh * cs;
+      deviation.y = hh * sn;
+      deviation.z = ada_expon_call(r1, 1.0f / (param + 1.0f));
+    }
+    const f3 axis = lam ? normal : refl;
+    const f3 nextDir = map_tail(deviation, axis, normal);
+    if (lam) {                                                                // :204-213
+      float cosTheta = dot(nextDir, normal);
       ms.pdf = fabsf(cosTheta) * ART_INV_PI;
       f3 color = refl_c * ART_INV_PI;
       if (cosTheta < 1.0e-6f) color = mk3(0.0f, 0.0f, 0.0f);
-      ms.color = color; ms.direction = newDir; ms.pureSpecular = false;
-      return ms;
-    }
-    case MAT_MIRROR: {                                                                // :247-254
-      f3 nextDir = reflect(ray_dir, normal);
-      float cosThetaDiv = 1.0f / max2(dot(nextDir, normal), 1.0e-20f);
-      ms.color = refl_c * cosThetaDiv; ms.direction = nextDir; ms.pdf = 1.0f; ms.pureSpecular = true;
-      return ms;
-    }
-    case MAT_GLASS: {                                                                 // :285-331
-      f3 trans = ld3(mat.color2);
-      float ior = mat.param;
-      float f = fresnel_ada(dot(ray_dir, normal), ior, 1.0f);
-      f3 refl = f * refl_c;
-      trans = (1.0f - f) * trans;
-      float lr = length(refl), lt = length(trans);
-      float ksitrans = lt / (lr + lt);
-      float ksirefl  = lr / (lr + lt);
-      f3 nextDirection, bxdf;
-      bool do_reflect;
-      if (r1 > ksitrans) { do_reflect = true; bxdf = refl * (1.0f / ksirefl); }
-      else {
-        bxdf = trans * (1.0f / ksitrans);
-        // TotalInternalReflection :18-32
-        float cos_thetai = dot(neg(ray_dir), normal);
-        float eta = ior;
-        if (cos_thetai < 0.0f) eta = 1.0f / eta;
-        float k2 = 1.0f - (1.0f - cos_thetai * cos_thetai) / (eta * eta);
-        do_reflect = (k2 < 0.0f);
-        if (!do_reflect) {                                                            // refract :34-52
-          f3 n = normal;
-          f3 wo = neg(ray_dir);
-          if (cos_thetai < 0.0f) { cos_thetai = -cos_thetai; n = neg(n); }
-          float cos_theta2 = sqrtf(k2);
-          nextDirection = normalize(neg(wo) * (1.0f / eta) - (cos_theta2 - cos_thetai / eta) * n);
-        }
-      }
-      if (do_reflect) nextDirection = reflect(ray_dir, normal);
-      float cosThetaDiv = 1.0f / max2(fabsf(dot(nextDirection, normal)), 1.0e-20f);
-      ms.color = bxdf * cosThetaDiv; ms.direction = nextDirection; ms.pdf = 1.0f; ms.pureSpecular = true;
-      return ms;
-    }
-    case MAT_PHONG: {                                                                 // :363-387
-      float cosPower = mat.param;
-      f3 r = reflect(ray_dir, normal);
-      f3 nextDir = map_cosine_fixed(r1, r2, r, normal, cosPower);
-      float cosTheta = clampf(dot(nextDir, r), 0.0f, ART_PI * 0.499995f);
-      float pw = pow_ada(cosTheta, cosPower);
-      f3 color = refl_c * (cosPower + 2.0f) * 0.5f * ART_INV_PI * pw;
-      ms.pdf = pw * (cosPower + 1.0f) * (0.5f * ART_INV_PI);
+      ms.color = color; ms.direction = nextDir;
+    } else {                                                                  // :374-385
+      float cosTheta = clampf(dot(nextDir, refl), 0.0f, ART_PI * 0.499995f);
+      float pw = pow_ada_call(cosTheta, param);
+      f3 color = refl_c * (param + 2.0f) * 0.5f * ART_INV_PI * pw;
+      ms.pdf = pw * (param + 1.0f) * (0.5f * ART_INV_PI);
       float cosThetaGeo = dot(nextDir, normal);
       float cosThetaDiv = 1.0f / max2(fabsf(cosThetaGeo), 1.0e-20f);
       if (cosThetaGeo < 1.0e-6f) color = mk3(0.0f, 0.0f, 0.0f);
-      ms.color = color * cosThetaDiv; ms.direction = nextDir; ms.pureSpecular = false;
-      return ms;
+      ms.color = color * cosThetaDiv; ms.direction = nextDir;
     }
-    default:                                                                          // MaterialLight :163-166 / null
-      ms.color = mk3(0.0f, 0.0f, 0.0f); ms.direction = mk3(0.0f, 0.0f, 0.0f); ms.pdf = 1.0f; ms.pureSpecular = false;
-      return ms;
+  } else if (type == MAT_MIRROR) {                                            // :247-254
+    float cosThetaDiv = 1.0f / max2(dot(refl, normal), 1.0e-20f);
+    ms.color = refl_c * cosThetaDiv; ms.direction = refl; ms.pdf = 1.0f; ms.pureSpecular = true;
+  } else if (type == MAT_GLASS) {                                             // :285-331
+    f3 trans = ld3(mat.color2);
+    float ior = param;
+    float f = fresnel_ada(dot(ray_dir, normal), ior, 1.0f);
+    f3 rf = f * refl_c;
+    trans = (1.0f - f) * trans;
+    float lr = length(rf), lt = length(trans);
+    float ksitrans = lt / (lr + lt);
+    float ksirefl  = lr / (lr + lt);
+    f3 nextDirection = refl, bxdf;
+    if (r1 > ksitrans) { bxdf = rf * (1.0f / ksirefl); }
+    else {
+      bxdf = trans * (1.0f / ksitrans);
+      // TotalInternalReflection :18-32
+      float cos_thetai = dot(neg(ray_dir), normal);
+      float eta = ior;
+      if (cos_thetai < 0.0f) eta = 1.0f / eta;
+      float k2 = 1.0f - (1.0f - cos_thetai * cos_thetai) / (eta * eta);
+      if (!(k2 < 0.0f)) {                                                     // refract :34-52
+        f3 n = normal;
+        f3 wo = neg(ray_dir);
+        if (cos_thetai < 0.0f) { cos_thetai = -cos_thetai; n = neg(n); }
+        float cos_theta2 = sqrtf(k2);
+        nextDirection = normalize(neg(wo) * (1.0f / eta) - (cos_theta2 - cos_thetai / eta) * n);
+      }
+    }
+    float cosThetaDiv = 1.0f / max2(fabsf(dot(nextDirection, normal)), 1.0e-20f);
+    ms.color = bxdf * cosThetaDiv; ms.direction = nextDirection; ms.pdf = 1.0f; ms.pureSpecular = true;
   }
+  return ms;
 }
 
-// EvalBxDF and EvalPDF for the light direction l (materials.adb:168-176, 217-226, 256-264, 333-341, 389-410)
-ART_D void mat_eval(const DMaterial& mat, f3 l, f3 v, f3 n, f3& bxdf, float& pdf) {
-  switch (mat.type) {
-    case MAT_LAMBERT: {
-      bxdf = ld3(mat.color) * ART_INV_PI;
-      pdf  = max2(dot(n, l), 0.0f) * ART_INV_PI;
-      return;
-    }
-    case MAT_PHONG: {
-      float cosPower = mat.param;
-      f3 r = reflect(neg(v), n);
-      float cosTheta = clampf(dot(l, r), 0.0f, ART_PI * 0.499995f);
-      float cosThetaDiv = 1.0f / max2(dot(l, n), 1.0e-20f);
-      float pw = pow_ada(cosTheta, cosPower);
-      bxdf = ld3(mat.color) * (cosPower + 2.0f) * 0.5f * ART_INV_PI * pw * cosThetaDiv;
-      pdf  = pw * (cosPower + 1.0f) * (0.5f * ART_INV_PI);
-      return;
-    }
-    default:
-      bxdf = mk3(0.0f, 0.0f, 0.0f); pdf = 1.0f;
-      return;
+// EvalBxDF and EvalPDF for the light direction l (materials.adb:168-176, 217-226, 256-264, 333-341, 389-410);
+// refl = reflect((-1.0)*v, n) with v = (-1.0)*ray_dir, i.e. reflect(ray_dir, n) -- the negations are exact
+ART_D void mat_eval(const DMaterial& mat, f3 l, f3 n, f3 refl, f3& bxdf, float& pdf) {
+  const int type = mat.type;
+  if (type == MAT_LAMBERT) {
+    bxdf = ld3(mat.color) * ART_INV_PI;
+    pdf  = max2(dot(n, l), 0.0f) * ART_INV_PI;
+  } else if (type == MAT_PHONG) {
+    float cosPower = mat.param;
+    float cosTheta = clampf(dot(l, refl), 0.0f, ART_PI * 0.499995f);
+    float cosThetaDiv = 1.0f / max2(dot(l, n), 1.0e-20f);
+    float pw = pow_ada_call(cosTheta, cosPower);
+    bxdf = ld3(mat.color) * (cosPower + 2.0f) * 0.5f * ART_INV_PI * pw * cosThetaDiv;
+    pdf  = pw * (cosPower + 1.0f) * (0.5f * ART_INV_PI);
+  } else {
+    bxdf = mk3(0.0f, 0.0f, 0.0f); pdf = 1.0f;
   }
 }
 

@@ -48,7 +48,7 @@ struct State {
   int rank = 0, world = 1;
   float4* d_accum = nullptr; int nslots = 0;
   unsigned long long* d_rays = nullptr;      // 3 cumulative counters: rays, mesh-bbox queries, bounces
-  unsigned long long last_counters[3] = {0, 0, 0};
+  unsigned long long last_counters[4] = {0, 0, 0, 0};
   float4* d_hdr = nullptr; uint32_t* d_ldr = nullptr; size_t out_pixels = 0;
 
   int  err_code = 0;
@@ -78,8 +78,8 @@ int ensure_device() {
   CU(cudaSetDevice(s.device), "cudaSetDevice");
   CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
   CU(cudaEventCreate(&s.ev0), "cudaEventCreate"); CU(cudaEventCreate(&s.ev1), "cudaEventCreate"); CU(cudaEventCreate(&s.ev2), "cudaEventCreate");
-  CU(cudaMalloc(&s.d_rays, 3 * sizeof(unsigned long long)), "cudaMalloc");
-  CU(cudaMemset(s.d_rays, 0, 3 * sizeof(unsigned long long)), "cudaMemset");
+  CU(cudaMalloc(&s.d_rays, 4 * sizeof(unsigned long long)), "cudaMalloc");
+  CU(cudaMemset(s.d_rays, 0, 4 * sizeof(unsigned long long)), "cudaMemset");
   s.dev_ready = true;
   s.scene_dirty = true;
   return 0;
@@ -125,8 +125,8 @@ int alloc_accum() {
   s.nslots = local_tiles * GC_TILE * GC_TILE;
   CU(cudaMalloc(&s.d_accum, sizeof(float4) * (size_t)s.nslots), "cudaMalloc accum");
   CU(cudaMemsetAsync(s.d_accum, 0, sizeof(float4) * (size_t)s.nslots, s.stream), "memset accum");
-  CU(cudaMemsetAsync(s.d_rays, 0, 3 * sizeof(unsigned long long), s.stream), "memset counters");
-  s.last_counters[0] = s.last_counters[1] = s.last_counters[2] = 0;
+  CU(cudaMemsetAsync(s.d_rays, 0, 4 * sizeof(unsigned long long), s.stream), "memset counters");
+  s.last_counters[0] = s.last_counters[1] = s.last_counters[2] = s.last_counters[3] = 0;
   s.spp = 0;
   return 0;
 }
@@ -291,12 +291,13 @@ int render_units_locked(int units, gcore_render_stats* stats) {
   }
   CU(cudaEventRecord(s.ev1, s.stream), "event");
   if (stats) {
-    unsigned long long c[3] = {0, 0, 0};
+    unsigned long long c[4] = {0, 0, 0, 0};
     CU(cudaMemcpyAsync(c, s.d_rays, sizeof(c), cudaMemcpyDeviceToHost, s.stream), "memcpy counters");
     CU(cudaStreamSynchronize(s.stream), "render sync");
     float ms = 0.f; cudaEventElapsedTime(&ms, s.ev0, s.ev1);
     stats->rays = c[0] - s.last_counters[0]; stats->mesh_queries = c[1] - s.last_counters[1]; stats->bounces = c[2] - s.last_counters[2];
-    s.last_counters[0] = c[0]; s.last_counters[1] = c[1]; s.last_counters[2] = c[2];
+    stats->hoisted_rays = c[3] - s.last_counters[3];
+    s.last_counters[0] = c[0]; s.last_counters[1] = c[1]; s.last_counters[2] = c[2]; s.last_counters[3] = c[3];
     stats->samples = samples; stats->kernel_ms = ms; stats->total_ms = ms; stats->spp = s.spp;
     stats->kernel_launches = launches;
   }
@@ -717,10 +718,10 @@ int gcore_get_counters(uint64_t* out3) {
   std::lock_guard<std::recursive_mutex> lk(s.mu);
   if (!out3) return fail(GCORE_E_ARG, "gcore_get_counters: null");
   if (int rc = ensure_device()) return rc;
-  unsigned long long c[3] = {0, 0, 0};
+  unsigned long long c[4] = {0, 0, 0, 0};
   CU(cudaMemcpyAsync(c, s.d_rays, sizeof(c), cudaMemcpyDeviceToHost, s.stream), "memcpy counters");
   CU(cudaStreamSynchronize(s.stream), "counters sync");
-  out3[0] = c[0]; out3[1] = c[1]; out3[2] = c[2];
+  out3[0] = c[0]; out3[1] = c[1]; out3[2] = c[2]; out3[3] = c[3];
   return 0;
 }
 
@@ -744,8 +745,8 @@ int gcore_render(const gcore_render_config* cfg, int width, int height, int unit
   if (width != s.width || height != s.height || !s.d_accum) { if ((rc = gcore_resize_viewport(width, height))) return rc; }
   else {                                                               // same viewport: clear like Resize_Viewport does
     CU(cudaMemsetAsync(s.d_accum, 0, sizeof(float4) * (size_t)s.nslots, s.stream), "memset accum");
-    CU(cudaMemsetAsync(s.d_rays, 0, 3 * sizeof(unsigned long long), s.stream), "memset counters");
-    s.last_counters[0] = s.last_counters[1] = s.last_counters[2] = 0;
+    CU(cudaMemsetAsync(s.d_rays, 0, 4 * sizeof(unsigned long long), s.stream), "memset counters");
+    s.last_counters[0] = s.last_counters[1] = s.last_counters[2] = s.last_counters[3] = 0;
     s.spp = 0;
   }
   gcore_render_stats st; memset(&st, 0, sizeof(st));

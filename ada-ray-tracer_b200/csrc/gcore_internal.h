@@ -24,7 +24,7 @@ struct RenderArgs {
   float    zdir;                         // -float(width) / safe_tan(fov/2)   (ray_tracer.adb:67)
   float    half_w, half_h;               // float(width)/2, float(height)/2
   float4*  accum;                        // slot-major accumulator (rgb, unused)
-  unsigned long long* counters;          // [0] += scene queries, [1] += queries inside the mesh bbox, [2] += shaded bounces
+  unsigned long long* counters;          // [0] += scene queries, [1] += queries inside the mesh bbox, [2] += shaded bounces, [3] += hoisted camera-ray queries
 };
 
 cudaError_t upload_scene(const art::DeviceScene* host_copy, cudaStream_t s);

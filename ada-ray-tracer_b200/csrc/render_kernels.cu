@@ -23,7 +23,12 @@ using namespace art;
 
 namespace {
 
+#ifndef RENDER_BLOCK
 #define RENDER_BLOCK 128
+#endif
+#ifndef RENDER_MINB
+#define RENDER_MINB 6        // resident blocks per SM the register allocation is bounded for (6 x 128 thr -> <= 85 regs); measured best of 4..10
+#endif
 #define MAX_DEPTH_CAP 16
 
 struct PixelId { int x, y, active; };
@@ -74,15 +79,15 @@ __device__ __forceinline__ void store_hit(gcore_hit* o, const DHit& h) {
   o->t = h.t; o->normal[0] = h.normal.x; o->normal[1] = h.normal.y; o->normal[2] = h.normal.z; o->tx = h.tx; o->ty = h.ty;
 }
 
-enum { PH_NEW = 0, PH_BOUNCE = 1, PH_SHADOW = 2 };
-
 template <int RT, int MESHK>
-__global__ void __launch_bounds__(RENDER_BLOCK) render_kernel(const __grid_constant__ gcore_dev::RenderArgs a) {
+__global__ void __launch_bounds__(RENDER_BLOCK, RENDER_MINB) render_kernel(const __grid_constant__ gcore_dev::RenderArgs a) {
   const int slot = blockIdx.x * RENDER_BLOCK + threadIdx.x;
-  unsigned int nrays = 0, nmesh = 0, nbounce = 0;
+  unsigned int nrays = 0, nmesh = 0, nbounce = 0, nhoisted = 0;
   const PixelId px = slot_to_pixel(a, slot < a.nslots ? slot : 0, a.rank);
-  if (slot < a.nslots && px.active) {
-    const float4 acc4 = a.accum[slot];
+  const bool was_live = (slot < a.nslots) && px.active;
+  {
+    float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (was_live) acc4 = a.accum[slot];
     f3 acc = mk3(acc4.x, acc4.y, acc4.z);
     const f3 bg = mk3(a.bg[0], a.bg[1], a.bg[2]);
     const int aa = a.anti_aliasing;
@@ -91,102 +96,151 @@ __global__ void __launch_bounds__(RENDER_BLOCK) render_kernel(const __grid_const
     const uint32_t pixel = (uint32_t)(px.y * a.width + px.x);
 
     f3 E[MAX_DEPTH_CAP], Wt[MAX_DEPTH_CAP];     // per-bounce explicit term and continuation weight (local memory)
+    f3 Lprim[4];                                // radiance of the sub-pixel camera rays known to end at depth 0
+    unsigned int term_mask = 0;                 // bit i: camera ray of sub-pixel i misses / ends on a light
     f3 color = bg;
-    f3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f);   // the ray of the next scene query
-    // surface state carried from the BOUNCE query to the SHADOW query of the same bounce
-    f3 hpos = o, hn = d, din = d;
-    int hmat = 0;
-    float ls_pdf = 1.0f, sh_thi = 0.0f, sh_tlo = 0.0f, r1 = 0.0f, r2 = 0.0f;
+    f3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f);   // the path ray of the next scene query
+    f3 Lterm = mk3(0.f, 0.f, 0.f);
     float prev_pdf = 1.0f;
     bool  prev_spec = true;
     int   s = 0, depth = 0;
-    int   phase = PH_NEW;
+    bool  live = was_live, has_ray = false, fold_pending = false;
 
-    for (;;) {
-      if (phase == PH_NEW) {
-        if (s == total) break;
-        const int sub = aa ? (s & 3) : -1;
-        o = ld3(g_scn.cam_pos);
-        d = eye_ray_dir(a, px.x, px.y, sub);
-        depth = 0; prev_pdf = 1.0f; prev_spec = true;                         // StartSample, materials.ads:25
-        if (sub <= 0) color = bg;                                             // integrators.adb:42
-        phase = PH_BOUNCE;
+    // Warp-uniform loop, one bounce of every live lane per iteration, all lanes in the same stage at the same time:
+    //   (regenerate) -> A path query -> B light sample -> C shadow query -> D NEE + BSDF sample.
+    // A lane whose path ended idles through B-D of that iteration and regenerates at the top of the next one; a lane
+    // out of samples idles (live = false) instead of leaving, and there is no break/continue in divergent code, so
+    // every branch re-converges inside the body.
+    while (__any_sync(0xffffffffu, live)) {
+      if (live && !has_ray) {
+        if (fold_pending) {                                                   // unwind the recursion: integrators.adb:124,191,299
+          f3 L = Lterm;
+#pragma unroll 1
+          for (int k = depth - 1; k >= 0; k--) {
+            if (RT == GCORE_PT_STUPID) L = Wt[k] * L;
+            else L = E[k] + Wt[k] * L;
+          }
+          const int sub = aa ? (s & 3) : 0;
+          if (depth == 0) { term_mask |= 1u << sub; Lprim[sub] = L; }        // this camera ray ends at depth 0 in every pass
+          if (aa) {
+            if (sub == 0) color = bg;                                         // :42
+            color = color + L;                                                // :47
+            if (sub == 3) acc = color + acc;                                  // :51
+          } else {
+            acc = L + acc;                                                    // :60-63
+          }
+          s++;
+          fold_pending = false;
+        }
+        // Samples whose camera ray is already known to end at depth 0: the 4 sub-pixel directions are fixed
+        // (ray_tracer.adb:72-97), so that query is loop-invariant over the passes of this call; its radiance is added
+        // in the reference's order without re-tracing it.
+#pragma unroll 1
+        while (s < total && ((term_mask >> (aa ? (s & 3) : 0)) & 1u)) {
+          const int sub = aa ? (s & 3) : 0;
+          const f3 L = Lprim[sub];
+          if (aa) {
+            if (sub == 0) color = bg;
+            color = color + L;
+            if (sub == 3) acc = color + acc;
+          } else {
+            acc = L + acc;
+          }
+          s++; nhoisted++;
+        }
+        if (s == total) live = false;
+        else {
+          o = ld3(g_scn.cam_pos);
+          d = eye_ray_dir(a, px.x, px.y, aa ? (s & 3) : -1);
+          depth = 0; prev_pdf = 1.0f; prev_spec = true;                       // StartSample, materials.ads:25
+          has_ray = true;
+        }
       }
+      __syncwarp();
 
+      // ---- A: path query (camera or bounce ray), all live lanes
+      bool surf = false;
       DHit h;
-      find_closest_hit<MESHK>(o, d, phase == PH_BOUNCE, h, nmesh);
-      nrays++;
-
-      f3   Lterm = mk3(0.f, 0.f, 0.f);
-      f3   explicitColor = mk3(0.f, 0.f, 0.f);
-      bool terminal = false, do_bsdf = false;
-
-      if (phase == PH_BOUNCE) {
-        if (!h.is_hit) {
-          terminal = true;                                                    // integrators.adb:98,151,218
-        } else {
-          const int mtype = g_scn.mats[h.mat].type;
-          if (mtype == MAT_LIGHT) {
-            terminal = true;
-            if (RT == GCORE_PT_SHADOW) {
-              Lterm = mk3(0.f, 0.f, 0.f);                                     // :155-157
-            } else if (dot(neg(d), h.normal) < 0.0f) {
-              Lterm = mk3(0.f, 0.f, 0.f);                                     // :103, :224
-            } else {
-              f3 emit = (g_scn.mats[h.mat].light < 0) ? mk3(0.f, 0.f, 0.f) : ld3(g_scn.l_intensity);   // materials.adb:147-156
-              if (RT == GCORE_PT_STUPID) Lterm = emit;                        // :106
-              else {                                                          // :230-243
-                float lgtPdf = light_eval_pdf(o, d, h.t);
-                float bsdfPdf = prev_pdf;
-                float misWeight = prev_spec ? 1.0f : (bsdfPdf * bsdfPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf));
-                Lterm = emit * misWeight;
-              }
-            }
-          } else {
-            nbounce++;
-            const BounceRand br = bounce_rand(a.seed, pixel, (uint32_t)(a.first_sample + s), (uint32_t)depth);
-            hpos = mk3(o.x + h.t * d.x, o.y + h.t * d.y, o.z + h.t * d.z);
-            hn = h.normal; hmat = h.mat; din = d;
-            r1 = br.u2; r2 = br.u3;
-            if (RT == GCORE_PT_STUPID) {
-              do_bsdf = true;
-            } else {                                                          // :161-178 / :251-287
-              LightSample ls = light_sample(br.u0, br.u1, hpos);
-              ls_pdf = ls.pdf;
-              // Compute_Shadow (ray_tracer.adb:100-132): the shadow ray becomes the next query
-              float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
-              epsilon = max2(epsilon, 1.0e-30f);
-              f3 sdir = normalize(ls.pos - hpos);                             // == normalize(lsam.pos - hpos) of :165/:268
-              o = hpos + sdir * epsilon;
-              d = sdir;
-              float maxDist  = length(hpos - ls.pos);
-              float epsilon2 = max2(maxDist * 0.000001f, 1.0e-30f);
-              sh_thi = maxDist - epsilon2;
-              sh_tlo = 10.0f * epsilon;
-              phase = PH_SHADOW;
-            }
-          }
-        }
-      } else {                                                                // PH_SHADOW
-        const bool shadowed = h.is_hit && (h.t < sh_thi && h.t > sh_tlo);     // ray_tracer.adb:122
-        if (!shadowed) {
-          f3 bxdfVal; float bsdfPdf;
-          mat_eval(g_scn.mats[hmat], d, neg(din), hn, bxdfVal, bsdfPdf);
-          float cosTheta1 = max2(dot(d, hn), 0.0f);
-          f3 intensity = ld3(g_scn.l_intensity);
+      if (live) {
+        find_closest_hit<MESHK>(o, d, true, h, nmesh);
+        nrays++;
+        if (!h.is_hit) {                                                      // integrators.adb:98,151,218
+          Lterm = mk3(0.f, 0.f, 0.f); has_ray = false; fold_pending = true;
+        } else if (g_scn.mats[h.mat].type == MAT_LIGHT) {
+          has_ray = false; fold_pending = true;
           if (RT == GCORE_PT_SHADOW) {
-            explicitColor = intensity * (cosTheta1 * bxdfVal) * (1.0f / max2(ls_pdf, 1.0e-20f));
+            Lterm = mk3(0.f, 0.f, 0.f);                                       // :155-157
+          } else if (dot(neg(d), h.normal) < 0.0f) {
+            Lterm = mk3(0.f, 0.f, 0.f);                                       // :103, :224
           } else {
-            float lgtPdf = ls_pdf;
-            float misWeight = lgtPdf * lgtPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf);
-            explicitColor = intensity * (1.0f / max2(lgtPdf, 1.0e-20f)) * (cosTheta1 * bxdfVal) * misWeight;
+            f3 emit = (g_scn.mats[h.mat].light < 0) ? mk3(0.f, 0.f, 0.f) : ld3(g_scn.l_intensity);   // materials.adb:147-156
+            if (RT == GCORE_PT_STUPID) Lterm = emit;                          // :106
+            else {                                                            // :230-243
+              float lgtPdf = light_eval_pdf(o, d, h.t);
+              float bsdfPdf = prev_pdf;
+              float misWeight = prev_spec ? 1.0f : (bsdfPdf * bsdfPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf));
+              Lterm = emit * misWeight;
+            }
           }
-        }
-        do_bsdf = true;
+        } else surf = true;
       }
 
-      if (do_bsdf) {                                                          // pick up next ray, :116,183,291
-        MatSampleD ms = mat_sample(g_scn.mats[hmat], r1, r2, din, hn);
+      // ---- B: light sample + shadow ray (Compute_Shadow, ray_tracer.adb:100-132), lanes standing on a surface
+      f3 hpos = o, sdir = d;
+      float ls_pdf = 1.0f, sh_thi = 0.0f, sh_tlo = 0.0f, r1 = 0.0f, r2 = 0.0f;
+      f3 so = o;
+      if (surf) {
+        nbounce++;
+        const BounceRand br = bounce_rand(a.seed, pixel, (uint32_t)(a.first_sample + s), (uint32_t)depth);
+        hpos = mk3(o.x + h.t * d.x, o.y + h.t * d.y, o.z + h.t * d.z);
+        r1 = br.u2; r2 = br.u3;
+        if (RT != GCORE_PT_STUPID) {                                          // :161-178 / :251-287
+          LightSample ls = light_sample(br.u0, br.u1, hpos);
+          ls_pdf = ls.pdf;
+          float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
+          epsilon = max2(epsilon, 1.0e-30f);
+          sdir = normalize(ls.pos - hpos);                                    // == normalize(lsam.pos - hpos) of :165/:268
+          so = hpos + sdir * epsilon;
+          float maxDist  = length(hpos - ls.pos);
+          float epsilon2 = max2(maxDist * 0.000001f, 1.0e-30f);
+          sh_thi = maxDist - epsilon2;
+          sh_tlo = 10.0f * epsilon;
+        }
+      }
+
+      // ---- C: shadow query (closest hit, only is_hit / t are read: ray_tracer.adb:117-122)
+      bool shadowed = false;
+      if (RT != GCORE_PT_STUPID) {
+        if (surf) {
+          DHit hs;
+          find_closest_hit<MESHK>(so, sdir, false, hs, nmesh);
+          nrays++;
+          shadowed = hs.is_hit && (hs.t < sh_thi && hs.t > sh_tlo);
+        }
+      }
+
+      // ---- D: explicit light term + BSDF sample + next ray
+      if (surf) {
+        const DMaterial& m = g_scn.mats[h.mat];
+        const f3 hn = h.normal;
+        const f3 refl = reflect(d, hn);           // shared by Phong eval/sample, mirror, glass (materials.adb:251,313,371,394)
+        f3 explicitColor = mk3(0.f, 0.f, 0.f);
+        if (RT != GCORE_PT_STUPID) {
+          if (!shadowed) {
+            f3 bxdfVal; float bsdfPdf;
+            mat_eval(m, sdir, hn, refl, bxdfVal, bsdfPdf);
+            float cosTheta1 = max2(dot(sdir, hn), 0.0f);
+            f3 intensity = ld3(g_scn.l_intensity);
+            if (RT == GCORE_PT_SHADOW) {
+              explicitColor = intensity * (cosTheta1 * bxdfVal) * (1.0f / max2(ls_pdf, 1.0e-20f));
+            } else {
+              float lgtPdf = ls_pdf;
+              float misWeight = lgtPdf * lgtPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf);
+              explicitColor = intensity * (1.0f / max2(lgtPdf, 1.0e-20f)) * (cosTheta1 * bxdfVal) * misWeight;
+            }
+          }
+        }
+        MatSampleD ms = mat_sample(m, r1, r2, d, hn, refl);                   // pick up next ray, :116,183,291
         f3 bxdfVal = ms.color * (1.0f / max2(ms.pdf, 1.0e-20f));
         float cosTheta = dot(ms.direction, hn);
         E[depth]  = explicitColor;
@@ -196,37 +250,23 @@ __global__ void __launch_bounds__(RENDER_BLOCK) render_kernel(const __grid_const
         o = hpos + off;
         d = ms.direction;
         prev_pdf = ms.pdf; prev_spec = ms.pureSpecular;
-        phase = PH_BOUNCE;
-        if (depth == max_depth) terminal = true;                              // recursion_level = 0 -> (0,0,0)
-      }
-
-      if (terminal) {
-        f3 L = Lterm;                                                         // unwind the recursion: :124,191,299
-#pragma unroll 1
-        for (int k = depth - 1; k >= 0; k--) {
-          if (RT == GCORE_PT_STUPID) L = Wt[k] * L;
-          else L = E[k] + Wt[k] * L;
+        if (depth == max_depth) {                                             // recursion_level = 0 -> (0,0,0)
+          Lterm = mk3(0.f, 0.f, 0.f); has_ray = false; fold_pending = true;
         }
-        if (aa) {
-          color = color + L;                                                  // :47
-          if ((s & 3) == 3) acc = color + acc;                                // :51
-        } else {
-          acc = L + acc;                                                      // :60-63
-        }
-        s++;
-        phase = PH_NEW;
       }
     }
-    a.accum[slot] = make_float4(acc.x, acc.y, acc.z, acc4.w);
+    if (was_live) a.accum[slot] = make_float4(acc.x, acc.y, acc.z, acc4.w);
   }
   // statistics: one atomic per warp and counter
   unsigned int total_rays = __reduce_add_sync(0xffffffffu, nrays);
   unsigned int total_mesh = __reduce_add_sync(0xffffffffu, nmesh);
   unsigned int total_bnc  = __reduce_add_sync(0xffffffffu, nbounce);
-  if ((threadIdx.x & 31) == 0 && total_rays) {
+  unsigned int total_hst  = __reduce_add_sync(0xffffffffu, nhoisted);
+  if ((threadIdx.x & 31) == 0 && (total_rays | total_hst)) {
     atomicAdd(&a.counters[0], (unsigned long long)total_rays);
     atomicAdd(&a.counters[1], (unsigned long long)total_mesh);
     atomicAdd(&a.counters[2], (unsigned long long)total_bnc);
+    atomicAdd(&a.counters[3], (unsigned long long)total_hst);
   }
 }
 

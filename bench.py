@@ -242,13 +242,13 @@ def main():
     c1 = pkg.get_counters()
     step_ms = sum(a.elapsed_time(c) for a, _, c in ev)
     kern_ms = sum(a.elapsed_time(b) for a, b, _ in ev)
-    rays_local, mesh_local, bounce_local = (c1[i] - c0[i] for i in range(3))
+    rays_local, mesh_local, bounce_local, hoisted_local = (c1[i] - c0[i] for i in range(4))
     t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([rays_local, mesh_local, bounce_local, launches], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([rays_local, mesh_local, bounce_local, launches, hoisted_local], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     step_ms, kern_ms = float(t[0]), float(t[1])
-    rays, mesh_q, bounces, launches_all = (float(x) for x in cnt)
+    rays, mesh_q, bounces, launches_all, hoisted = (float(x) for x in cnt)
     value = rays / (step_ms * 1e-3) / 1e6
 
     # ---------------------------------------------------------------- e2e: C-ABI call with host buffers
@@ -338,7 +338,8 @@ def main():
                            "l2": "256 MiB buffer written between timed steps (outside the per-step CUDA events); inputs are < L2",
                            "numerics": "bit-exact mode (-fmad=false, IEEE div/sqrt), identical to the CPU oracle"},
                 "msamples_per_s": (npx * units * (4 if aa else 1)) / (step_ms / args.steps * 1e-3) / 1e6,
-                "rays_per_step": rays / args.steps, "wall_s": wall,
+                "rays_per_step": rays / args.steps, "hoisted_rays_per_step": hoisted / args.steps,
+                "reference_equivalent_mrays_per_s": (rays + hoisted) / (step_ms * 1e-3) / 1e6, "wall_s": wall,
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                           "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": int(launches_all), "roofline": roofline, "cpu_baseline": cpu_baseline}

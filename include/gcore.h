@@ -146,10 +146,13 @@ typedef struct gcore_render_config {          /* the package-level variables of 
 } gcore_render_config;
 
 typedef struct gcore_render_stats {
-  uint64_t rays;            /* scene queries traced by the last render call (primary + bounce + shadow) */
+  uint64_t rays;            /* scene queries TRACED by the last render call (primary + bounce + shadow)  */
   uint64_t samples;         /* pixel samples added by the last render call                             */
   uint64_t mesh_queries;    /* of `rays`, those that entered the mesh bounding box (triangle loop run)  */
   uint64_t bounces;         /* shaded (non-light) surface interactions of the last render call         */
+  uint64_t hoisted_rays;    /* camera-ray queries NOT traced: loop-invariant over the passes of the call (a fixed sub-pixel
+                               ray that misses / ends on a light does so in every pass); rays + hoisted_rays is the
+                               number of Find_Closest_Hit calls the reference makes for the same samples */
   float    kernel_ms;       /* device time of the render kernel(s), CUDA events                        */
   float    total_ms;        /* device time including resolve and copies                                */
   int32_t  spp;             /* samples per pixel accumulated so far                                    */
@@ -167,9 +170,9 @@ GCORE_API int gcore_resize_viewport(int width, int height);
 /* `units` DoPass units on the device; each adds 4 (AA) or 1 spp, exactly like one Path_Trace_Thread doing one
  * pass (Render_Pass = Threads_Num units).  No host transfer. */
 GCORE_API int gcore_render_units(int units, gcore_render_stats* stats);
-/* counters accumulated since the last gcore_resize_viewport (rays, mesh_queries, bounces): lets a caller enqueue
- * many gcore_render_units(units, NULL) calls without a host sync and read the totals once.  out3 = 3 x uint64 */
-GCORE_API int gcore_get_counters(uint64_t* out3);
+/* counters accumulated since the last gcore_resize_viewport (rays, mesh_queries, bounces, hoisted_rays): lets a caller
+ * enqueue many gcore_render_units(units, NULL) calls without a host sync and read the totals once.  out4 = 4 x uint64 */
+GCORE_API int gcore_get_counters(uint64_t* out4);
 /* GetSPP */
 GCORE_API int gcore_get_spp(void);
 /* resolve the accumulator (ray_tracer.adb:281-291) and copy to HOST buffers, row-major [y*W+x];

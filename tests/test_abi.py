@@ -45,7 +45,7 @@ def test_pod_layouts(pkg):
     assert pkg.light_dt.itemsize == 72
     assert pkg.camera_dt.itemsize == 100
     assert C.sizeof(pkg.RenderConfig) == 28
-    assert C.sizeof(pkg.RenderStats) == 48
+    assert C.sizeof(pkg.RenderStats) == 56
 
 
 def test_error_reporting_without_device(pkg):
