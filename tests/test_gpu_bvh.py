@@ -1,0 +1,200 @@
+"""GPU LBVH build + traversal (K3/K4) against the oracle: legacy gcore_* seam (the Embree replacement) and the
+nearest-hit mesh mode of the renderer.  Primitive ids AND t/u/v must be bit-exact: the boxes only cull."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _syn(pkg):
+    spec = importlib.util.spec_from_file_location("ada_ray_tracer_b200_synthetic", os.path.join(os.path.dirname(pkg.__file__), "synthetic.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a, np.float32)
+    b = a.view(np.uint32).copy(); b[np.isnan(a)] = 0x7FC00000
+    return b
+
+
+def _soup(rng, ntris, extent=2.0, size=0.3):
+    c = rng.uniform(-extent, extent, (ntris, 1, 3))
+    v = (c + rng.uniform(-size, size, (ntris, 3, 3))).astype(np.float32).reshape(-1, 3)
+    return v, np.arange(3 * ntris, dtype=np.int32).reshape(-1, 3)
+
+
+def _rays(rng, n, pkg, extent=3.0):
+    r = np.zeros(n, pkg.ray_dt)
+    r["origin"] = rng.uniform(-extent, extent, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[: n // 16] = 0; d[np.arange(n // 16), rng.integers(0, 3, n // 16)] = 1.0       # axis-parallel: 1/0 = inf in the slab tests
+    r["direction"] = d.astype(np.float32)
+    return r
+
+
+def _brute(ob, verts, tris, rays, t0, t1):
+    n = len(rays)
+    prim = np.zeros(n, np.int32); t = np.zeros(n, np.float32); u = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
+    rr = np.ascontiguousarray(rays.view(ob.ray_dt))
+    ob.lib().ao_bruteforce_closest(verts.ctypes.data, tris.ctypes.data, len(tris), n, rr.ctypes.data, t0, t1,
+                                   prim.ctypes.data, t.ctypes.data, u.ctypes.data, v.ctypes.data)
+    return prim, t, u, v
+
+
+def _check(found, hits, prim, t, u, v):
+    assert np.array_equal(found != 0, prim >= 0)
+    m = prim >= 0
+    assert np.array_equal(hits["primIndex"][m], prim[m])
+    assert np.array_equal(_bits(hits["t"][m]), _bits(t[m]))
+    # texCoord = (weight of B, weight of C) = (reference v, reference u)
+    assert np.array_equal(_bits(hits["texCoord"][m, 0]), _bits(v[m]))
+    assert np.array_equal(_bits(hits["texCoord"][m, 1]), _bits(u[m]))
+    assert np.all(hits["primIndex"][~m] == -1)                         # records are only written on a hit
+
+
+@pytest.mark.parametrize("ntris", [1, 2, 3, 17, 2000])
+def test_legacy_seam_random_soup(pkg, ob, ntris):
+    rng = np.random.default_rng(100 + ntris)
+    verts, tris = _soup(rng, ntris)
+    gc = pkg.GeometryCore()
+    gc.init_and_clear()
+    assert gc.add_mesh_3f(verts, tris) == 0
+    gc.commit_scene()
+    rays = _rays(rng, 20000, pkg)
+    found, hits = gc.closest_hit_batch(rays, 0.0, 100000.0)
+    prim, t, u, v = _brute(ob, verts, tris, rays, 0.0, 100000.0)
+    _check(found, hits, prim, t, u, v)
+    if ntris >= 17:
+        assert (prim >= 0).sum() > 50
+    info = gc.bvh_info()
+    assert info["ntris"] == ntris and info["nnodes"] == max(ntris - 1, 0)
+    gc.destroy()
+
+
+def test_legacy_seam_t_window_and_single_ray(pkg, ob):
+    rng = np.random.default_rng(5)
+    verts, tris = _soup(rng, 500)
+    gc = pkg.GeometryCore(); gc.init_and_clear(); gc.add_mesh_3f(verts, tris); gc.commit_scene()
+    rays = _rays(rng, 5000, pkg)
+    found, hits = gc.closest_hit_batch(rays, 0.5, 2.5)
+    prim, t, u, v = _brute(ob, verts, tris, rays, 0.5, 2.5)
+    _check(found, hits, prim, t, u, v)
+    # one ray per call (the signature scene_hydra_embree.adb:426-446 uses): same answers, record untouched on a miss
+    idx = np.concatenate([np.flatnonzero(prim >= 0)[:20], np.flatnonzero(prim < 0)[:20]])
+    for i in idx:
+        ok, h = gc.closest_hit(rays["origin"][i], rays["direction"][i], 0.5, 2.5)
+        assert ok == (prim[i] >= 0)
+        if ok:
+            assert h["primIndex"] == prim[i] and np.float32(h["t"]).view(np.uint32) == t[i].view(np.uint32)
+        else:
+            assert h["primIndex"] == -1
+    gc.destroy()
+
+
+def test_legacy_seam_instances_and_index_sanitising(pkg, ob):
+    rng = np.random.default_rng(9)
+    v0, t0 = _soup(rng, 300, extent=0.8, size=0.2)
+    v1, t1 = _soup(rng, 200, extent=0.5, size=0.3)
+    t0 = t0.copy(); t0[5] = (10_000, 1, 2); t0[7] = (-3, 4, 5)         # embree_connect.cpp:98-109 -> (vertexNum-1) x3
+    gc = pkg.GeometryCore(); gc.init_and_clear()
+    assert gc.add_mesh_3f(v0, t0) == 0 and gc.add_mesh_3f(v1, t1) == 1
+    mats = []
+    for k in range(3):
+        M = np.eye(4, dtype=np.float32); M[:3, 3] = rng.uniform(-1.5, 1.5, 3); M[0, 0] = 1.0 + 0.25 * k; M[1, 2] = 0.1 * k
+        mats.append(M)
+    gc.instance_meshes(0, np.stack(mats[:2]).reshape(-1, 16))
+    gc.instance_meshes(1, mats[2].reshape(1, 16))
+    gc.commit_scene()
+    # flattened world-space copy, same binary32 operation order as the commit (row-major 3x4)
+    ts0 = t0.copy(); ts0[5] = len(v0) - 1; ts0[7] = len(v0) - 1
+    fv, ft, fprim, finst = [], [], [], []
+    base = 0
+    for ii, (vv, tt, M) in enumerate([(v0, ts0, mats[0]), (v0, ts0, mats[1]), (v1, t1, mats[2])]):
+        x, y, z = vv[:, 0], vv[:, 1], vv[:, 2]
+        w = np.stack([M[r, 0] * x + M[r, 1] * y + M[r, 2] * z + M[r, 3] for r in range(3)], 1).astype(np.float32)
+        fv.append(w); ft.append(tt + base); fprim.append(np.arange(len(tt))); finst.append(np.full(len(tt), ii)); base += len(vv)
+    fv = np.ascontiguousarray(np.concatenate(fv)); ft = np.ascontiguousarray(np.concatenate(ft).astype(np.int32))
+    fprim = np.concatenate(fprim); finst = np.concatenate(finst)
+    rays = _rays(rng, 20000, pkg)
+    found, hits = gc.closest_hit_batch(rays, 0.0, 1000.0)
+    prim, t, u, v = _brute(ob, fv, ft, rays, 0.0, 1000.0)
+    m = prim >= 0
+    assert np.array_equal(found != 0, m) and m.sum() > 200
+    assert np.array_equal(hits["primIndex"][m], fprim[prim[m]])
+    assert np.array_equal(hits["instIndex"][m], finst[prim[m]])
+    assert np.all(hits["geomIndex"][m] == 0)
+    assert np.array_equal(_bits(hits["t"][m]), _bits(t[m]))
+    gc.destroy()
+
+
+def test_lbvh_large_mesh_vs_cpu_bvh(pkg, ob):
+    """C5-shaped mesh at reduced tessellation (196 608 triangles): 200 k random + primary-like rays vs the oracle's own CPU
+    BVH (checked against brute force on a sample)"""
+    syn = _syn(pkg)
+    pos, nrm, tris = syn.cube_sphere(128)
+    pos = np.ascontiguousarray(pos); tris = np.ascontiguousarray(tris)
+    gc = pkg.GeometryCore(); gc.init_and_clear(); gc.add_mesh_3f(pos, tris); gc.commit_scene()
+    rng = np.random.default_rng(3)
+    n = 200_000
+    rays = np.zeros(n, pkg.ray_dt)
+    o = rng.uniform([-2.4, 0.1, 0.1], [2.4, 4.9, 12.0], (n, 3))
+    target = np.array([0.0, 1.6, 2.5]) + rng.normal(size=(n, 3)) * 0.9
+    d = target - o; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays["origin"], rays["direction"] = o.astype(np.float32), d.astype(np.float32)
+    found, hits = gc.closest_hit_batch(rays, 0.0, 1000000.0)
+    L = ob.lib()
+    bvh = L.ao_bvh_build(pos.ctypes.data, len(pos), tris.ctypes.data, len(tris))
+    prim = np.zeros(n, np.int32); t = np.zeros(n, np.float32); u = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
+    rr = np.ascontiguousarray(rays.view(ob.ray_dt))
+    L.ao_bvh_closest(bvh, n, rr.ctypes.data, 0.0, 1000000.0, prim.ctypes.data, t.ctypes.data, u.ctypes.data, v.ctypes.data, 0)
+    L.ao_bvh_free(bvh)
+    _check(found, hits, prim, t, u, v)
+    assert 0.3 < (prim >= 0).mean() < 0.95
+    sub = slice(0, 300)                                                 # the CPU BVH itself against brute force
+    p2, t2, u2, v2 = _brute(ob, pos, tris, rays[sub], 0.0, 1000000.0)
+    assert np.array_equal(p2, prim[sub]) and np.array_equal(_bits(t2), _bits(t[sub]))
+    gc.destroy()
+
+
+def _mesh_scene(pkg, ob, nseg, mode):
+    """Cornell scene whose mesh is a tessellated, displaced sphere (nearest-hit semantics), set on both sides"""
+    syn = _syn(pkg)
+    pos, nrm, tris = syn.cube_sphere(nseg, radius=0.9, center=(0.3, 1.2, 2.6))
+    osc = ob.OracleScene()
+    osc.set_mesh(pos, nrm, tris)
+    pkg.set_partition(0, 1)
+    gs = pkg.Scene(); gs.Init()
+    gs.set_mesh(pos, nrm, tris, mesh_mode=mode)
+    return gs, osc
+
+
+@pytest.mark.parametrize("nseg", [2, 24])              # 48 triangles: constant-memory loop; 6912 triangles: LBVH
+def test_render_with_nearest_mesh_bit_exact(pkg, ob, nseg):
+    gs, osc = _mesh_scene(pkg, ob, nseg, pkg.MESH_NEAREST)
+    w, h = 96, 72
+    g = gs.primary_hits(w, h); o = osc.primary_hits(w, h, mesh_mode=ob.MESH_NEAREST)
+    for f in g.dtype.names:
+        a, b = g[f], o[f]
+        if a.dtype.kind == "f":
+            a, b = _bits(a), _bits(b)
+        assert np.array_equal(a, b), f
+    assert ((g["prim_type"] == 2) & (g["is_hit"] == 1)).sum() > 100
+    rt = pkg.Ray_Tracer(); rt.Threads_Num = 2; rt.seed = 31
+    rt.Init_Render(pkg.PT_MIS); rt.Resize_Viewport(w, h)
+    hdr = rt.Render_Pass(read_hdr=True)
+    acc, rays = osc.render(ob.make_params(w, h, ob.PT_MIS, passes=2, seed=31, mesh_mode=ob.MESH_NEAREST))
+    assert np.array_equal(_bits(hdr[..., :3]), _bits(acc))
+    assert int(rt.last_stats.rays + rt.last_stats.hoisted_rays) == rays
+
+
+def test_reference_bf_mode_rejects_big_meshes(pkg, ob):
+    syn = _syn(pkg)
+    pos, nrm, tris = syn.cube_sphere(8)
+    gs = pkg.Scene(); gs.Init()
+    with pytest.raises(pkg.GCoreError):
+        gs.set_mesh(pos, nrm, tris, mesh_mode=pkg.MESH_REFERENCE_BF)    # brute-force reference semantics: <= 64 triangles
+    gs.Init()
