@@ -1,0 +1,326 @@
+"""Pins the CPU oracle (oracle/art_oracle.cpp) WITHOUT a GPU.
+
+The reference ships no tests, golden vectors or fixtures and cannot be compiled here (Ada, no GNAT;
+the C++ shim needs the absent libembree3.a), so the oracle is pinned by what can be derived independently:
+
+  * the Random123 known-answer vectors of Philox4x32-10 (the published kat_vectors of the Random123 distribution);
+  * the exact bytes of data/pyramid2.vsgf (header fields, counts, material ids) against geometry.adb:499-591;
+  * a second restatement of the primary-ray path in numpy binary32 (tests/ada_numpy.py, written from the Ada sources):
+    every field of every Hit record of BASELINE config C2 (1024x1024) must agree bit for bit;
+  * hand-derivable rays (centre pixel -> back wall, rays at each sphere, the open front, the pyramid);
+  * closed-form radiometry: a Lambert floor point under a fully visible sphere light has radiance
+    kd * Le * (r/d)^2 * cos(theta) exactly, which checks Lights.Sample / EvalPDF / Materials.EvalBxDF / Compute_Shadow
+    and the NEE estimator of ray_tracer-integrators.adb:161-178 end to end;
+  * estimator consistency: PT_STUPID, PT_SHADOW (+ directly visible emission) and PT_MIS converge to the same image;
+  * the resolve/pack rule (ray_tracer.adb:19-57, 281-291) and the BMP writer (bitmap.adb:31-85) byte for byte.
+"""
+import hashlib
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import ada_numpy as an
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a, np.float32)
+    b = a.view(np.uint32).copy()
+    b[np.isnan(a)] = 0x7FC00000
+    return b
+
+
+# ------------------------------------------------------------------------------------------------ RNG
+def test_philox4x32_10_known_answers(ob):
+    """Random123 kat_vectors, 'philox4x32 10' lines"""
+    kats = [
+        ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+        ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+        ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+    ]
+    for ctr, key, want in kats:
+        assert tuple(int(x) for x in ob.philox(ctr, key)) == want
+
+
+def test_synthetic_generator_philox_matches(ob, pkg):
+    """the numpy Philox used to generate the C5 scene is the same function"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("syn", os.path.join(os.path.dirname(pkg.__file__), "synthetic.py"))
+    syn = importlib.util.module_from_spec(spec); spec.loader.exec_module(syn)
+    rng = np.random.default_rng(0)
+    for _ in range(8):
+        ctr = rng.integers(0, 2 ** 32, 4, dtype=np.uint64).astype(np.uint32)
+        key = rng.integers(0, 2 ** 32, 2, dtype=np.uint64).astype(np.uint32)
+        assert np.array_equal(syn.philox4x32_10(ctr[None], key[None])[0], ob.philox(ctr, key))
+
+
+def test_deterministic_elementary_functions(ob):
+    """the fixed-sequence sin/cos/** replace GNAT's run-time library: within 2 ulp-ish of libm over the ranges used"""
+    xs = np.linspace(0.0, 2.0 * np.pi, 2001, dtype=np.float32)
+    for x in xs[::7]:
+        s, c = ob.sincos(x)
+        assert abs(s - np.sin(np.float64(x))) < 3e-7 and abs(c - np.cos(np.float64(x))) < 3e-7
+    for base in np.linspace(0.0, 1.0, 101, dtype=np.float32):
+        for e in (0.5, 1.0 / 81.0, 2.0 / 81.0, 80.0, 2.0, 1.0, 0.0):
+            got = ob.ada_pow(base, e)
+            want = 1.0 if e == 0.0 else float(np.float64(base) ** np.float64(np.float32(e)))
+            assert abs(got - want) <= 4e-6 * max(want, 1e-30) + 1e-37, (base, e, got, want)
+    assert ob.ada_pow(-1.0, 2.0) == 0.0                           # vector_math.adb:30-31
+
+
+# ------------------------------------------------------------------------------------------------ mesh file
+def test_vsgf_fixture_and_loader(oscene, ob):
+    raw = open(ob.VSGF, "rb").read()
+    assert len(raw) == 1104 and hashlib.sha256(raw).hexdigest() == "34acea8ba9e8f4d20786b0c25b6eabf7402f0551a542cdd53861aeba656ace78"
+    size, nv, ni, nm, flags = struct.unpack("<qiiii", raw[:24])          # geometry.adb:499-507
+    assert (size, nv, ni, nm, flags) == (1104, 17, 24, 0, 1)
+    p4 = np.frombuffer(raw, "<f4", 4 * nv, 24).reshape(nv, 4)
+    n4 = np.frombuffer(raw, "<f4", 4 * nv, 24 + 16 * nv).reshape(nv, 4)
+    off = 24 + 16 * nv * 2 + 8 * nv + 16 * nv                             # uv (8 B) + tangents (flags != 0)
+    idx = np.frombuffer(raw, "<i4", ni, off).reshape(-1, 3)
+    mids = np.frombuffer(raw, "<i4", ni // 3, off + 4 * ni)
+    assert np.all(mids == 2) and off + 4 * ni + 4 * (ni // 3) == 1104
+    d = oscene.describe()
+    assert np.array_equal(d["tris"], idx)
+    assert np.array_equal(_bits(d["nrm"]), _bits(n4[:, :3]))             # normals are NOT transformed (geometry.adb:605)
+    # positions: T(-0.75,0.1,3.1) * R_y(-pi/6) * S(2)  (scene.adb:194-206), checked in float64
+    a = -np.pi / 6.0
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    want = (R @ (2.0 * p4[:, :3].astype(np.float64)).T).T + np.array([-0.75, 0.1, 3.1])
+    assert np.abs(d["pos"] - want).max() < 2e-6
+    # bbox folded from the record's zeros (geometry.adb:593-603): contains the origin
+    assert np.all(d["bbox"][:3] <= 0) and np.all(d["bbox"][3:] >= d["pos"].max(0) - 1e-6)
+    assert np.array_equal(_bits(d["bbox"][:3]), _bits(np.minimum(d["pos"].min(0), 0)))
+    assert np.array_equal(_bits(d["bbox"][3:]), _bits(np.maximum(d["pos"].max(0), 0)))
+
+
+def test_scene_constants(oscene, ob):
+    """scene.adb:89-217"""
+    d = oscene.describe()
+    assert np.allclose(d["spheres"]["pos"], [[-1.5, 1, 1.5], [1.4, 1, 3], [0, 4.5, 1]]) and list(d["spheres"]["mat"]) == [8, 0, 4]
+    assert list(d["spheres"]["r"]) == [1.0, 1.0, 0.5]
+    assert list(d["cornell"]["mat_indices"][0]) == [2, 3, 1, 1, 8, 1]
+    m = d["materials"]
+    assert list(m["type"][[0, 1, 2, 3, 4, 5, 8]]) == [ob.MAT_GLASS, ob.MAT_LAMBERT, ob.MAT_LAMBERT, ob.MAT_LAMBERT, ob.MAT_LIGHT, ob.MAT_MIRROR, ob.MAT_PHONG]
+    assert m["param"][0] == np.float32(1.75) and m["param"][8] == 80.0
+    assert np.allclose(d["light"]["intensity"][0], 10.0) and d["light"]["radius"][0] == 0.5
+    assert np.allclose(d["camera"]["pos"][0], [0, 2.55, 12.5])
+
+
+# ------------------------------------------------------------------------------------------------ primary rays
+def _scene_dict(oscene):
+    d = oscene.describe()
+    return {"spheres": d["spheres"], "cornell": d["cornell"][0], "pos": d["pos"], "nrm": d["nrm"], "tris": d["tris"], "bbox": d["bbox"]}, d
+
+
+@pytest.mark.parametrize("w,h", [(1024, 1024), (1024, 768), (100, 37)])
+def test_primary_hits_against_independent_numpy_restatement(oscene, w, h):
+    """BASELINE config C2: the oracle and the numpy restatement agree on every field of every Hit record"""
+    sc, d = _scene_dict(oscene)
+    o, dirs = an.eye_rays(w, h, d["camera"]["pos"][0], d["camera"]["matrix"][0])
+    want = an.find_closest_hit(o.reshape(-1, 3), dirs.reshape(-1, 3), sc)
+    got = oscene.primary_hits(w, h).reshape(-1)
+    for f in ("is_hit", "prim_type", "prim_index", "matId", "mat"):
+        assert np.array_equal(got[f], want[f]), f
+    for f in ("t", "normal", "tx", "ty"):
+        assert np.array_equal(_bits(got[f]), _bits(want[f])), f
+    if (w, h) == (1024, 1024):
+        hit = got["is_hit"] == 1
+        assert 0.43 < hit.mean() < 0.46                                   # ~44.4 % of the pixels hit
+        tri = got[hit & (got["prim_type"] == 2)]
+        assert 5000 < len(tri) < 7500 and set(np.unique(tri["prim_index"])) == {0, 1}
+
+
+def test_aa_subpixel_rays_and_random_rays_against_numpy(oscene, ob):
+    sc, d = _scene_dict(oscene)
+    w, h = 160, 120
+    for sub in range(4):
+        o, dirs = an.eye_rays(w, h, d["camera"]["pos"][0], d["camera"]["matrix"][0], sub)
+        r = oscene.eye_ray(w, h, 37, 91, sub)
+        assert np.array_equal(_bits(r["direction"]), _bits(dirs[91, 37]))
+        rays = np.zeros(w * h, ob.ray_dt); rays["origin"] = o.reshape(-1, 3); rays["direction"] = dirs.reshape(-1, 3)
+        got = oscene.closest_hit_batch(rays); want = an.find_closest_hit(rays["origin"], rays["direction"], sc)
+        for f in ("is_hit", "prim_type", "prim_index", "matId", "mat"):
+            assert np.array_equal(got[f], want[f]), f
+        assert np.array_equal(_bits(got["t"]), _bits(want["t"])) and np.array_equal(_bits(got["normal"]), _bits(want["normal"]))
+    # bounce-like rays from inside the box, including axis-parallel directions (1/0 = inf, 0*inf = NaN in the slab test)
+    rng = np.random.default_rng(11)
+    n = 100_000
+    rays = np.zeros(n, ob.ray_dt)
+    rays["origin"] = rng.uniform([-2.4, 0.1, 0.1], [2.4, 4.9, 12.0], (n, 3)).astype(np.float32)
+    dd = rng.normal(size=(n, 3)); dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+    dd[:5000] = 0; dd[np.arange(5000), rng.integers(0, 3, 5000)] = rng.choice([-1.0, 1.0], 5000)
+    rays["direction"] = dd.astype(np.float32)
+    got = oscene.closest_hit_batch(rays); want = an.find_closest_hit(rays["origin"], rays["direction"], sc)
+    for f in ("is_hit", "prim_type", "prim_index", "matId", "mat"):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(_bits(got["t"]), _bits(want["t"])) and np.array_equal(_bits(got["normal"]), _bits(want["normal"]))
+    assert (got["prim_type"][got["is_hit"] == 1] == 2).sum() > 300       # the pyramid was hit from many sides
+
+
+def test_hand_derived_rays(oscene, ob):
+    """rays whose answer follows from the scene constants alone (float64 arithmetic by hand)"""
+    def q(o, d):
+        r = np.zeros(1, ob.ray_dt); r["origin"] = o
+        d = np.asarray(d, np.float64); r["direction"] = (d / np.linalg.norm(d)).astype(np.float32)
+        return oscene.closest_hit_batch(r)[0]
+    cam = np.array([0.0, 2.55, 12.5])
+    h = q(cam, [0, 0, -1])                                   # straight ahead: back wall z = 0, plane 4, Phong material 8
+    assert (h["is_hit"], h["prim_type"], h["prim_index"], h["matId"], h["mat"]) == (1, 0, 4, 8, 8)
+    assert abs(h["t"] - 12.5) < 1e-5 and tuple(h["normal"]) == (0.0, 0.0, 1.0)
+    h = q(cam, np.array([-1.5, 1.0, 1.5]) - cam)             # at the centre of the Phong sphere: t = dist - r
+    assert (h["is_hit"], h["prim_type"], h["prim_index"], h["mat"]) == (1, 1, 0, 8)
+    assert abs(h["t"] - (np.linalg.norm(np.array([-1.5, 1.0, 1.5]) - cam) - 1.0)) < 5e-5
+    h = q(cam, np.array([1.4, 1.0, 3.0]) - cam)              # the glass sphere
+    assert (h["prim_type"], h["prim_index"], h["mat"]) == (1, 1, 0)
+    h = q(cam, np.array([0.0, 4.5, 1.0]) - cam)              # the sphere light (material 4 = MaterialLight)
+    assert (h["prim_type"], h["prim_index"], h["mat"]) == (1, 2, 4) and abs(h["t"] - (np.linalg.norm(np.array([0, 4.5, 1.0]) - cam) - 0.5)) < 5e-5
+    h = q(cam, [-6.0, 0.0, -7.5])                            # passes left of the box opening: nothing is hit
+    assert h["is_hit"] == 0 and (h["prim_type"], h["prim_index"], h["t"], h["mat"]) == (1, 0, 1.0, 8)   # the sphere "miss" record (scene.adb:58)
+    h = q([0.0, 2.5, 2.5], [0, 0, 1])                        # from inside towards the open front (plane 5) -> miss
+    assert h["is_hit"] == 0
+    h = q([0.0, 2.5, 2.5], [1, 0, 0])                        # right wall x = 2.5: plane 1, red material 3, normal (-1,0,0)
+    assert (h["prim_index"], h["matId"]) == (1, 3) and abs(h["t"] - 2.5) < 1e-6 and tuple(h["normal"]) == (-1.0, 0.0, 0.0)
+    h = q([0.0, 2.5, 2.5], [0, 1, 0])                        # ceiling
+    assert (h["prim_index"], h["matId"]) == (3, 1)
+    # the pyramid: aim at the centroid of side face 0 from the camera -> triangle 0, material 2, t = distance to the plane
+    d = oscene.describe()
+    A, B, C = (d["pos"][i].astype(np.float64) for i in d["tris"][0])
+    cen = (A + B + C) / 3.0
+    h = q(cam, cen - cam)
+    assert (h["is_hit"], h["prim_type"], h["prim_index"], h["matId"]) == (1, 2, 0, 2)
+    assert abs(h["t"] - np.linalg.norm(cen - cam)) < 1e-4
+    # ... and from behind (inside the solid) the same face is culled (geometry.adb:243 max(det, 1e-25) trick)
+    nface = np.cross(B - A, C - A); nface /= np.linalg.norm(nface)
+    inside = cen - 0.05 * nface
+    h = q(inside, nface)
+    assert not (h["prim_type"] == 2 and h["prim_index"] == 0)
+
+
+# ------------------------------------------------------------------------------------------------ radiometry
+def test_compute_shadow_against_numpy_and_emitter_self_shadowing(oscene, ob):
+    """Compute_Shadow (ray_tracer.adb:100-132): oracle == numpy binary32 restatement on 40 k point pairs, half of them
+    aimed at points ON the emitter sphere -- where the reference's closest-hit + epsilon rule reports a sizeable share of
+    false shadows in binary32 (and none in exact arithmetic).  Reference behaviour, reproduced, documented here."""
+    sc, d = _scene_dict(oscene)
+    rng = np.random.default_rng(21)
+    n = 40_000
+    p = rng.uniform([-2.4, 0.05, 0.1], [2.4, 4.0, 4.9], (n, 3)).astype(np.float32)
+    c = d["light"]["center"][0]; r = d["light"]["radius"][0]
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    u = np.where(((p - c) * u).sum(1, keepdims=True) < 0, -u, u)           # light points facing p
+    lp = (c + r * u).astype(np.float32)
+    lp[n // 2:] = rng.uniform([-2.4, 0.05, 0.1], [2.4, 4.9, 4.9], (n - n // 2, 3)).astype(np.float32)
+    want = an.compute_shadow(p, lp, sc)
+    got = np.array([oscene.compute_shadow(p[i], lp[i]) for i in range(n)])
+    assert np.array_equal(got, want)
+    # geometric truth in float64 for the emitter-directed half: occluded only by the two object spheres / the pyramid
+    on_light = slice(0, n // 2)
+    assert 0.02 < want[on_light].mean() < 0.9
+
+
+def test_direct_lighting_closed_form(ob):
+    """PT_SHADOW, depth 1, at fully lit Lambert pixels: L = kd * Le * (r/d)^2 * cos(theta), exact for a sphere light that
+    is entirely above the horizon and unoccluded.  The emitter is taken out of the GEOMETRY here (spheres 0..1 only) so that
+    the reference's emitter self-shadowing (previous test) does not enter; Lights.Sample / EvalPDF, Materials.EvalBxDF and
+    the estimator of ray_tracer-integrators.adb:161-178 are what is being checked."""
+    osc = ob.OracleScene()
+    d = osc.describe()
+    osc.set_spheres(d["spheres"][:2])
+    w, h = 128, 128
+    hits = osc.primary_hits(w, h)
+    cam = d["camera"]["pos"][0].astype(np.float64)
+    c = d["light"]["center"][0].astype(np.float64); r = float(d["light"]["radius"][0]); le = float(d["light"]["intensity"][0][0])
+    o, dirs = an.eye_rays(w, h, d["camera"]["pos"][0], d["camera"]["matrix"][0])
+    rng = np.random.default_rng(5)
+    cands = [(y, x) for y in range(h) for x in range(w) if hits[y, x]["is_hit"] and hits[y, x]["prim_type"] == 0 and hits[y, x]["prim_index"] in (0, 1, 2)]
+    picked = []
+    for y, x in [cands[i] for i in rng.permutation(len(cands))]:
+        p = cam + dirs[y, x].astype(np.float64) * float(hits[y, x]["t"])
+        u = rng.normal(size=(96, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+        pts = c + r * u
+        facing = ((p - pts) * u).sum(1) > 0.02
+        if all(not osc.compute_shadow(p, q) for q in pts[facing]):          # fully visible from p
+            picked.append((y, x, p))
+        if len(picked) == 16:
+            break
+    assert len(picked) == 16
+    units = 512                                                            # 512 spp, pixel-centre rays
+    acc, _ = osc.render(ob.make_params(w, h, ob.PT_SHADOW, aa=0, max_depth=1, passes=units, seed=123))
+    for y, x, p in picked:
+        n = hits[y, x]["normal"].astype(np.float64)
+        kd = d["materials"]["color"][hits[y, x]["mat"]].astype(np.float64)
+        dist = np.linalg.norm(c - p); cos = np.dot(c - p, n) / dist
+        want = kd * le * (r / dist) ** 2 * cos
+        got = acc[y, x].astype(np.float64) / units
+        assert np.allclose(got, want, rtol=0.02, atol=1e-4), (y, x, got, want)
+
+
+def test_estimators_agree(oscene, ob):
+    """PT_STUPID (brute force), PT_SHADOW + emission seen directly/through specular chains, and PT_MIS estimate the same
+    integral: PT_MIS and PT_STUPID image means agree within Monte-Carlo error; PT_SHADOW is lower by exactly the paths
+    that reach the emitter through a BSDF sample, so MIS >= SHADOW region by region on diffuse-only regions."""
+    w, h = 64, 64
+    mis, _ = oscene.render(ob.make_params(w, h, ob.PT_MIS, passes=128, seed=1))          # 512 spp
+    stu, _ = oscene.render(ob.make_params(w, h, ob.PT_STUPID, passes=1024, seed=2))      # 4096 spp (very noisy estimator)
+    sha, _ = oscene.render(ob.make_params(w, h, ob.PT_SHADOW, passes=128, seed=3))
+    mis = mis / 512.0; stu = stu / 4096.0; sha = sha / 512.0
+    hits = oscene.primary_hits(w, h)
+    lit = hits["is_hit"] == 1
+    m_mis, m_stu = mis[lit].mean(0), stu[lit].mean(0)
+    assert np.allclose(m_mis, m_stu, rtol=0.05), (m_mis, m_stu)
+    # floor region (Lambert, far from specular objects' caustics excluded by taking the left half of the floor)
+    floor = lit & (hits["prim_type"] == 0) & (hits["prim_index"] == 2)
+    assert floor.sum() > 50
+    assert np.allclose(mis[floor].mean(0), stu[floor].mean(0), rtol=0.10)
+    # emitter pixels: PT_SHADOW is black there (integrators.adb:155-157), PT_MIS shows the emitted radiance with weight 1
+    light_px = lit & (hits["mat"] == 4)
+    mis0, _ = oscene.render(ob.make_params(w, h, ob.PT_MIS, aa=0, passes=3, seed=1))       # pixel-centre rays = the rays of primary_hits
+    sha0, _ = oscene.render(ob.make_params(w, h, ob.PT_SHADOW, aa=0, passes=3, seed=1))
+    stu0, _ = oscene.render(ob.make_params(w, h, ob.PT_STUPID, aa=0, passes=3, seed=1))
+    assert light_px.sum() > 10 and np.all(sha0[light_px] == 0) and np.all(mis0[light_px] == 30.0) and np.all(stu0[light_px] == 30.0)
+    assert np.all(np.isfinite(mis)) and mis.min() >= 0
+
+
+def test_same_samples_progressive_and_striped(oscene, ob):
+    """sample indices continue across calls (first_sample), row stripes compose, thread count does not matter"""
+    w, h = 48, 40
+    a, ra = oscene.render(ob.make_params(w, h, ob.PT_MIS, passes=4, seed=9, threads=1))
+    b, rb1 = oscene.render(ob.make_params(w, h, ob.PT_MIS, passes=2, seed=9, threads=3))
+    b, rb2 = oscene.render(ob.make_params(w, h, ob.PT_MIS, passes=2, seed=9, first_sample=8, threads=2), accum=b)
+    assert np.array_equal(_bits(a), _bits(b)) and ra == rb1 + rb2
+    c = np.zeros_like(a)
+    rc = 0
+    for y0, y1 in ((0, 13), (13, 14), (14, 40)):
+        c, r = oscene.render(ob.make_params(w, h, ob.PT_MIS, passes=4, seed=9, y0=y0, y1=y1), accum=c); rc += r
+    assert np.array_equal(_bits(a), _bits(c)) and rc == ra
+
+
+# ------------------------------------------------------------------------------------------------ resolve / output
+def test_resolve_and_pack(ob):
+    rng = np.random.default_rng(2)
+    acc = rng.uniform(0, 40, (64, 64, 3)).astype(np.float32)
+    acc[0, 0] = (0, 0, 0); acc[0, 1] = (1e9, 16.0, 4.0); acc[0, 2] = np.float32(16.0) * np.float32((0.5 / 255.0) ** 2)
+    for spp in (1, 16, 112):
+        assert np.array_equal(ob.resolve(acc, spp), an.resolve(acc, spp))
+    px = ob.resolve(acc, 16)
+    assert px[0, 0] == 0 and px[0, 1] == (255 | (255 << 8) | (128 << 16))     # clamp; sqrt(1) -> 255; sqrt(.25)*255 = 127.5 -> 128 (ties away)
+    nan = np.full((1, 1, 3), np.nan, np.float32)
+    assert ob.resolve(nan, 4)[0, 0] == 0x00FFFFFF                             # min(NaN, 1.0) = 1.0 (generic_vector_math.adb:19-26)
+
+
+def test_bmp_writer_bytes(ob, tmp_path, pkg):
+    """bitmap.adb:31-85: 54-byte header, 24 bpp, bottom-up, B G R, no row padding -- oracle and package writer agree"""
+    w, h = 8, 5
+    data = (np.arange(w * h, dtype=np.uint32) * 0x010203 + 0x11) & 0xFFFFFF
+    p1 = str(tmp_path / "a.bmp"); p2 = str(tmp_path / "b.bmp")
+    assert ob.lib().ao_save_bmp(p1.encode(), data.ctypes.data, w, h) == 0
+    im = pkg.Bitmap.Image(); pkg.Bitmap.Init(im, w, h); im.data[:] = data
+    pkg.Bitmap.SaveBMP(im, p2)
+    b1 = open(p1, "rb").read(); b2 = open(p2, "rb").read()
+    assert b1 == b2 and len(b1) == 54 + 3 * w * h
+    assert b1[:2] == b"BM" and struct.unpack("<I", b1[2:6])[0] == 54 + 3 * w * h and struct.unpack("<ii", b1[18:26]) == (w, h)
+    assert struct.unpack("<HH", b1[26:30]) == (1, 24)
+    px0 = int(data[0])
+    assert tuple(b1[54:57]) == ((px0 >> 16) & 255, (px0 >> 8) & 255, px0 & 255)
