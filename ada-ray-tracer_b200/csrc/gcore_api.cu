@@ -7,12 +7,14 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
 
 using gcore_dev::LbvhBuffers;
 using gcore_dev::RenderArgs;
+using gcore_dev::WaveBuffers;
 
 namespace {
 
@@ -50,6 +52,8 @@ struct State {
   unsigned long long* d_rays = nullptr;      // 3 cumulative counters: rays, mesh-bbox queries, bounces
   unsigned long long last_counters[4] = {0, 0, 0, 0};
   float4* d_hdr = nullptr; uint32_t* d_ldr = nullptr; size_t out_pixels = 0;
+  WaveBuffers wave;                          // work buffers of the wavefront render kernel
+  int sm_count = 0;
 
   int  err_code = 0;
   std::string err_text;
@@ -128,6 +132,28 @@ int alloc_accum() {
   CU(cudaMemsetAsync(s.d_rays, 0, 4 * sizeof(unsigned long long), s.stream), "memset counters");
   s.last_counters[0] = s.last_counters[1] = s.last_counters[2] = s.last_counters[3] = 0;
   s.spp = 0;
+  return 0;
+}
+
+// work buffers of render_wave_kernel: per-slot recursion stacks (fixed size) and the (pass, pixel) colour buffer
+#define GC_COLBUF_CAP_BYTES ((size_t)2 << 30)
+int ensure_wave_buffers(size_t items) {
+  State& s = S();
+  if (!s.wave.grid) {
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, s.device), "cudaGetDeviceProperties");
+    s.sm_count = prop.multiProcessorCount;
+    s.wave.grid = s.sm_count * gcore_dev::wave_blocks_per_sm();             // persistent: one wave of resident blocks
+    const size_t total_slots = (size_t)s.wave.grid * gcore_dev::wave_slots_per_block();
+    CU(cudaMalloc(&s.wave.stackA, sizeof(float4) * total_slots * gcore_dev::wave_max_depth()), "cudaMalloc stackA");
+    CU(cudaMalloc(&s.wave.stackB, sizeof(float2) * total_slots * gcore_dev::wave_max_depth()), "cudaMalloc stackB");
+    CU(cudaMalloc(&s.wave.next_item, sizeof(unsigned int)), "cudaMalloc next_item");
+  }
+  if (items > s.wave.colbuf_items) {
+    if (s.wave.colbuf) { cudaFree(s.wave.colbuf); s.wave.colbuf = nullptr; s.wave.colbuf_items = 0; }
+    CU(cudaMalloc(&s.wave.colbuf, sizeof(float4) * items), "cudaMalloc colbuf");
+    s.wave.colbuf_items = items;
+  }
   return 0;
 }
 
@@ -283,10 +309,27 @@ int render_units_locked(int units, gcore_render_stats* stats) {
     launches = 1; samples = pixels;
     if (s.spp == 0) s.spp = 1;
   } else if (units > 0) {
-    CU(gcore_dev::launch_render(s.cfg.render_type, s.hs.mesh_kind, a, s.stream), "render_kernel");
-    launches = 1;
     const int per = s.cfg.anti_aliasing ? 4 : 1;
-    s.spp += units * per;                                                // ray_tracer.adb:168-176
+    static const bool use_mega = getenv("GCORE_AB_MEGAKERNEL") != nullptr;   // A/B experiments only (to be removed)
+    if (use_mega) {
+      CU(gcore_dev::launch_render(s.cfg.render_type, s.hs.mesh_kind, a, s.stream), "render_kernel");
+      launches = 1; s.spp += units * per;
+    } else {
+    // the colour buffer holds one float4 per (pass, pixel): long renders go in chunks of passes
+    size_t chunk = GC_COLBUF_CAP_BYTES / (sizeof(float4) * (size_t)s.nslots);
+    if (chunk < 1) chunk = 1;
+    if (chunk > (size_t)units) chunk = (size_t)units;
+    while ((chunk * (size_t)s.nslots) >> 31) chunk >>= 1;
+    if (chunk < 1) return fail(GCORE_E_LIMIT, "viewport too large for the work-item counter");
+    if (int rc = ensure_wave_buffers(chunk * (size_t)s.nslots)) return rc;
+    for (int done = 0; done < units; done += (int)chunk) {
+      const int n = (units - done < (int)chunk) ? (units - done) : (int)chunk;
+      a.passes = n; a.first_sample = s.spp;
+      CU(gcore_dev::launch_render_wave(s.cfg.render_type, s.hs.mesh_kind, a, s.wave, n, s.stream), "render_wave_kernel");
+      launches += 2;
+      s.spp += n * per;                                                  // ray_tracer.adb:168-176
+    }
+    }
     samples = pixels * (uint64_t)(units * per);
   }
   CU(cudaEventRecord(s.ev1, s.stream), "event");

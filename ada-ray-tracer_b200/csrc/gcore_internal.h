@@ -44,6 +44,21 @@ cudaError_t launch_resolve(const RenderArgs& a, int spp, float4* d_hdr4, uint32_
 cudaError_t launch_resolve_gathered(const RenderArgs& a, const float4* d_all, int spp, float4* d_hdr4, uint32_t* d_ldr, cudaStream_t s);
 int render_kernel_regs(int render_type);
 
+// ---- block-synchronous wavefront render (render_wave.cuh): persistent grid of `grid` blocks ----
+struct WaveBuffers {
+  float4* colbuf = nullptr;              // [units][nslots] colour of every (pass, pixel) work item
+  size_t  colbuf_items = 0;
+  float4* stackA = nullptr;              // [max_depth][grid * slots_per_block] per-bounce (explicit.xyz, weight.x)
+  float2* stackB = nullptr;              //                                                (weight.y, weight.z)
+  unsigned int* next_item = nullptr;     // global work counter
+  int     grid = 0;
+};
+int wave_slots_per_block();
+int wave_blocks_per_sm();
+int wave_max_depth();
+// `units` DoPass units over this rank's slots (units * nslots < 2^31): wavefront kernel + fold into a.accum
+cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, cudaStream_t s);
+
 // ---- lbvh_build.cu ----
 struct LbvhBuffers {                     // device allocations owned by the builder
   float4* nodes = nullptr; float4* tris = nullptr; float* tri_normals = nullptr;

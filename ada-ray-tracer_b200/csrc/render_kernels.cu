@@ -18,6 +18,7 @@
 //   resolve_kernel      K6b/K7: slot-major accumulator(s) -> row-major HDR float4 and LDR u32 (ray_tracer.adb:281-291).
 #include "gcore_internal.h"
 #include "art_shade.cuh"
+#include "render_wave.cuh"
 
 using namespace art;
 
@@ -431,13 +432,52 @@ cudaError_t launch_resolve_gathered(const RenderArgs& a, const float4* d_all, in
   return cudaGetLastError();
 }
 
+// ---- block-synchronous wavefront render (render_wave.cuh) ----
+template <int RT, int MESHK>
+static cudaError_t launch_wave_t(const art::WaveArgs& wa, int grid, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(art::render_wave_kernel<RT, MESHK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(art::WaveSmem));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  art::render_wave_kernel<RT, MESHK><<<grid, WAVE_THREADS, sizeof(art::WaveSmem), s>>>(wa);
+  return cudaGetLastError();
+}
+
+template <int MESHK>
+static cudaError_t launch_wave_m(int render_type, const art::WaveArgs& wa, int grid, cudaStream_t s) {
+  switch (render_type) {
+    case GCORE_PT_STUPID: return launch_wave_t<GCORE_PT_STUPID, MESHK>(wa, grid, s);
+    case GCORE_PT_SHADOW: return launch_wave_t<GCORE_PT_SHADOW, MESHK>(wa, grid, s);
+    case GCORE_PT_MIS:    return launch_wave_t<GCORE_PT_MIS, MESHK>(wa, grid, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+int wave_slots_per_block() { return WAVE_NS; }
+int wave_blocks_per_sm() { return WAVE_MINB; }
+int wave_max_depth() { return WAVE_MAX_DEPTH; }
+
+cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, cudaStream_t s) {
+  if (a.nslots <= 0 || units <= 0) return cudaSuccess;
+  art::WaveArgs wa;
+  wa.r = a; wa.colbuf = wb.colbuf; wa.stackA = wb.stackA; wa.stackB = wb.stackB; wa.next_item = wb.next_item; wa.units = units;
+  cudaError_t e = cudaMemsetAsync(wb.next_item, 0, sizeof(unsigned int), s);
+  if (e != cudaSuccess) return e;
+  e = (mesh_kind == 2) ? launch_wave_m<MESHK_BVH>(render_type, wa, wb.grid, s) : launch_wave_m<MESHK_CONST>(render_type, wa, wb.grid, s);
+  if (e != cudaSuccess) return e;
+  art::fold_kernel<<<blocks_for(a.nslots, 256), 256, 0, s>>>(a, wb.colbuf, units);
+  return cudaGetLastError();
+}
+
 int render_kernel_regs(int render_type) {
   cudaFuncAttributes at;
   cudaError_t e;
   switch (render_type) {
-    case GCORE_PT_STUPID: e = cudaFuncGetAttributes(&at, render_kernel<GCORE_PT_STUPID, MESHK_CONST>); break;
-    case GCORE_PT_SHADOW: e = cudaFuncGetAttributes(&at, render_kernel<GCORE_PT_SHADOW, MESHK_CONST>); break;
-    default:              e = cudaFuncGetAttributes(&at, render_kernel<GCORE_PT_MIS, MESHK_CONST>); break;
+    case GCORE_PT_STUPID: e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_STUPID, MESHK_CONST>); break;
+    case GCORE_PT_SHADOW: e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_SHADOW, MESHK_CONST>); break;
+    default:              e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_MIS, MESHK_CONST>); break;
   }
   if (e != cudaSuccess) { cudaGetLastError(); return -1; }
   return at.numRegs;

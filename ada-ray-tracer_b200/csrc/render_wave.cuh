@@ -1,0 +1,576 @@
+// render_wave.cuh -- the render hot path as a block-synchronous wavefront (K1+K2+K4+K5+K6a of SURVEY 2b).
+//
+// Replaces ray_tracer-integrators.adb:25-301 (DoPass + the three PathTrace variants), ray_tracer.adb:61-132 (camera rays,
+// Compute_Shadow) and the Ada task pool of ray_tracer.adb:142-194.
+//
+// Why this shape.  A one-thread-per-pixel megakernel of this path runs with 12.7 of 32 lanes active and spends 47 % of
+// its stall samples waiting for instructions (profiles/r01_render_megakernel.md): lanes of a warp sit on different
+// materials and bounce depths, the 8-triangle mesh loop runs for ~2 lanes, and 60 KB of inlined code thrash the 32 KB
+// instruction cache.  Here a persistent block owns NS path slots whose state lives in shared memory (SoA), and walks
+// all of them through five stages separated by __syncthreads().  Between stages slots are re-packed into dense queues,
+// so every stage runs with full warps on one small piece of code that all warps of the block execute at the same time:
+//
+//   S1  regenerate   queue R : unwind the finished path (integrators.adb:124,191,299), add its radiance to the pixel-pass
+//                              colour in the reference's order (:42-51), publish the colour when the pass is complete,
+//                              fetch the next work item (pixel, pass), generate the camera ray (ray_tracer.adb:61-97)
+//   S2  mesh         queue T : triangle tests (geometry.adb:231-323) / LBVH traversal for the path rays that reach the mesh
+//   S3  hit + light  all     : spheres, Cornell box, flat light, merge with S2 (scene.adb:56-86); miss / emitter -> path
+//                              ends; surface -> Philox draws, Lights.Sample, shadow ray (ray_tracer.adb:100-116)
+//   S4  shadow mesh  queue T': triangle tests for the shadow rays; counting sort of the surface slots by material type
+//   S5  shade        sorted  : shadow spheres/box + in_shadow rule (ray_tracer.adb:117-128), EvalBxDF/EvalPDF + MIS
+//                              (integrators.adb:161-178, 251-287), SampleAndEvalBxDF (:116,183,291), next ray
+//
+// A work item is one DoPass of one pixel (4 fixed sub-pixel paths, or 1): items are handed out from a global counter,
+// so no slot idles while others finish long paths, and the colour of item (pass k, pixel q) goes to colbuf[k][q].
+// fold_kernel then adds the passes into the accumulator in pass order -- the float additions happen in exactly the
+// reference's order (colBuff(x,y) := color + colBuff(x,y), integrators.adb:51), so the result is bit-identical to the
+// oracle although paths complete out of order.  The recursion's per-bounce terms (explicit light, BSDF weight) are
+// kept on a per-slot stack in global memory (L2-resident) and unwound innermost-first like the recursion returns.
+#pragma once
+
+#include "art_shade.cuh"
+
+namespace art {
+
+#ifndef WAVE_THREADS
+#define WAVE_THREADS 512
+#endif
+#ifndef WAVE_MINB
+#define WAVE_MINB 2
+#endif
+#define WAVE_NS WAVE_THREADS              // path slots per block
+#define WAVE_BATCH (2 * WAVE_NS)          // work items fetched from the global counter at a time
+#define WAVE_MAX_DEPTH 16
+
+enum { ST_DEPTH_MASK = 31, ST_SUB_SHIFT = 5, ST_SPEC = 1 << 7, ST_HASRAY = 1 << 8, ST_FOLD = 1 << 9, ST_SURF = 1 << 10,
+       ST_BUCKET_SHIFT = 11 /* 3 bits */ };
+
+struct WaveSmem {
+  // path ray
+  float ox[WAVE_NS], oy[WAVE_NS], oz[WAVE_NS], dx[WAVE_NS], dy[WAVE_NS], dz[WAVE_NS];
+  // mesh candidate of the path ray (S2) and of the shadow ray (S4); id < 0: none
+  float tri_t[WAVE_NS], tri_u[WAVE_NS], tri_v[WAVE_NS], stri_t[WAVE_NS];
+  int   tri_id[WAVE_NS], stri_id[WAVE_NS];
+  // surface hit + light sample of the current bounce (S3 -> S5)
+  float ht[WAVE_NS], nx[WAVE_NS], ny[WAVE_NS], nz[WAVE_NS];
+  float sx[WAVE_NS], sy[WAVE_NS], sz[WAVE_NS], ls_pdf[WAVE_NS], sh_thi[WAVE_NS];
+  float r1[WAVE_NS], r2[WAVE_NS];
+  float prev_pdf[WAVE_NS];
+  // colour of the work item so far / radiance at the end of the path
+  float cr[WAVE_NS], cg[WAVE_NS], cb[WAVE_NS], lx[WAVE_NS], ly[WAVE_NS], lz[WAVE_NS];
+  int   item[WAVE_NS];                    // unit * nslots + q, or -1: no item
+  int   state[WAVE_NS];                   // depth | sub << 5 | flags
+  short hmat[WAVE_NS], mrank[WAVE_NS];
+  short q_r[2][WAVE_NS], q_t[WAVE_NS], q_ts[WAVE_NS], q_m[WAVE_NS + 5 * 32];
+  int   cnt_r[2], cnt_t, cnt_ts, cnt_m[5], off_m[6];
+  int   pool_next, pool_end, exhausted, retired;
+};
+
+// warp-aggregated append of `slot` to a shared-memory queue (one atomic per warp)
+ART_D void queue_push(bool pred, short* q, int* cnt, int slot) {
+  const unsigned m = __ballot_sync(0xffffffffu, pred);
+  if (m == 0u) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(cnt, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = (short)slot;
+}
+
+struct WaveArgs {
+  gcore_dev::RenderArgs r;
+  float4* colbuf;                         // [units][nslots]
+  float4* stackA;                         // [WAVE_MAX_DEPTH][total_slots]  (E.xyz, W.x)
+  float2* stackB;                         // [WAVE_MAX_DEPTH][total_slots]  (W.y, W.z)
+  unsigned int* next_item;                // global work counter
+  int     units;
+};
+
+// does the ray need the mesh stage?  Counts the reference's bbox entries (the 564-flop queries of SURVEY 8d).
+template <int MESHK>
+ART_D bool mesh_candidate(f3 o, f3 inv, unsigned int& mesh_queries) {
+  if (MESHK == MESHK_CONST) {
+    if (g_scn.ntris_bf <= 0) return false;
+    if (g_scn.mesh_mode == MESH_REFERENCE_BF) {                              // IntersectMeshBF bbox reject, geometry.adb:272-274
+      float t0, t1;
+      if (!intersect_box_inv(o, inv, g_scn.mesh_bmin, g_scn.mesh_bmax, t0, t1)) return false;
+    }
+  } else {
+    if (g_scn.bvh.ntris <= 0) return false;
+  }
+  mesh_queries++;
+  // the reference's bbox also spans the origin (never reset, geometry.adb:593-603): rays that miss the padded tight box
+  // of the vertices cannot pass any triangle test
+  return cull_box_pass(o, inv, g_scn.mesh_tight_min, g_scn.mesh_tight_max);
+}
+
+template <int MESHK>
+ART_D void mesh_query(f3 o, f3 d, float& t_o, float& u_o, float& v_o, int& id_o) {
+  id_o = -1; t_o = 0.0f; u_o = 0.0f; v_o = 0.0f;
+  if (MESHK == MESHK_CONST) {
+    const bool ref_mode = (g_scn.mesh_mode == MESH_REFERENCE_BF);
+    // every triangle in index order against the window (nearest.tmin, nearest.tmax); in reference mode a hit moves the
+    // window to (t, t + 1e-6) (geometry.adb:289-293, 255-256), in nearest mode to (0, t)
+    float w_min = 0.0f, w_max = 1000000.0f;
+#pragma unroll 1
+    for (int i = 0; i < g_scn.ntris_bf; i++) {
+      float t, u, v;
+      if (intersect_triangle(o, d, ld3(g_scn.triA[i]), ld3(g_scn.triE1[i]), ld3(g_scn.triE2[i]), w_min, w_max, t, u, v)) {
+        if (ref_mode) { w_min = t; w_max = t + 1.0e-6f; } else { w_max = t; }
+        t_o = t; u_o = u; v_o = v; id_o = i;
+      }
+    }
+  } else {
+    const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    bvh_closest(g_scn.bvh, o, d, inv, 0.0f, 1000000.0f, id_o, t_o, u_o, v_o);
+  }
+}
+
+// Scene.Find_Closest_Hit (scene.adb:56-86) given the mesh candidate: spheres, Cornell box, flat light in the reference's
+// order, strict '<'; the record is materialised for the winner only (shadow queries read is_hit / t alone)
+template <int MESHK>
+ART_D void closest_with_mesh(f3 o, f3 d, f3 inv, int tri_id, float tri_t, float tri_u, float tri_v, bool want_record, DHit& h) {
+  float min_t = ART_FLT_LAST;                                                 // IntersectAllSpheres, geometry.adb:48-115
+  int   min_i = 0;
+#pragma unroll 1
+  for (int i = 0; i < g_scn.nspheres; i++) {
+    f3 k = mk3(o.x - g_scn.sph[i][0], o.y - g_scn.sph[i][1], o.z - g_scn.sph[i][2]);
+    float b = dot(k, d);
+    float c = dot(k, k) - g_scn.sph[i][3] * g_scn.sph[i][3];
+    float dd = b * b - c;
+    if (dd >= 0.0f) {
+      float sqrtd = sqrtf(dd);
+      float t1 = -b - sqrtd;
+      float t2 = -b + sqrtd;
+      if (t1 > 0.0f && t1 < min_t) { min_t = t1; min_i = i; }
+      else if (t2 > 0.0f && t2 < min_t) { min_t = t2; min_i = i; }
+    }
+  }
+  const bool sph_hit = (min_t > 0.0f && min_t < ART_FLT_LAST);
+  int   winner = 0;
+  float nearestHitDist = ART_FLT_LAST;
+  if (sph_hit && min_t < nearestHitDist) { winner = 0; nearestHitDist = min_t; }
+
+  int box_plane = 0;                                                          // IntersectCornellBox, geometry.adb:193-229
+  {
+    float tmin, tmax;
+    if (intersect_box_inv(o, inv, g_scn.box_min, g_scn.box_max, tmin, tmax)) {
+      if (tmax < nearestHitDist) {
+        f3 p = mk3(o.x + tmax * d.x, o.y + tmax * d.y, o.z + tmax * d.z);
+        const float eps = 1.0e-5f;
+        int planeId = 0;
+        if (fabsf(p.x - g_scn.box_min[0]) < eps) planeId = 0;
+        if (fabsf(p.x - g_scn.box_max[0]) < eps) planeId = 1;
+        if (fabsf(p.y - g_scn.box_min[1]) < eps) planeId = 2;
+        if (fabsf(p.y - g_scn.box_max[1]) < eps) planeId = 3;
+        if (fabsf(p.z - g_scn.box_min[2]) < eps) planeId = 4;
+        if (fabsf(p.z - g_scn.box_max[2]) < eps) planeId = 5;
+        if (planeId != 5) { winner = 1; nearestHitDist = tmax; box_plane = planeId; }
+      }
+    }
+  }
+  if (g_scn.light_shape == LIGHT_RECT) {                                      // IntersectFlatLight, geometry.adb:118-143
+    float tmin = (g_scn.fl_max[1] - o.y) * inv.y;
+    f3 hp = mk3(o.x + tmin * d.x, o.y + tmin * d.y, o.z + tmin * d.z);
+    bool is_hit = (hp.x > g_scn.fl_min[0]) && (hp.x < g_scn.fl_max[0]) && (hp.z > g_scn.fl_min[2]) && (hp.z < g_scn.fl_max[2]) && (tmin >= 0.0f);
+    if (is_hit && tmin < nearestHitDist) { winner = 2; nearestHitDist = tmin; }
+  }
+  if (tri_id >= 0 && tri_t < nearestHitDist) { winner = 3; nearestHitDist = tri_t; }   // IntersectMeshBF result (S2 / S4)
+
+  h.is_hit = (winner == 0) ? (sph_hit ? 1 : 0) : 1;
+  h.t = (winner == 0) ? (sph_hit ? min_t : 1.0f) : nearestHitDist;
+  if (!want_record) return;
+  h.tx = 0.0f; h.ty = 0.0f;
+  if (winner == 0) {
+    h.prim_type = PRIM_SPHERE; h.prim_index = min_i; h.matId = 0;
+    h.mat = (g_scn.nspheres > 0) ? g_scn.sph_mat[min_i] : -1;
+    if (sph_hit) {
+      f3 p = mk3(o.x + min_t * d.x, o.y + min_t * d.y, o.z + min_t * d.z);
+      h.normal = normalize(mk3(p.x - g_scn.sph[min_i][0], p.y - g_scn.sph[min_i][1], p.z - g_scn.sph[min_i][2]));
+    } else { h.normal = mk3(0.0f, 1.0f, 0.0f); }
+  } else if (winner == 1) {
+    h.prim_type = PRIM_PLANE; h.prim_index = box_plane;
+    h.matId = g_scn.box_mat[box_plane]; h.mat = -1;
+    h.normal = ld3(&g_scn.box_nrm[3 * box_plane]);
+  } else if (winner == 2) {
+    h.prim_type = PRIM_QUAD; h.prim_index = 0; h.matId = 0; h.mat = 4;
+    h.normal = mk3(0.0f, -1.0f, 0.0f);
+  } else {
+    h.prim_type = PRIM_TRIANGLE; h.prim_index = tri_id; h.matId = 2; h.mat = -1;
+    const float* n9 = (MESHK == MESHK_CONST) ? g_scn.triN[tri_id] : (g_scn.bvh.tri_normals + 9 * (size_t)tri_id);
+    float w = 1.0f - tri_u - tri_v;                                            // geometry.adb:301
+    h.normal = mk3(w * n9[0] + tri_v * n9[3] + tri_u * n9[6],
+                   w * n9[1] + tri_v * n9[4] + tri_u * n9[7],
+                   w * n9[2] + tri_v * n9[5] + tri_u * n9[8]);
+    h.tx = w * 0.0f + tri_v * 0.0f + tri_u * 0.0f;                             // uvs zeroed by the loader, geometry.adb:565-566
+    h.ty = h.tx;
+  }
+  if (h.mat < 0) h.mat = h.matId;                                              // scene.adb:80-82
+}
+
+// slot q of this rank -> pixel (tile layout shared with the resolve kernel, see render_kernels.cu)
+struct WavePixel { int x, y, active; };
+ART_D WavePixel wave_slot_to_pixel(const gcore_dev::RenderArgs& a, int q) {
+  int tile_local = q >> 10, r = q & 1023;
+  int tile = tile_local * a.world + a.rank;
+  int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+  int w = r >> 5, l = r & 31;
+  WavePixel p;
+  p.x = tx * GC_TILE + (w & 3) * 8 + (l & 7);
+  p.y = ty * GC_TILE + (w >> 2) * 4 + (l >> 3);
+  p.active = (tile < a.ntiles) && (p.x < a.width) && (p.y < a.height);
+  return p;
+}
+
+ART_D f3 wave_eye_ray_dir(const gcore_dev::RenderArgs& a, int x, int y, int sub) {   // ray_tracer.adb:61-97, integrators.adb:46,58
+  const float third = 1.0f / 3.0f, two_thirds = 2.0f / 3.0f;
+  float offx = (sub < 0) ? 0.5f : ((sub & 2) ? two_thirds : third);
+  float offy = (sub < 0) ? 0.5f : ((sub & 1) ? two_thirds : third);
+  f3 r;
+  r.x = (float)x + offx - a.half_w;
+  r.y = (float)y + offy - a.half_h;
+  r.z = a.zdir;
+  r = normalize(r);
+  f3 m;
+  m.x = g_scn.cam_m[0] * r.x + g_scn.cam_m[1] * r.y + g_scn.cam_m[2] * r.z + g_scn.cam_m[3];   // vector_math.adb:137-144
+  m.y = g_scn.cam_m[4] * r.x + g_scn.cam_m[5] * r.y + g_scn.cam_m[6] * r.z + g_scn.cam_m[7];
+  m.z = g_scn.cam_m[8] * r.x + g_scn.cam_m[9] * r.y + g_scn.cam_m[10] * r.z + g_scn.cam_m[11];
+  return normalize(m);
+}
+
+template <int RT, int MESHK>
+__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MINB) render_wave_kernel(const __grid_constant__ WaveArgs wa) {
+  extern __shared__ __align__(16) unsigned char wave_smem_raw[];
+  WaveSmem& S = *reinterpret_cast<WaveSmem*>(wave_smem_raw);
+  const gcore_dev::RenderArgs& a = wa.r;
+  const int tid = threadIdx.x;
+  const int gslot0 = blockIdx.x * WAVE_NS;
+  const int total_slots = gridDim.x * WAVE_NS;
+  const unsigned int total_items = (unsigned int)wa.units * (unsigned int)a.nslots;
+  const int aa = a.anti_aliasing;
+  const int max_depth = a.max_depth;
+  const f3 bg = mk3(a.bg[0], a.bg[1], a.bg[2]);
+  unsigned int nrays = 0, nmesh = 0, nbounce = 0;
+
+  for (int s = tid; s < WAVE_NS; s += WAVE_THREADS) {
+    S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s; S.tri_id[s] = -1; S.stri_id[s] = -1;
+  }
+  if (tid == 0) {
+    S.cnt_r[0] = WAVE_NS; S.cnt_r[1] = 0; S.cnt_t = 0; S.cnt_ts = 0; S.retired = 0; S.exhausted = 0;
+    for (int b = 0; b < 5; b++) S.cnt_m[b] = 0;
+    unsigned int base = atomicAdd(wa.next_item, (unsigned int)WAVE_BATCH);
+    if (base >= total_items) { S.exhausted = 1; S.pool_next = 0; S.pool_end = 0; }
+    else { S.pool_next = (int)base; S.pool_end = (int)min(base + (unsigned int)WAVE_BATCH, total_items); }
+  }
+  __syncthreads();
+
+  int par = 0;
+  for (;;) {
+    // ================================================================= S1: regenerate (queue R[par])
+    const int n_r = S.cnt_r[par];
+    for (int i = tid; i < ((n_r + 31) & ~31); i += WAVE_THREADS) {
+      const bool on = i < n_r;
+      const int s = on ? (int)S.q_r[par][i] : 0;
+      int st = on ? S.state[s] : 0;
+      int item = on ? S.item[s] : -1;
+      bool starved = false, push_t = false;
+      if (on) {
+        if (st & ST_FOLD) {                                                   // unwind the recursion: integrators.adb:124,191,299
+          f3 L = mk3(S.lx[s], S.ly[s], S.lz[s]);
+          const int depth = st & ST_DEPTH_MASK;
+#pragma unroll 1
+          for (int k = depth - 1; k >= 0; k--) {
+            const float4 A = wa.stackA[(size_t)k * total_slots + gslot0 + s];
+            const float2 B = wa.stackB[(size_t)k * total_slots + gslot0 + s];
+            const f3 W = mk3(A.w, B.x, B.y);
+            if (RT == GCORE_PT_STUPID) L = W * L;
+            else L = mk3(A.x, A.y, A.z) + W * L;
+          }
+          const int sub = (st >> ST_SUB_SHIFT) & 3;
+          f3 color = mk3(S.cr[s], S.cg[s], S.cb[s]);
+          bool done;
+          if (aa) {
+            if (sub == 0) color = bg;                                         // :42
+            color = color + L;                                                // :47
+            done = (sub == 3);
+          } else { color = L; done = true; }                                  // :60
+          if (done) { wa.colbuf[item] = make_float4(color.x, color.y, color.z, 0.0f); item = -1; }
+          else { S.cr[s] = color.x; S.cg[s] = color.y; S.cb[s] = color.z; }
+          st = (st & ~(ST_FOLD | (3 << ST_SUB_SHIFT))) | (((sub + 1) & 3) << ST_SUB_SHIFT);
+        }
+        WavePixel px; px.x = 0; px.y = 0; px.active = 0;
+        if (item < 0) {                                                       // next work item: (pass, pixel)
+          for (;;) {
+            const int got = atomicAdd(&S.pool_next, 1);
+            if (got >= S.pool_end) { starved = true; break; }
+            px = wave_slot_to_pixel(a, got % a.nslots);
+            if (px.active) { item = got; break; }
+          }
+          st &= ~(3 << ST_SUB_SHIFT);
+        } else {
+          px = wave_slot_to_pixel(a, item % a.nslots);
+        }
+        S.item[s] = item;
+        if (!starved) {
+          const int sub = (st >> ST_SUB_SHIFT) & 3;
+          const f3 o = ld3(g_scn.cam_pos);
+          const f3 d = wave_eye_ray_dir(a, px.x, px.y, aa ? sub : -1);
+          S.ox[s] = o.x; S.oy[s] = o.y; S.oz[s] = o.z; S.dx[s] = d.x; S.dy[s] = d.y; S.dz[s] = d.z;
+          S.prev_pdf[s] = 1.0f;                                               // StartSample, materials.ads:25
+          st = (st & (3 << ST_SUB_SHIFT)) | ST_SPEC | ST_HASRAY;              // depth 0
+          S.tri_id[s] = -1;
+          push_t = mesh_candidate<MESHK>(o, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), nmesh);
+        } else {
+          st &= ~ST_HASRAY;
+        }
+        S.state[s] = st;
+      }
+      queue_push(push_t, S.q_t, &S.cnt_t, s);
+      // a starved slot waits for the next batch, or retires once the global counter is exhausted
+      const bool retire = starved && S.exhausted;
+      queue_push(starved && !retire, S.q_r[par ^ 1], &S.cnt_r[par ^ 1], s);
+      const unsigned rm = __ballot_sync(0xffffffffu, retire);
+      if (rm && (tid & 31) == 0) atomicAdd(&S.retired, __popc(rm));
+    }
+    __syncthreads();
+    if (S.retired >= WAVE_NS) break;        // uniform: `retired` only changes in S1, which the barrier above closes
+
+    // ================================================================= S2: mesh stage of the path rays (queue T)
+    if (tid == 0) {
+      S.cnt_r[par] = 0;
+      if (!S.exhausted && S.pool_next >= S.pool_end) {                        // refill the item pool
+        unsigned int base = atomicAdd(wa.next_item, (unsigned int)WAVE_BATCH);
+        if (base >= total_items) S.exhausted = 1;
+        else { S.pool_next = (int)base; S.pool_end = (int)min(base + (unsigned int)WAVE_BATCH, total_items); }
+      }
+    }
+    {
+      const int n_t = S.cnt_t;
+      for (int i = tid; i < n_t; i += WAVE_THREADS) {
+        const int s = S.q_t[i];
+        float t, u, v; int id;
+        mesh_query<MESHK>(mk3(S.ox[s], S.oy[s], S.oz[s]), mk3(S.dx[s], S.dy[s], S.dz[s]), t, u, v, id);
+        S.tri_t[s] = t; S.tri_u[s] = u; S.tri_v[s] = v; S.tri_id[s] = id;
+      }
+    }
+    __syncthreads();
+
+    // ================================================================= S3: closest hit, path end or light sample (all slots with a ray)
+    if (tid == 0) S.cnt_t = 0;
+    for (int s = tid; s < WAVE_NS; s += WAVE_THREADS) {
+      int st = S.state[s];
+      const bool on = (st & ST_HASRAY) != 0;
+      bool ended = false, push_ts = false;
+      int bucket = -1;
+      if (on) {
+        const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
+        const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        DHit h;
+        closest_with_mesh<MESHK>(o, d, inv, S.tri_id[s], S.tri_t[s], S.tri_u[s], S.tri_v[s], true, h);
+        nrays++;
+        st &= ~ST_SURF;
+        f3 Lterm = mk3(0.f, 0.f, 0.f);
+        if (!h.is_hit) {                                                      // integrators.adb:98,151,218
+          ended = true;
+        } else if (g_scn.mats[h.mat].type == MAT_LIGHT) {
+          ended = true;
+          if (RT != GCORE_PT_SHADOW && !(dot(neg(d), h.normal) < 0.0f)) {     // :155-157 ; :103, :224
+            f3 emit = (g_scn.mats[h.mat].light < 0) ? mk3(0.f, 0.f, 0.f) : ld3(g_scn.l_intensity);   // materials.adb:147-156
+            if (RT == GCORE_PT_STUPID) Lterm = emit;                          // :106
+            else {                                                            // :230-243
+              float lgtPdf = light_eval_pdf(o, d, h.t);
+              float bsdfPdf = S.prev_pdf[s];
+              float misWeight = (st & ST_SPEC) ? 1.0f : (bsdfPdf * bsdfPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf));
+              Lterm = emit * misWeight;
+            }
+          }
+        } else {
+          // ---- surface: Philox draws, light sample + shadow ray (Compute_Shadow, ray_tracer.adb:100-116)
+          nbounce++;
+          st |= ST_SURF;
+          const int item = S.item[s];
+          const int q = item % a.nslots, unit = item / a.nslots;
+          const WavePixel px = wave_slot_to_pixel(a, q);
+          const uint32_t pixel = (uint32_t)(px.y * a.width + px.x);
+          const int sub = (st >> ST_SUB_SHIFT) & 3;
+          const uint32_t sample = (uint32_t)(a.first_sample + (aa ? (unit * 4 + sub) : unit));
+          const BounceRand br = bounce_rand(a.seed, pixel, sample, (uint32_t)(st & ST_DEPTH_MASK));
+          S.r1[s] = br.u2; S.r2[s] = br.u3;
+          S.ht[s] = h.t; S.nx[s] = h.normal.x; S.ny[s] = h.normal.y; S.nz[s] = h.normal.z; S.hmat[s] = (short)h.mat;
+          if (RT != GCORE_PT_STUPID) {                                        // :161-178 / :251-287
+            const f3 hpos = mk3(o.x + h.t * d.x, o.y + h.t * d.y, o.z + h.t * d.z);
+            LightSample ls = light_sample(br.u0, br.u1, hpos);
+            float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
+            epsilon = max2(epsilon, 1.0e-30f);
+            const f3 sdir = normalize(ls.pos - hpos);
+            const f3 so = hpos + sdir * epsilon;
+            float maxDist  = length(hpos - ls.pos);
+            float epsilon2 = max2(maxDist * 0.000001f, 1.0e-30f);
+            S.sx[s] = sdir.x; S.sy[s] = sdir.y; S.sz[s] = sdir.z; S.ls_pdf[s] = ls.pdf; S.sh_thi[s] = maxDist - epsilon2;
+            S.stri_id[s] = -1;
+            push_ts = mesh_candidate<MESHK>(so, mk3(1.0f / sdir.x, 1.0f / sdir.y, 1.0f / sdir.z), nmesh);
+          }
+          const int type = g_scn.mats[h.mat].type;
+          bucket = (type == MAT_LAMBERT) ? 0 : (type == MAT_PHONG) ? 1 : (type == MAT_GLASS) ? 2 : (type == MAT_MIRROR) ? 3 : 4;
+          st = (st & ~(7 << ST_BUCKET_SHIFT)) | (bucket << ST_BUCKET_SHIFT);
+        }
+        if (ended) {
+          S.lx[s] = Lterm.x; S.ly[s] = Lterm.y; S.lz[s] = Lterm.z;
+          st = (st & ~ST_HASRAY) | ST_FOLD;
+        }
+        S.state[s] = st;
+      }
+      queue_push(ended, S.q_r[par ^ 1], &S.cnt_r[par ^ 1], s);
+      if (RT != GCORE_PT_STUPID) queue_push(push_ts, S.q_ts, &S.cnt_ts, s);
+      // rank inside the material bucket (counting sort, scattered in S4)
+#pragma unroll
+      for (int b = 0; b < 5; b++) {
+        const unsigned m = __ballot_sync(0xffffffffu, bucket == b);
+        if (m) {
+          const int lane = tid & 31, leader = __ffs(m) - 1;
+          int base = 0;
+          if (lane == leader) base = atomicAdd(&S.cnt_m[b], __popc(m));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (bucket == b) S.mrank[s] = (short)(base + __popc(m & ((1u << lane) - 1u)));
+        }
+      }
+    }
+    __syncthreads();
+
+    // ================================================================= S4: mesh stage of the shadow rays + material sort
+    if (tid == 0) {
+      int off = 0;
+      for (int b = 0; b < 5; b++) { S.off_m[b] = off; off += (S.cnt_m[b] + 31) & ~31; }
+      S.off_m[5] = off;
+    }
+    if (RT != GCORE_PT_STUPID) {
+      const int n_ts = S.cnt_ts;
+      for (int i = tid; i < n_ts; i += WAVE_THREADS) {
+        const int s = S.q_ts[i];
+        const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
+        const float ht = S.ht[s];
+        const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
+        const f3 sdir = mk3(S.sx[s], S.sy[s], S.sz[s]);
+        float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
+        epsilon = max2(epsilon, 1.0e-30f);
+        float t, u, v; int id;
+        mesh_query<MESHK>(hpos + sdir * epsilon, sdir, t, u, v, id);
+        S.stri_t[s] = t; S.stri_id[s] = id;
+      }
+    }
+    __syncthreads();
+    for (int s = tid; s < WAVE_NS; s += WAVE_THREADS) {                       // scatter (off_m is ready after the barrier)
+      const int st = S.state[s];
+      if ((st & (ST_SURF | ST_HASRAY)) == (ST_SURF | ST_HASRAY)) {
+        const int b = (st >> ST_BUCKET_SHIFT) & 7;
+        S.q_m[S.off_m[b] + S.mrank[s]] = (short)s;
+      }
+    }
+    __syncthreads();
+
+    // ================================================================= S5: shade (slots sorted by material type)
+    if (tid == 0) S.cnt_ts = 0;
+    {
+      const int n_m = S.off_m[5];
+      for (int i = tid; i < n_m; i += WAVE_THREADS) {
+        int b = 0;
+#pragma unroll
+        for (int k = 1; k < 5; k++) if (i >= S.off_m[k]) b = k;               // warp-uniform: segments are multiples of 32
+        const bool on = (i - S.off_m[b]) < S.cnt_m[b];
+        const int s = on ? (int)S.q_m[i] : 0;
+        bool ended = false, push_t = false;
+        if (on) {
+          int st = S.state[s];
+          const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
+          const float ht = S.ht[s];
+          const f3 hn = mk3(S.nx[s], S.ny[s], S.nz[s]);
+          const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
+          const DMaterial& m = g_scn.mats[S.hmat[s]];
+          const f3 refl = reflect(d, hn);         // shared by Phong eval/sample, mirror, glass (materials.adb:251,313,371,394)
+          f3 explicitColor = mk3(0.f, 0.f, 0.f);
+          if (RT != GCORE_PT_STUPID) {
+            const f3 sdir = mk3(S.sx[s], S.sy[s], S.sz[s]);
+            float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
+            epsilon = max2(epsilon, 1.0e-30f);
+            const f3 so = hpos + sdir * epsilon;
+            DHit hs;                                                          // closest hit; only is_hit / t are read (ray_tracer.adb:117-122)
+            closest_with_mesh<MESHK>(so, sdir, mk3(1.0f / sdir.x, 1.0f / sdir.y, 1.0f / sdir.z), S.stri_id[s], S.stri_t[s], 0.0f, 0.0f, false, hs);
+            nrays++;
+            const bool shadowed = hs.is_hit && (hs.t < S.sh_thi[s] && hs.t > 10.0f * epsilon);
+            if (!shadowed) {
+              f3 bxdfVal; float bsdfPdf;
+              mat_eval(m, sdir, hn, refl, bxdfVal, bsdfPdf);
+              float cosTheta1 = max2(dot(sdir, hn), 0.0f);
+              f3 intensity = ld3(g_scn.l_intensity);
+              const float ls_pdf = S.ls_pdf[s];
+              if (RT == GCORE_PT_SHADOW) {
+                explicitColor = intensity * (cosTheta1 * bxdfVal) * (1.0f / max2(ls_pdf, 1.0e-20f));
+              } else {
+                float lgtPdf = ls_pdf;
+                float misWeight = lgtPdf * lgtPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf);
+                explicitColor = intensity * (1.0f / max2(lgtPdf, 1.0e-20f)) * (cosTheta1 * bxdfVal) * misWeight;
+              }
+            }
+          }
+          MatSampleD ms = mat_sample(m, S.r1[s], S.r2[s], d, hn, refl);       // pick up next ray, :116,183,291
+          f3 bxdfVal = ms.color * (1.0f / max2(ms.pdf, 1.0e-20f));
+          float cosTheta = dot(ms.direction, hn);
+          const f3 W = fabsf(cosTheta) * bxdfVal;
+          int depth = st & ST_DEPTH_MASK;
+          wa.stackA[(size_t)depth * total_slots + gslot0 + s] = make_float4(explicitColor.x, explicitColor.y, explicitColor.z, W.x);
+          wa.stackB[(size_t)depth * total_slots + gslot0 + s] = make_float2(W.y, W.z);
+          depth++;
+          const f3 off = (sign_ada(cosTheta) * hn) * 1.0e-5f;                 // :122,189,297
+          const f3 no = hpos + off, nd = ms.direction;
+          S.ox[s] = no.x; S.oy[s] = no.y; S.oz[s] = no.z; S.dx[s] = nd.x; S.dy[s] = nd.y; S.dz[s] = nd.z;
+          S.prev_pdf[s] = ms.pdf;
+          st = (st & ~(ST_DEPTH_MASK | ST_SPEC | ST_SURF)) | depth | (ms.pureSpecular ? ST_SPEC : 0);
+          if (depth == max_depth) {                                           // recursion_level = 0 -> (0,0,0)
+            S.lx[s] = 0.f; S.ly[s] = 0.f; S.lz[s] = 0.f;
+            st = (st & ~ST_HASRAY) | ST_FOLD;
+            ended = true;
+          } else {
+            S.tri_id[s] = -1;
+            push_t = mesh_candidate<MESHK>(no, mk3(1.0f / nd.x, 1.0f / nd.y, 1.0f / nd.z), nmesh);
+          }
+          S.state[s] = st;
+        }
+        queue_push(ended, S.q_r[par ^ 1], &S.cnt_r[par ^ 1], s);
+        queue_push(push_t, S.q_t, &S.cnt_t, s);
+      }
+    }
+    __syncthreads();
+    if (tid < 5) S.cnt_m[tid] = 0;
+    par ^= 1;
+    __syncthreads();
+  }
+
+  // statistics: one atomic per warp and counter
+  unsigned int total_rays = __reduce_add_sync(0xffffffffu, nrays);
+  unsigned int total_mesh = __reduce_add_sync(0xffffffffu, nmesh);
+  unsigned int total_bnc  = __reduce_add_sync(0xffffffffu, nbounce);
+  if ((threadIdx.x & 31) == 0 && total_rays) {
+    atomicAdd(&a.counters[0], (unsigned long long)total_rays);
+    atomicAdd(&a.counters[1], (unsigned long long)total_mesh);
+    atomicAdd(&a.counters[2], (unsigned long long)total_bnc);
+  }
+}
+
+// K6a: acc[q] := colour(pass k, q) + acc[q] for k = 0 .. units-1 -- the additions of integrators.adb:51/:63 in pass order
+__global__ void __launch_bounds__(256) fold_kernel(const __grid_constant__ gcore_dev::RenderArgs a, const float4* __restrict__ colbuf, int units) {
+  const int q = blockIdx.x * 256 + threadIdx.x;
+  if (q >= a.nslots) return;
+  const WavePixel px = wave_slot_to_pixel(a, q);
+  if (!px.active) return;
+  float4 acc4 = a.accum[q];
+  f3 acc = mk3(acc4.x, acc4.y, acc4.z);
+#pragma unroll 4
+  for (int k = 0; k < units; k++) {
+    const float4 c = __ldcs(&colbuf[(size_t)k * a.nslots + q]);
+    acc = mk3(c.x, c.y, c.z) + acc;
+  }
+  a.accum[q] = make_float4(acc.x, acc.y, acc.z, acc4.w);
+}
+
+}  // namespace art

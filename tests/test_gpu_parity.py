@@ -170,7 +170,7 @@ def test_one_shot_render_call(gscene, oscene, pkg, ob):
     acc, rays = oscene.render(ob.make_params(w, h, ob.PT_SHADOW, passes=2, seed=5))
     assert np.array_equal(_bits(hdr[..., :3]), _bits(acc))
     assert np.array_equal(ldr, ob.resolve(acc, 8))
-    assert st.rays + st.hoisted_rays == rays and st.spp == 8 and st.kernel_launches == 2 and st.samples == w * h * 8
+    assert st.rays + st.hoisted_rays == rays and st.spp == 8 and st.kernel_launches == 3 and st.samples == w * h * 8
 
 
 def test_full_size_properties(gscene, pkg):
