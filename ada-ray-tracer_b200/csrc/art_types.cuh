@@ -29,7 +29,7 @@ struct BvhView {                   // packed LBVH (see lbvh.cuh); all pointers a
 struct DeviceScene {
   int   nspheres, nmaterials, ntris_bf, mesh_mode;
   int   light_shape, mesh_kind;    // mesh_kind: 0 none, 1 constant-memory triangles, 2 LBVH
-  int   pad0, pad1;
+  int   pair_group, pad1;      // pair_group: lanes per ray in the (ray, triangle) pair stage (power of two >= ntris_bf, <= 32; 0: one ray per thread)
   float sph[GC_MAX_SPHERES][4];    // pos.xyz, r
   int   sph_mat[GC_MAX_SPHERES];
   float box_min[3], box_max[3];

@@ -231,7 +231,7 @@ int install_mesh(int mesh_mode) {
   for (int v : s.mesh_tris) if (v < 0 || v >= nverts) return fail(GCORE_E_ARG, "gcore_set_mesh: triangle index out of range");
   gcore_dev::lbvh_free(&s.mesh_bvh);
   s.hs.mesh_mode = mesh_mode;
-  s.hs.ntris_bf = 0; s.hs.mesh_kind = 0;
+  s.hs.ntris_bf = 0; s.hs.mesh_kind = 0; s.hs.pair_group = 0;
   for (int k = 0; k < 3; k++) { s.hs.mesh_bmin[k] = s.mesh_bbox[k]; s.hs.mesh_bmax[k] = s.mesh_bbox[3 + k]; }
   s.scene_dirty = true;
   if (ntris == 0) return 0;
@@ -257,6 +257,8 @@ int install_mesh(int mesh_mode) {
       }
     }
     s.hs.ntris_bf = ntris; s.hs.mesh_kind = 1;
+    s.hs.pair_group = 0;
+    if (ntris <= 8) s.hs.pair_group = ntris;            // WAVE_PAIR_TRIS of render_wave.cuh
     return 0;
   }
   if (mesh_mode == GCORE_MESH_REFERENCE_BF)

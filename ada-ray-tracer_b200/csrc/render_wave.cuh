@@ -7,18 +7,21 @@
 // its stall samples waiting for instructions (profiles/r01_render_megakernel.md): lanes of a warp sit on different
 // materials and bounce depths, the 8-triangle mesh loop runs for ~2 lanes, and 60 KB of inlined code thrash the 32 KB
 // instruction cache.  Here a persistent block owns NS path slots whose state lives in shared memory (SoA), and walks
-// all of them through five stages separated by __syncthreads().  Between stages slots are re-packed into dense queues,
-// so every stage runs with full warps on one small piece of code that all warps of the block execute at the same time:
+// all of them through two wide and two narrow stages per bounce, separated by __syncthreads().  Between stages slots
+// are re-packed into dense queues, so every stage runs with full warps on one small piece of code that all warps of the
+// block execute at the same time:
 //
-//   S1  regenerate   queue R : unwind the finished path (integrators.adb:124,191,299), add its radiance to the pixel-pass
-//                              colour in the reference's order (:42-51), publish the colour when the pass is complete,
-//                              fetch the next work item (pixel, pass), generate the camera ray (ray_tracer.adb:61-97)
-//   S2  mesh         queue T : triangle tests (geometry.adb:231-323) / LBVH traversal for the path rays that reach the mesh
-//   S3  hit + light  all     : spheres, Cornell box, flat light, merge with S2 (scene.adb:56-86); miss / emitter -> path
-//                              ends; surface -> Philox draws, Lights.Sample, shadow ray (ray_tracer.adb:100-116)
-//   S4  shadow mesh  queue T': triangle tests for the shadow rays; counting sort of the surface slots by material type
-//   S5  shade        sorted  : shadow spheres/box + in_shadow rule (ray_tracer.adb:117-128), EvalBxDF/EvalPDF + MIS
-//                              (integrators.adb:161-178, 251-287), SampleAndEvalBxDF (:116,183,291), next ray
+//   X   extend       all slots with a ray : mesh candidate of M2 merged with spheres, Cornell box, flat light
+//                    (scene.adb:56-86); miss / emitter -> the path ends (queue R); surface -> Philox draws, Lights.Sample,
+//                    shadow ray (ray_tracer.adb:100-116), bucket by material type
+//   M1  shadow mesh  (shadow ray, triangle) pairs : one triangle test per thread (geometry.adb:231-263) / LBVH traversal
+//   Y   shade        surface slots sorted by material : shadow spheres/box + in_shadow rule (ray_tracer.adb:117-128),
+//                    EvalBxDF/EvalPDF + MIS (integrators.adb:161-178, 251-287), SampleAndEvalBxDF (:116,183,291), next
+//                    ray;  in the same interval the spare threads take queue R: unwind the finished path
+//                    (integrators.adb:124,191,299), add its radiance to the pixel-pass colour in the reference's order
+//                    (:42-51), publish the colour when the pass is complete, fetch the next work item, camera ray
+//                    (ray_tracer.adb:61-97)
+//   M2  path mesh    (path ray, triangle) pairs for the rays made in Y
 //
 // A work item is one DoPass of one pixel (4 fixed sub-pixel paths, or 1): items are handed out from a global counter,
 // so no slot idles while others finish long paths, and the colour of item (pass k, pixel q) goes to colbuf[k][q].
@@ -33,25 +36,23 @@
 namespace art {
 
 #ifndef WAVE_THREADS
-#define WAVE_THREADS 512
+#define WAVE_THREADS 1024
 #endif
 #ifndef WAVE_MINB
-#define WAVE_MINB 2
+#define WAVE_MINB 1
 #endif
 #define WAVE_NS WAVE_THREADS              // path slots per block
 #define WAVE_BATCH (2 * WAVE_NS)          // work items fetched from the global counter at a time
 #define WAVE_MAX_DEPTH 16
 
-enum { ST_DEPTH_MASK = 31, ST_SUB_SHIFT = 5, ST_SPEC = 1 << 7, ST_HASRAY = 1 << 8, ST_FOLD = 1 << 9, ST_SURF = 1 << 10,
-       ST_BUCKET_SHIFT = 11 /* 3 bits */ };
+#define WAVE_PAIR_TRIS 8                  // constant-memory meshes up to this size are tested as (ray, triangle) pairs
+
+enum { ST_DEPTH_MASK = 31, ST_SUB_SHIFT = 5, ST_SPEC = 1 << 7, ST_HASRAY = 1 << 8, ST_FOLD = 1 << 9, ST_SURF = 1 << 10 };
 
 struct WaveSmem {
   // path ray
   float ox[WAVE_NS], oy[WAVE_NS], oz[WAVE_NS], dx[WAVE_NS], dy[WAVE_NS], dz[WAVE_NS];
-  // mesh candidate of the path ray (S2) and of the shadow ray (S4); id < 0: none
-  float tri_t[WAVE_NS], tri_u[WAVE_NS], tri_v[WAVE_NS], stri_t[WAVE_NS];
-  int   tri_id[WAVE_NS], stri_id[WAVE_NS];
-  // surface hit + light sample of the current bounce (S3 -> S5)
+  // surface hit + light sample of the current bounce (X -> Y)
   float ht[WAVE_NS], nx[WAVE_NS], ny[WAVE_NS], nz[WAVE_NS];
   float sx[WAVE_NS], sy[WAVE_NS], sz[WAVE_NS], ls_pdf[WAVE_NS], sh_thi[WAVE_NS];
   float r1[WAVE_NS], r2[WAVE_NS];
@@ -59,23 +60,29 @@ struct WaveSmem {
   // colour of the work item so far / radiance at the end of the path
   float cr[WAVE_NS], cg[WAVE_NS], cb[WAVE_NS], lx[WAVE_NS], ly[WAVE_NS], lz[WAVE_NS];
   int   item[WAVE_NS];                    // unit * nslots + q, or -1: no item
+  unsigned int pixel[WAVE_NS], sample[WAVE_NS];   // Philox key word 1 / counter word 0 of the current path
   int   state[WAVE_NS];                   // depth | sub << 5 | flags
-  short hmat[WAVE_NS], mrank[WAVE_NS];
-  short q_r[2][WAVE_NS], q_t[WAVE_NS], q_ts[WAVE_NS], q_m[WAVE_NS + 5 * 32];
-  int   cnt_r[2], cnt_t, cnt_ts, cnt_m[5], off_m[6];
+  // mesh stage results per candidate (see wave_mesh_stage)
+  float mesh_res[WAVE_PAIR_TRIS * WAVE_NS];
+  short cand[WAVE_NS];                    // candidate index of the slot's pending ray in the mesh stage, -1: none
+  short hmat[WAVE_NS];
+  short q_r[2][WAVE_NS], q_cs[WAVE_NS], q_cp[WAVE_NS], q_m[5][WAVE_NS];
+  int   cnt_r[2], cnt_cs, cnt_cp, cnt_m[5];
   int   pool_next, pool_end, exhausted, retired;
 };
 
-// warp-aggregated append of `slot` to a shared-memory queue (one atomic per warp)
-ART_D void queue_push(bool pred, short* q, int* cnt, int slot) {
+// warp-aggregated append of `slot` to a shared-memory queue (one atomic per warp); returns the position
+ART_D int queue_push(bool pred, short* q, int* cnt, int slot) {
   const unsigned m = __ballot_sync(0xffffffffu, pred);
-  if (m == 0u) return;
+  if (m == 0u) return -1;
   const int lane = threadIdx.x & 31;
   const int leader = __ffs(m) - 1;
   int base = 0;
   if (lane == leader) base = atomicAdd(cnt, __popc(m));
   base = __shfl_sync(0xffffffffu, base, leader);
-  if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = (short)slot;
+  const int pos = base + __popc(m & ((1u << lane) - 1u));
+  if (pred) q[pos] = (short)slot;
+  return pred ? pos : -1;
 }
 
 struct WaveArgs {
@@ -239,6 +246,81 @@ ART_D f3 wave_eye_ray_dir(const gcore_dev::RenderArgs& a, int x, int y, int sub)
   return normalize(m);
 }
 
+// raw Moeller-Trumbore values of geometry.adb:238-248 (no acceptance test): the same operation sequence as
+// intersect_triangle, used to re-derive (t, u, v) of the triangle the pair stage selected
+ART_D void triangle_tuv(f3 o, f3 d, f3 A, f3 edge1, f3 edge2, float& t, float& u, float& v) {
+  f3 pvec = cross(d, edge2);
+  f3 tvec = o - A;
+  float invDet = 1.0f / max2(dot(edge1, pvec), 1.0e-25f);
+  v = dot(tvec, pvec) * invDet;
+  f3 qvec = cross(tvec, edge1);
+  u = dot(qvec, d) * invDet;
+  t = dot(edge2, qvec) * invDet;
+}
+
+// mesh stage (M1 / M2) for the rays queued in q_c.  SHADOW: the ray is the shadow ray of the slot's hit.  Constant-memory
+// meshes of up to WAVE_PAIR_TRIS triangles are tested as (ray, triangle) pairs, one triangle test per thread, so the
+// stage is as short as one triangle test (nothing else runs on the SM meanwhile): mesh_res[c * ntris + i] = t of
+// triangle i if its (u, v) test passes, NaN otherwise.  Bigger meshes: one ray per thread, mesh_res[4c..] = t, u, v, id.
+template <int MESHK, bool SHADOW>
+ART_D void wave_mesh_stage(WaveSmem& S, const short* q_c, int n_c, int tid) {
+  const int ntris = g_scn.ntris_bf;
+  const bool pair_mode = (MESHK == MESHK_CONST) && (g_scn.pair_group != 0);
+  const int work = pair_mode ? n_c * ntris : n_c;
+  for (int j = tid; j < work; j += WAVE_THREADS) {
+    const int c = pair_mode ? j / ntris : j;
+    const int i = pair_mode ? j - c * ntris : 0;
+    const int s = q_c[c];
+    f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
+    if (SHADOW) {                                                             // shadow ray of Compute_Shadow, ray_tracer.adb:109-113
+      const float ht = S.ht[s];
+      const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
+      d = mk3(S.sx[s], S.sy[s], S.sz[s]);
+      float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
+      epsilon = max2(epsilon, 1.0e-30f);
+      o = hpos + d * epsilon;
+    }
+    if (pair_mode) {
+      float t, u, v;
+      triangle_tuv(o, d, ld3(g_scn.triA[i]), ld3(g_scn.triE1[i]), ld3(g_scn.triE2[i]), t, u, v);
+      S.mesh_res[j] = (v > 0.0f && u > 0.0f && u + v < 1.0f) ? t : __int_as_float(0x7fc00000);
+    } else {
+      float t, u, v; int id;
+      mesh_query<MESHK>(o, d, t, u, v, id);
+      S.mesh_res[4 * c + 0] = t; S.mesh_res[4 * c + 1] = u; S.mesh_res[4 * c + 2] = v; S.mesh_res[4 * c + 3] = __int_as_float(id);
+    }
+  }
+}
+
+// the mesh candidate of a ray out of mesh_res: the window walk of IntersectMeshBF (geometry.adb:276-296) over the pair
+// results in triangle order (u, v of the selected triangle are re-derived when the caller needs them), or the stored
+// per-ray result
+template <int MESHK>
+ART_D void wave_mesh_result(const WaveSmem& S, int c, f3 o, f3 d, bool want_uv, int& id, float& t, float& u, float& v) {
+  id = -1; t = 0.0f; u = 0.0f; v = 0.0f;
+  if (c < 0) return;
+  const bool pair_mode = (MESHK == MESHK_CONST) && (g_scn.pair_group != 0);
+  if (pair_mode) {
+    const int ntris = g_scn.ntris_bf;
+    const bool ref_mode = (g_scn.mesh_mode == MESH_REFERENCE_BF);
+    float w_min = 0.0f, w_max = 1000000.0f;
+#pragma unroll 1
+    for (int i = 0; i < ntris; i++) {
+      const float ti = S.mesh_res[c * ntris + i];
+      if (ti > w_min && ti < w_max) {                                         // NaN (failed u/v test) never passes
+        if (ref_mode) { w_min = ti; w_max = ti + 1.0e-6f; } else { w_max = ti; }
+        t = ti; id = i;
+      }
+    }
+    if (id >= 0 && want_uv) {
+      float t2;
+      triangle_tuv(o, d, ld3(g_scn.triA[id]), ld3(g_scn.triE1[id]), ld3(g_scn.triE2[id]), t2, u, v);
+    }
+  } else {
+    t = S.mesh_res[4 * c + 0]; u = S.mesh_res[4 * c + 1]; v = S.mesh_res[4 * c + 2]; id = __float_as_int(S.mesh_res[4 * c + 3]);
+  }
+}
+
 template <int RT, int MESHK>
 __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MINB) render_wave_kernel(const __grid_constant__ WaveArgs wa) {
   extern __shared__ __align__(16) unsigned char wave_smem_raw[];
@@ -254,10 +336,10 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MINB) render_wave_kernel(co
   unsigned int nrays = 0, nmesh = 0, nbounce = 0;
 
   for (int s = tid; s < WAVE_NS; s += WAVE_THREADS) {
-    S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s; S.tri_id[s] = -1; S.stri_id[s] = -1;
+    S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s; S.cand[s] = -1;
   }
   if (tid == 0) {
-    S.cnt_r[0] = WAVE_NS; S.cnt_r[1] = 0; S.cnt_t = 0; S.cnt_ts = 0; S.retired = 0; S.exhausted = 0;
+    S.cnt_r[0] = WAVE_NS; S.cnt_r[1] = 0; S.cnt_cs = 0; S.cnt_cp = 0; S.retired = 0; S.exhausted = 0;
     for (int b = 0; b < 5; b++) S.cnt_m[b] = 0;
     unsigned int base = atomicAdd(wa.next_item, (unsigned int)WAVE_BATCH);
     if (base >= total_items) { S.exhausted = 1; S.pool_next = 0; S.pool_end = 0; }
@@ -267,107 +349,27 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MINB) render_wave_kernel(co
 
   int par = 0;
   for (;;) {
-    // ================================================================= S1: regenerate (queue R[par])
-    const int n_r = S.cnt_r[par];
-    for (int i = tid; i < ((n_r + 31) & ~31); i += WAVE_THREADS) {
-      const bool on = i < n_r;
-      const int s = on ? (int)S.q_r[par][i] : 0;
-      int st = on ? S.state[s] : 0;
-      int item = on ? S.item[s] : -1;
-      bool starved = false, push_t = false;
-      if (on) {
-        if (st & ST_FOLD) {                                                   // unwind the recursion: integrators.adb:124,191,299
-          f3 L = mk3(S.lx[s], S.ly[s], S.lz[s]);
-          const int depth = st & ST_DEPTH_MASK;
-#pragma unroll 1
-          for (int k = depth - 1; k >= 0; k--) {
-            const float4 A = wa.stackA[(size_t)k * total_slots + gslot0 + s];
-            const float2 B = wa.stackB[(size_t)k * total_slots + gslot0 + s];
-            const f3 W = mk3(A.w, B.x, B.y);
-            if (RT == GCORE_PT_STUPID) L = W * L;
-            else L = mk3(A.x, A.y, A.z) + W * L;
-          }
-          const int sub = (st >> ST_SUB_SHIFT) & 3;
-          f3 color = mk3(S.cr[s], S.cg[s], S.cb[s]);
-          bool done;
-          if (aa) {
-            if (sub == 0) color = bg;                                         // :42
-            color = color + L;                                                // :47
-            done = (sub == 3);
-          } else { color = L; done = true; }                                  // :60
-          if (done) { wa.colbuf[item] = make_float4(color.x, color.y, color.z, 0.0f); item = -1; }
-          else { S.cr[s] = color.x; S.cg[s] = color.y; S.cb[s] = color.z; }
-          st = (st & ~(ST_FOLD | (3 << ST_SUB_SHIFT))) | (((sub + 1) & 3) << ST_SUB_SHIFT);
-        }
-        WavePixel px; px.x = 0; px.y = 0; px.active = 0;
-        if (item < 0) {                                                       // next work item: (pass, pixel)
-          for (;;) {
-            const int got = atomicAdd(&S.pool_next, 1);
-            if (got >= S.pool_end) { starved = true; break; }
-            px = wave_slot_to_pixel(a, got % a.nslots);
-            if (px.active) { item = got; break; }
-          }
-          st &= ~(3 << ST_SUB_SHIFT);
-        } else {
-          px = wave_slot_to_pixel(a, item % a.nslots);
-        }
-        S.item[s] = item;
-        if (!starved) {
-          const int sub = (st >> ST_SUB_SHIFT) & 3;
-          const f3 o = ld3(g_scn.cam_pos);
-          const f3 d = wave_eye_ray_dir(a, px.x, px.y, aa ? sub : -1);
-          S.ox[s] = o.x; S.oy[s] = o.y; S.oz[s] = o.z; S.dx[s] = d.x; S.dy[s] = d.y; S.dz[s] = d.z;
-          S.prev_pdf[s] = 1.0f;                                               // StartSample, materials.ads:25
-          st = (st & (3 << ST_SUB_SHIFT)) | ST_SPEC | ST_HASRAY;              // depth 0
-          S.tri_id[s] = -1;
-          push_t = mesh_candidate<MESHK>(o, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), nmesh);
-        } else {
-          st &= ~ST_HASRAY;
-        }
-        S.state[s] = st;
-      }
-      queue_push(push_t, S.q_t, &S.cnt_t, s);
-      // a starved slot waits for the next batch, or retires once the global counter is exhausted
-      const bool retire = starved && S.exhausted;
-      queue_push(starved && !retire, S.q_r[par ^ 1], &S.cnt_r[par ^ 1], s);
-      const unsigned rm = __ballot_sync(0xffffffffu, retire);
-      if (rm && (tid & 31) == 0) atomicAdd(&S.retired, __popc(rm));
-    }
-    __syncthreads();
-    if (S.retired >= WAVE_NS) break;        // uniform: `retired` only changes in S1, which the barrier above closes
-
-    // ================================================================= S2: mesh stage of the path rays (queue T)
+    // ================================================================= X: closest hit, path end or light sample
     if (tid == 0) {
-      S.cnt_r[par] = 0;
-      if (!S.exhausted && S.pool_next >= S.pool_end) {                        // refill the item pool
+      S.cnt_cp = 0;                                                           // consumed by M2 of the previous round
+      if (!S.exhausted && S.pool_next >= S.pool_end) {                        // refill the item pool (fetched from in Y only)
         unsigned int base = atomicAdd(wa.next_item, (unsigned int)WAVE_BATCH);
         if (base >= total_items) S.exhausted = 1;
         else { S.pool_next = (int)base; S.pool_end = (int)min(base + (unsigned int)WAVE_BATCH, total_items); }
       }
     }
-    {
-      const int n_t = S.cnt_t;
-      for (int i = tid; i < n_t; i += WAVE_THREADS) {
-        const int s = S.q_t[i];
-        float t, u, v; int id;
-        mesh_query<MESHK>(mk3(S.ox[s], S.oy[s], S.oz[s]), mk3(S.dx[s], S.dy[s], S.dz[s]), t, u, v, id);
-        S.tri_t[s] = t; S.tri_u[s] = u; S.tri_v[s] = v; S.tri_id[s] = id;
-      }
-    }
-    __syncthreads();
-
-    // ================================================================= S3: closest hit, path end or light sample (all slots with a ray)
-    if (tid == 0) S.cnt_t = 0;
     for (int s = tid; s < WAVE_NS; s += WAVE_THREADS) {
       int st = S.state[s];
       const bool on = (st & ST_HASRAY) != 0;
-      bool ended = false, push_ts = false;
-      int bucket = -1;
+      bool ended = false, push_cs = false;
+      int bucket = -1 - (tid & 31);                                           // distinct per lane: no peers in the match below
       if (on) {
         const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
         const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        int tri_id; float tri_t, tri_u, tri_v;
+        wave_mesh_result<MESHK>(S, S.cand[s], o, d, true, tri_id, tri_t, tri_u, tri_v);
         DHit h;
-        closest_with_mesh<MESHK>(o, d, inv, S.tri_id[s], S.tri_t[s], S.tri_u[s], S.tri_v[s], true, h);
+        closest_with_mesh<MESHK>(o, d, inv, tri_id, tri_t, tri_u, tri_v, true, h);
         nrays++;
         st &= ~ST_SURF;
         f3 Lterm = mk3(0.f, 0.f, 0.f);
@@ -389,13 +391,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MINB) render_wave_kernel(co
           // ---- surface: Philox draws, light sample + shadow ray (Compute_Shadow, ray_tracer.adb:100-116)
           nbounce++;
           st |= ST_SURF;
-          const int item = S.item[s];
-          const int q = item % a.nslots, unit = item / a.nslots;
-          const WavePixel px = wave_slot_to_pixel(a, q);
-          const uint32_t pixel = (uint32_t)(px.y * a.width + px.x);
-          const int sub = (st >> ST_SUB_SHIFT) & 3;
-          const uint32_t sample = (uint32_t)(a.first_sample + (aa ? (unit * 4 + sub) : unit));
-          const BounceRand br = bounce_rand(a.seed, pixel, sample, (uint32_t)(st & ST_DEPTH_MASK));
+          const BounceRand br = bounce_rand(a.seed, S.pixel[s], S.sample[s], (uint32_t)(st & ST_DEPTH_MASK));
           S.r1[s] = br.u2; S.r2[s] = br.u3;
           S.ht[s] = h.t; S.nx[s] = h.normal.x; S.ny[s] = h.normal.y; S.nz[s] = h.normal.z; S.hmat[s] = (short)h.mat;
           if (RT != GCORE_PT_STUPID) {                                        // :161-178 / :251-287
@@ -408,12 +404,10 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MINB) render_wave_kernel(co
             float maxDist  = length(hpos - ls.pos);
             float epsilon2 = max2(maxDist * 0.000001f, 1.0e-30f);
             S.sx[s] = sdir.x; S.sy[s] = sdir.y; S.sz[s] = sdir.z; S.ls_pdf[s] = ls.pdf; S.sh_thi[s] = maxDist - epsilon2;
-            S.stri_id[s] = -1;
-            push_ts = mesh_candidate<MESHK>(so, mk3(1.0f / sdir.x, 1.0f / sdir.y, 1.0f / sdir.z), nmesh);
+            push_cs = mesh_candidate<MESHK>(so, mk3(1.0f / sdir.x, 1.0f / sdir.y, 1.0f / sdir.z), nmesh);
           }
           const int type = g_scn.mats[h.mat].type;
           bucket = (type == MAT_LAMBERT) ? 0 : (type == MAT_PHONG) ? 1 : (type == MAT_GLASS) ? 2 : (type == MAT_MIRROR) ? 3 : 4;
-          st = (st & ~(7 << ST_BUCKET_SHIFT)) | (bucket << ST_BUCKET_SHIFT);
         }
         if (ended) {
           S.lx[s] = Lterm.x; S.ly[s] = Lterm.y; S.lz[s] = Lterm.z;
@@ -421,127 +415,212 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MINB) render_wave_kernel(co
         }
         S.state[s] = st;
       }
-      queue_push(ended, S.q_r[par ^ 1], &S.cnt_r[par ^ 1], s);
-      if (RT != GCORE_PT_STUPID) queue_push(push_ts, S.q_ts, &S.cnt_ts, s);
-      // rank inside the material bucket (counting sort, scattered in S4)
-#pragma unroll
-      for (int b = 0; b < 5; b++) {
-        const unsigned m = __ballot_sync(0xffffffffu, bucket == b);
-        if (m) {
+      queue_push(ended, S.q_r[par], &S.cnt_r[par], s);
+      if (RT != GCORE_PT_STUPID) {
+        const int c = queue_push(push_cs, S.q_cs, &S.cnt_cs, s);
+        if (on) S.cand[s] = (short)c;                                         // -1 when the shadow ray skips the mesh
+      }
+      {                                                                       // append to the queue of the material type
+        const unsigned m = __match_any_sync(0xffffffffu, bucket);
+        if (bucket >= 0) {
           const int lane = tid & 31, leader = __ffs(m) - 1;
           int base = 0;
-          if (lane == leader) base = atomicAdd(&S.cnt_m[b], __popc(m));
-          base = __shfl_sync(0xffffffffu, base, leader);
-          if (bucket == b) S.mrank[s] = (short)(base + __popc(m & ((1u << lane) - 1u)));
+          if (lane == leader) base = atomicAdd(&S.cnt_m[bucket], __popc(m));
+          base = __shfl_sync(m, base, leader);
+          S.q_m[bucket][base + __popc(m & ((1u << lane) - 1u))] = (short)s;
         }
       }
     }
     __syncthreads();
 
-    // ================================================================= S4: mesh stage of the shadow rays + material sort
-    if (tid == 0) {
-      int off = 0;
-      for (int b = 0; b < 5; b++) { S.off_m[b] = off; off += (S.cnt_m[b] + 31) & ~31; }
-      S.off_m[5] = off;
-    }
+    // ================================================================= M1: mesh stage of the shadow rays
     if (RT != GCORE_PT_STUPID) {
-      const int n_ts = S.cnt_ts;
-      for (int i = tid; i < n_ts; i += WAVE_THREADS) {
-        const int s = S.q_ts[i];
-        const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
-        const float ht = S.ht[s];
-        const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
-        const f3 sdir = mk3(S.sx[s], S.sy[s], S.sz[s]);
-        float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
-        epsilon = max2(epsilon, 1.0e-30f);
-        float t, u, v; int id;
-        mesh_query<MESHK>(hpos + sdir * epsilon, sdir, t, u, v, id);
-        S.stri_t[s] = t; S.stri_id[s] = id;
-      }
+      wave_mesh_stage<MESHK, true>(S, S.q_cs, S.cnt_cs, tid);
+      __syncthreads();
     }
-    __syncthreads();
-    for (int s = tid; s < WAVE_NS; s += WAVE_THREADS) {                       // scatter (off_m is ready after the barrier)
-      const int st = S.state[s];
-      if ((st & (ST_SURF | ST_HASRAY)) == (ST_SURF | ST_HASRAY)) {
-        const int b = (st >> ST_BUCKET_SHIFT) & 7;
-        S.q_m[S.off_m[b] + S.mrank[s]] = (short)s;
-      }
-    }
-    __syncthreads();
 
-    // ================================================================= S5: shade (slots sorted by material type)
-    if (tid == 0) S.cnt_ts = 0;
+    // ================================================================= Y: shade (slots sorted by material) + regenerate (queue R)
     {
-      const int n_m = S.off_m[5];
-      for (int i = tid; i < n_m; i += WAVE_THREADS) {
-        int b = 0;
+      if (tid == 0) S.cnt_cs = 0;
+      const int c0 = S.cnt_m[0], c1 = S.cnt_m[1], c2 = S.cnt_m[2], c3 = S.cnt_m[3], c4 = S.cnt_m[4];
+      const int o1 = (c0 + 31) & ~31, o2 = o1 + ((c1 + 31) & ~31), o3 = o2 + ((c2 + 31) & ~31), o4 = o3 + ((c3 + 31) & ~31);
+      const int n_m = o4 + ((c4 + 31) & ~31);
+      const int n_r = S.cnt_r[par];
+      const int n_all = n_m + ((n_r + 31) & ~31);
+      for (int i = tid; i < n_all; i += WAVE_THREADS) {
+        bool ended = false, push_cp = false, starved = false, retire = false, newray = false;
+        int s = 0;
+        if (i < n_m) {
+          // ------------------------------------------------------------- shade
+          // warp-uniform: segments are multiples of 32
+          const int b = (i >= o1) + (i >= o2) + (i >= o3) + (i >= o4);
+          const int off_b = (b == 0) ? 0 : (b == 1) ? o1 : (b == 2) ? o2 : (b == 3) ? o3 : o4;
+          const int cnt_b = (b == 0) ? c0 : (b == 1) ? c1 : (b == 2) ? c2 : (b == 3) ? c3 : c4;
+          const bool on = (i - off_b) < cnt_b;
+          if (on) {
+            s = S.q_m[b][i - off_b];
+            int st = S.state[s];
+            const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
+            const float ht = S.ht[s];
+            const f3 hn = mk3(S.nx[s], S.ny[s], S.nz[s]);
+            const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
+            const DMaterial& m = g_scn.mats[S.hmat[s]];
+            const f3 refl = reflect(d, hn);       // shared by Phong eval/sample, mirror, glass (materials.adb:251,313,371,394)
+            f3 explicitColor = mk3(0.f, 0.f, 0.f);
+            if (RT != GCORE_PT_STUPID) {
+              const f3 sdir = mk3(S.sx[s], S.sy[s], S.sz[s]);
+              float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
+              epsilon = max2(epsilon, 1.0e-30f);
+              const f3 so = hpos + sdir * epsilon;
+              int tri_id; float tri_t, tri_u, tri_v;
+              wave_mesh_result<MESHK>(S, S.cand[s], so, sdir, false, tri_id, tri_t, tri_u, tri_v);
+              DHit hs;                                                        // closest hit; only is_hit / t are read (ray_tracer.adb:117-122)
+              closest_with_mesh<MESHK>(so, sdir, mk3(1.0f / sdir.x, 1.0f / sdir.y, 1.0f / sdir.z), tri_id, tri_t, 0.0f, 0.0f, false, hs);
+              nrays++;
+              const bool shadowed = hs.is_hit && (hs.t < S.sh_thi[s] && hs.t > 10.0f * epsilon);
+              if (!shadowed) {
+                f3 bxdfVal; float bsdfPdf;
+                mat_eval(m, sdir, hn, refl, bxdfVal, bsdfPdf);
+                float cosTheta1 = max2(dot(sdir, hn), 0.0f);
+                f3 intensity = ld3(g_scn.l_intensity);
+                const float ls_pdf = S.ls_pdf[s];
+                if (RT == GCORE_PT_SHADOW) {
+                  explicitColor = intensity * (cosTheta1 * bxdfVal) * (1.0f / max2(ls_pdf, 1.0e-20f));
+                } else {
+                  float lgtPdf = ls_pdf;
+                  float misWeight = lgtPdf * lgtPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf);
+                  explicitColor = intensity * (1.0f / max2(lgtPdf, 1.0e-20f)) * (cosTheta1 * bxdfVal) * misWeight;
+                }
+              }
+            }
+            MatSampleD ms = mat_sample(m, S.r1[s], S.r2[s], d, hn, refl);     // pick up next ray, :116,183,291
+            f3 bxdfVal = ms.color * (1.0f / max2(ms.pdf, 1.0e-20f));
+            float cosTheta = dot(ms.direction, hn);
+            const f3 W = fabsf(cosTheta) * bxdfVal;
+            int depth = st & ST_DEPTH_MASK;
+            wa.stackA[(size_t)depth * total_slots + gslot0 + s] = make_float4(explicitColor.x, explicitColor.y, explicitColor.z, W.x);
+            wa.stackB[(size_t)depth * total_slots + gslot0 + s] = make_float2(W.y, W.z);
+            depth++;
+            const f3 off3 = (sign_ada(cosTheta) * hn) * 1.0e-5f;              // :122,189,297
+            const f3 no = hpos + off3, nd = ms.direction;
+            S.ox[s] = no.x; S.oy[s] = no.y; S.oz[s] = no.z; S.dx[s] = nd.x; S.dy[s] = nd.y; S.dz[s] = nd.z;
+            S.prev_pdf[s] = ms.pdf;
+            st = (st & ~(ST_DEPTH_MASK | ST_SPEC | ST_SURF)) | depth | (ms.pureSpecular ? ST_SPEC : 0);
+            if (depth == max_depth) {                                         // recursion_level = 0 -> (0,0,0)
+              S.lx[s] = 0.f; S.ly[s] = 0.f; S.lz[s] = 0.f;
+              st = (st & ~ST_HASRAY) | ST_FOLD;
+              ended = true;
+            } else {
+              newray = true;
+              push_cp = mesh_candidate<MESHK>(no, mk3(1.0f / nd.x, 1.0f / nd.y, 1.0f / nd.z), nmesh);
+            }
+            S.state[s] = st;
+          }
+        } else {
+          // ------------------------------------------------------------- regenerate
+          const int r = i - n_m;
+          const bool on = r < n_r;
+          bool need = false, padded = false;
+          int st = 0, item = -1;
+          if (on) {
+            s = S.q_r[par][r];
+            st = S.state[s];
+            item = S.item[s];
+            if (st & ST_FOLD) {                                               // unwind the recursion: integrators.adb:124,191,299
+              f3 L = mk3(S.lx[s], S.ly[s], S.lz[s]);
+              const int depth = st & ST_DEPTH_MASK;
+#pragma unroll 1
+              for (int k0 = depth - 1; k0 >= 0; k0 -= 4) {                    // four levels of loads in flight at a time
+                float4 A[4]; float2 B[4];
 #pragma unroll
-        for (int k = 1; k < 5; k++) if (i >= S.off_m[k]) b = k;               // warp-uniform: segments are multiples of 32
-        const bool on = (i - S.off_m[b]) < S.cnt_m[b];
-        const int s = on ? (int)S.q_m[i] : 0;
-        bool ended = false, push_t = false;
-        if (on) {
-          int st = S.state[s];
-          const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
-          const float ht = S.ht[s];
-          const f3 hn = mk3(S.nx[s], S.ny[s], S.nz[s]);
-          const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
-          const DMaterial& m = g_scn.mats[S.hmat[s]];
-          const f3 refl = reflect(d, hn);         // shared by Phong eval/sample, mirror, glass (materials.adb:251,313,371,394)
-          f3 explicitColor = mk3(0.f, 0.f, 0.f);
-          if (RT != GCORE_PT_STUPID) {
-            const f3 sdir = mk3(S.sx[s], S.sy[s], S.sz[s]);
-            float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
-            epsilon = max2(epsilon, 1.0e-30f);
-            const f3 so = hpos + sdir * epsilon;
-            DHit hs;                                                          // closest hit; only is_hit / t are read (ray_tracer.adb:117-122)
-            closest_with_mesh<MESHK>(so, sdir, mk3(1.0f / sdir.x, 1.0f / sdir.y, 1.0f / sdir.z), S.stri_id[s], S.stri_t[s], 0.0f, 0.0f, false, hs);
-            nrays++;
-            const bool shadowed = hs.is_hit && (hs.t < S.sh_thi[s] && hs.t > 10.0f * epsilon);
-            if (!shadowed) {
-              f3 bxdfVal; float bsdfPdf;
-              mat_eval(m, sdir, hn, refl, bxdfVal, bsdfPdf);
-              float cosTheta1 = max2(dot(sdir, hn), 0.0f);
-              f3 intensity = ld3(g_scn.l_intensity);
-              const float ls_pdf = S.ls_pdf[s];
-              if (RT == GCORE_PT_SHADOW) {
-                explicitColor = intensity * (cosTheta1 * bxdfVal) * (1.0f / max2(ls_pdf, 1.0e-20f));
-              } else {
-                float lgtPdf = ls_pdf;
-                float misWeight = lgtPdf * lgtPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf);
-                explicitColor = intensity * (1.0f / max2(lgtPdf, 1.0e-20f)) * (cosTheta1 * bxdfVal) * misWeight;
+                for (int j = 0; j < 4; j++) {
+                  const int k = (k0 - j >= 0) ? (k0 - j) : 0;
+                  A[j] = wa.stackA[(size_t)k * total_slots + gslot0 + s];
+                  B[j] = wa.stackB[(size_t)k * total_slots + gslot0 + s];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                  if (k0 - j >= 0) {
+                    const f3 W = mk3(A[j].w, B[j].x, B[j].y);
+                    if (RT == GCORE_PT_STUPID) L = W * L;
+                    else L = mk3(A[j].x, A[j].y, A[j].z) + W * L;
+                  }
+                }
+              }
+              const int sub = (st >> ST_SUB_SHIFT) & 3;
+              f3 color = mk3(S.cr[s], S.cg[s], S.cb[s]);
+              bool done;
+              if (aa) {
+                if (sub == 0) color = bg;                                     // :42
+                color = color + L;                                            // :47
+                done = (sub == 3);
+              } else { color = L; done = true; }                              // :60
+              if (done) { wa.colbuf[item] = make_float4(color.x, color.y, color.z, 0.0f); item = -1; }
+              else { S.cr[s] = color.x; S.cg[s] = color.y; S.cb[s] = color.z; }
+              st = (st & ~(ST_FOLD | (3 << ST_SUB_SHIFT))) | (((sub + 1) & 3) << ST_SUB_SHIFT);
+            }
+            need = item < 0;
+            if (!need) S.sample[s] = S.sample[s] + 1u;                        // next sub-pixel sample of the same pass
+          }
+          {                                                                   // next work item (pass, pixel): one atomic per warp
+            const unsigned nm = __ballot_sync(0xffffffffu, need);
+            if (nm) {
+              const int lane = tid & 31, leader = __ffs(nm) - 1;
+              int base = 0;
+              if (lane == leader) base = atomicAdd(&S.pool_next, __popc(nm));
+              base = __shfl_sync(0xffffffffu, base, leader);
+              if (need) {
+                const int got = base + __popc(nm & ((1u << lane) - 1u));
+                starved = true;
+                if (got < S.pool_end) {
+                  const int q = got % a.nslots, unit = got / a.nslots;
+                  const WavePixel px = wave_slot_to_pixel(a, q);
+                  if (px.active) {                                            // (an item of a padding pixel is dropped; the slot asks again next round)
+                    starved = false;
+                    item = got;
+                    S.pixel[s] = (unsigned int)(px.y * a.width + px.x);
+                    S.sample[s] = (unsigned int)(a.first_sample + (aa ? unit * 4 : unit));
+                  } else padded = true;
+                }
+                st &= ~(3 << ST_SUB_SHIFT);
               }
             }
           }
-          MatSampleD ms = mat_sample(m, S.r1[s], S.r2[s], d, hn, refl);       // pick up next ray, :116,183,291
-          f3 bxdfVal = ms.color * (1.0f / max2(ms.pdf, 1.0e-20f));
-          float cosTheta = dot(ms.direction, hn);
-          const f3 W = fabsf(cosTheta) * bxdfVal;
-          int depth = st & ST_DEPTH_MASK;
-          wa.stackA[(size_t)depth * total_slots + gslot0 + s] = make_float4(explicitColor.x, explicitColor.y, explicitColor.z, W.x);
-          wa.stackB[(size_t)depth * total_slots + gslot0 + s] = make_float2(W.y, W.z);
-          depth++;
-          const f3 off = (sign_ada(cosTheta) * hn) * 1.0e-5f;                 // :122,189,297
-          const f3 no = hpos + off, nd = ms.direction;
-          S.ox[s] = no.x; S.oy[s] = no.y; S.oz[s] = no.z; S.dx[s] = nd.x; S.dy[s] = nd.y; S.dz[s] = nd.z;
-          S.prev_pdf[s] = ms.pdf;
-          st = (st & ~(ST_DEPTH_MASK | ST_SPEC | ST_SURF)) | depth | (ms.pureSpecular ? ST_SPEC : 0);
-          if (depth == max_depth) {                                           // recursion_level = 0 -> (0,0,0)
-            S.lx[s] = 0.f; S.ly[s] = 0.f; S.lz[s] = 0.f;
-            st = (st & ~ST_HASRAY) | ST_FOLD;
-            ended = true;
-          } else {
-            S.tri_id[s] = -1;
-            push_t = mesh_candidate<MESHK>(no, mk3(1.0f / nd.x, 1.0f / nd.y, 1.0f / nd.z), nmesh);
+          if (on) {
+            S.item[s] = item;
+            if (!starved) {
+              const int sub = (st >> ST_SUB_SHIFT) & 3;
+              const unsigned int pixel = S.pixel[s];
+              const int py = (int)(pixel / (unsigned int)a.width), pxx = (int)(pixel - (unsigned int)py * (unsigned int)a.width);
+              const f3 o = ld3(g_scn.cam_pos);
+              const f3 d = wave_eye_ray_dir(a, pxx, py, aa ? sub : -1);
+              S.ox[s] = o.x; S.oy[s] = o.y; S.oz[s] = o.z; S.dx[s] = d.x; S.dy[s] = d.y; S.dz[s] = d.z;
+              S.prev_pdf[s] = 1.0f;                                           // StartSample, materials.ads:25
+              st = (st & (3 << ST_SUB_SHIFT)) | ST_SPEC | ST_HASRAY;          // depth 0
+              newray = true;
+              push_cp = mesh_candidate<MESHK>(o, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), nmesh);
+            } else {
+              st &= ~(ST_HASRAY | ST_FOLD);
+              retire = (S.exhausted != 0) && !padded;                         // no work left anywhere: the slot retires
+            }
+            S.state[s] = st;
           }
-          S.state[s] = st;
         }
-        queue_push(ended, S.q_r[par ^ 1], &S.cnt_r[par ^ 1], s);
-        queue_push(push_t, S.q_t, &S.cnt_t, s);
+        const int c = queue_push(push_cp, S.q_cp, &S.cnt_cp, s);
+        if (newray) S.cand[s] = (short)c;
+        // paths that reached Max_Trace_Depth and starved slots wait for the next round's regenerate
+        queue_push(ended || (starved && !retire), S.q_r[par ^ 1], &S.cnt_r[par ^ 1], s);
+        const unsigned rm = __ballot_sync(0xffffffffu, retire);
+        if (rm && (tid & 31) == 0) atomicAdd(&S.retired, __popc(rm));
       }
     }
     __syncthreads();
+    if (S.retired >= WAVE_NS) break;          // uniform: `retired` only changes in Y, which the barrier above closes
+
+    // ================================================================= M2: mesh stage of the new path rays
+    if (tid == 0) S.cnt_r[par] = 0;
     if (tid < 5) S.cnt_m[tid] = 0;
+    wave_mesh_stage<MESHK, false>(S, S.q_cp, S.cnt_cp, tid);
     par ^= 1;
     __syncthreads();
   }
