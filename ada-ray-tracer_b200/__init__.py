@@ -397,3 +397,78 @@ def get_counters():
 
 def synchronize():
     _ck(lib().gcore_synchronize())
+
+
+# ======================================================================================================================
+# Render_Pass over the GPUs of one box: tiles split round-robin, accumulators gathered with NCCL
+# ======================================================================================================================
+class _DevicePtr:
+    """zero-copy view of library-owned device memory for torch (CUDA array interface)"""
+
+    def __init__(self, ptr, nfloats):
+        self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class Tiled_Ray_Tracer:
+    """One instance per process (= per GPU).  Mirrors Ray_Tracer's call sequence (Init_Render / Resize_Viewport /
+    Render_Pass); Render_Pass leaves the resolved frame on rank 0.  torch supplies streams and torch.distributed only."""
+
+    def __init__(self, rt, local_rank=0, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import tiles
+        self.torch, self.tiles = torch, tiles
+        self.rt = rt
+        self.L = lib()
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.device("cuda", local_rank)
+        set_device(local_rank)
+        set_partition(self.rank, self.world)
+        # torch sees the library's stream: NCCL and copies are ordered with the kernels without host syncs
+        self.stream = torch.cuda.ExternalStream(stream_handle(), device=self.device)
+        self.gather = None
+        self.d_ldr = self.d_hdr = self.local = None
+
+    def Resize_Viewport(self, size_x, size_y):
+        torch = self.torch
+        self.rt.Resize_Viewport(size_x, size_y)
+        ptr, nslots = accum_device_ptr()
+        assert nslots == self.tiles.local_slots(size_x, size_y, self.world)
+        with torch.cuda.stream(self.stream):
+            self.local = torch.as_tensor(_DevicePtr(ptr, nslots * 4), device=self.device)
+            if self.gather is None or self.gather.nslots != nslots:
+                self.gather = self.tiles.FrameGather(nslots, 4, self.device, torch.float32, self.group) if self.world > 1 else None
+            if self.rank == 0 and (self.d_ldr is None or self.d_ldr.numel() != size_x * size_y):
+                self.d_ldr = torch.empty(size_x * size_y, dtype=torch.int32, device=self.device)
+                self.d_hdr = None
+
+    def Render_Pass(self, host_ldr=None, want_hdr=False, events=None):
+        """Threads_Num DoPass units on every rank's tiles, gather, resolve on rank 0 (into self.d_ldr / self.d_hdr, device
+        memory); host_ldr: optional pinned int32 tensor that receives the frame on rank 0 (asynchronous copy on the
+        library's stream; synchronize before reading); events: optional 3 torch.cuda.Event recorded on the library's stream."""
+        torch, rt = self.torch, self.rt
+        cfg = rt._cfg()
+        _ck(self.L.gcore_init_render(C.byref(cfg)))
+        if events:
+            events[0].record(self.stream)
+        _ck(self.L.gcore_render_units(rt.Threads_Num, None))
+        if events:
+            events[1].record(self.stream)                # events[0..1]: the render kernels alone
+        npx = rt.width * rt.height
+        with torch.cuda.stream(self.stream):
+            if self.rank == 0 and want_hdr and self.d_hdr is None:
+                self.d_hdr = torch.empty(npx * 4, dtype=torch.float32, device=self.device)
+            hdr_p = C.c_void_p(self.d_hdr.data_ptr()) if (self.rank == 0 and want_hdr) else None
+            if self.world == 1:
+                _ck(self.L.gcore_resolve_device(hdr_p, C.c_void_p(self.d_ldr.data_ptr())))
+            else:
+                allb = self.gather.gather(self.local)
+                if self.rank == 0:
+                    _ck(self.L.gcore_resolve_gathered_device(C.c_void_p(allb.data_ptr()), rt.GetSPP(), hdr_p, C.c_void_p(self.d_ldr.data_ptr())))
+            if self.rank == 0 and host_ldr is not None:
+                host_ldr.copy_(self.d_ldr, non_blocking=True)
+        if events:
+            events[2].record(self.stream)                # events[0..2]: the whole pass on this rank
+        return 2 + (1 if self.rank == 0 else 0)          # kernels launched by this rank: wavefront + fold (+ resolve)

@@ -121,13 +121,16 @@ void free_accum() {
 int alloc_accum() {
   State& s = S();
   if (int rc = ensure_device()) return rc;
-  free_accum();
-  if (s.width <= 0 || s.height <= 0) return 0;
+  if (s.width <= 0 || s.height <= 0) { free_accum(); return 0; }
   int tiles_x = (s.width + GC_TILE - 1) / GC_TILE, tiles_y = (s.height + GC_TILE - 1) / GC_TILE;
   int ntiles = tiles_x * tiles_y;
   int local_tiles = (ntiles + s.world - 1) / s.world;           // equal share per rank (padded) so gathers are uniform
-  s.nslots = local_tiles * GC_TILE * GC_TILE;
-  CU(cudaMalloc(&s.d_accum, sizeof(float4) * (size_t)s.nslots), "cudaMalloc accum");
+  const int nslots = local_tiles * GC_TILE * GC_TILE;
+  if (!s.d_accum || nslots != s.nslots) {                       // same size: keep the allocation, just clear it
+    free_accum();
+    CU(cudaMalloc(&s.d_accum, sizeof(float4) * (size_t)nslots), "cudaMalloc accum");
+    s.nslots = nslots;
+  }
   CU(cudaMemsetAsync(s.d_accum, 0, sizeof(float4) * (size_t)s.nslots, s.stream), "memset accum");
   CU(cudaMemsetAsync(s.d_rays, 0, 4 * sizeof(unsigned long long), s.stream), "memset counters");
   s.last_counters[0] = s.last_counters[1] = s.last_counters[2] = s.last_counters[3] = 0;
@@ -312,11 +315,6 @@ int render_units_locked(int units, gcore_render_stats* stats) {
     if (s.spp == 0) s.spp = 1;
   } else if (units > 0) {
     const int per = s.cfg.anti_aliasing ? 4 : 1;
-    static const bool use_mega = getenv("GCORE_AB_MEGAKERNEL") != nullptr;   // A/B experiments only (to be removed)
-    if (use_mega) {
-      CU(gcore_dev::launch_render(s.cfg.render_type, s.hs.mesh_kind, a, s.stream), "render_kernel");
-      launches = 1; s.spp += units * per;
-    } else {
     // the colour buffer holds one float4 per (pass, pixel): long renders go in chunks of passes
     size_t chunk = GC_COLBUF_CAP_BYTES / (sizeof(float4) * (size_t)s.nslots);
     if (chunk < 1) chunk = 1;
@@ -330,7 +328,6 @@ int render_units_locked(int units, gcore_render_stats* stats) {
       CU(gcore_dev::launch_render_wave(s.cfg.render_type, s.hs.mesh_kind, a, s.wave, n, s.stream), "render_wave_kernel");
       launches += 2;
       s.spp += n * per;                                                  // ray_tracer.adb:168-176
-    }
     }
     samples = pixels * (uint64_t)(units * per);
   }

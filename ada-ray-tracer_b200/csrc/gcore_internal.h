@@ -24,12 +24,10 @@ struct RenderArgs {
   float    zdir;                         // -float(width) / safe_tan(fov/2)   (ray_tracer.adb:67)
   float    half_w, half_h;               // float(width)/2, float(height)/2
   float4*  accum;                        // slot-major accumulator (rgb, unused)
-  unsigned long long* counters;          // [0] += scene queries, [1] += queries inside the mesh bbox, [2] += shaded bounces, [3] += hoisted camera-ray queries
+  unsigned long long* counters;          // [0] += scene queries, [1] += queries inside the mesh bbox, [2] += shaded bounces, [3] unused
 };
 
 cudaError_t upload_scene(const art::DeviceScene* host_copy, cudaStream_t s);
-// render_type: GCORE_PT_STUPID / GCORE_PT_SHADOW / GCORE_PT_MIS
-cudaError_t launch_render(int render_type, int mesh_kind, const RenderArgs& a, cudaStream_t s);   // mesh_kind: DeviceScene::mesh_kind
 // RT_DEBUG / RT_WHITTED: palette of the primary hit written into accum (ray_tracer.adb:208-238)
 cudaError_t launch_debug(int mesh_kind, const RenderArgs& a, cudaStream_t s);
 // primary hits, row-major hits[y*W+x]

@@ -165,42 +165,16 @@ def main():
 
     pkg = ge.load_package()
     L = pkg.lib()
-    pkg.set_device(local_rank)
-    pkg.set_partition(rank, world)
-    scene = pkg.Scene(); scene.Init()
     rt = pkg.Ray_Tracer()
     rt.Threads_Num = units; rt.Anti_Aliasing_On = bool(aa); rt.Max_Trace_Depth = depth; rt.seed = SEED
+    tr = pkg.Tiled_Ray_Tracer(rt, local_rank)            # set_device + tile partition (rank, world) + the library's stream
+    scene = pkg.Scene(); scene.Init()
     rt.Init_Render(getattr(pkg, rtype))
-    rt.Resize_Viewport(width, height)
-
-    # torch sees the library's stream: events, NCCL and the L2 flush are ordered with the kernels
-    stream = torch.cuda.ExternalStream(pkg.stream_handle(), device=torch.device("cuda", local_rank))
+    tr.Resize_Viewport(width, height)
+    stream = tr.stream
     npx = width * height
-    acc_ptr, nslots = pkg.accum_device_ptr()
     with torch.cuda.stream(stream):
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
-        d_ldr = torch.empty(npx, dtype=torch.int32, device="cuda")
-        local = torch.empty(nslots * 4, dtype=torch.float32, device="cuda")
-        gathered = [torch.empty(nslots * 4, dtype=torch.float32, device="cuda") for _ in range(world)] if (world > 1 and rank == 0) else None
-        allb = torch.empty(world * nslots * 4, dtype=torch.float32, device="cuda") if (world > 1 and rank == 0) else None
-    cudart = C.CDLL("libcudart.so")
-    cudart.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
-
-    def device_step():
-        """one Render_Pass, everything resident on the device"""
-        rc = L.gcore_render_units(units, None)
-        if rc != 0:
-            raise RuntimeError(pkg.last_error())
-        if world == 1:
-            L.gcore_resolve_device(None, C.c_void_p(d_ldr.data_ptr()))
-            return 2
-        with torch.cuda.stream(stream):
-            cudart.cudaMemcpyAsync(C.c_void_p(local.data_ptr()), C.c_void_p(acc_ptr), C.c_size_t(nslots * 16), 3, C.c_void_p(stream.cuda_stream))
-            dist.gather(local, gathered, dst=0)
-            if rank == 0:
-                torch.cat(gathered, out=allb)
-                L.gcore_resolve_gathered_device(C.c_void_p(allb.data_ptr()), rt.GetSPP(), None, C.c_void_p(d_ldr.data_ptr()))
-        return 2 if rank == 0 else 1
 
     def barrier():
         if world > 1:
@@ -210,94 +184,64 @@ def main():
     # ---------------------------------------------------------------- value: device-resident, CUDA events
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
-            flush.fill_(1); device_step()
+            flush.fill_(1); tr.Render_Pass()
     barrier()
     c0 = pkg.get_counters()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
     launches = 0
     barrier()
     wall0 = time.perf_counter()
     with torch.cuda.stream(stream):
         for k in range(args.steps):
             flush.fill_(k & 255)                         # L2 flush between timed iterations (outside the events)
-            ev[k][0].record(stream)
-            rc = L.gcore_render_units(units, None)
-            ev[k][1].record(stream)                      # render kernel alone: ev0..ev1
-            if world == 1:
-                L.gcore_resolve_device(None, C.c_void_p(d_ldr.data_ptr())); launches += 2
-            else:
-                cudart.cudaMemcpyAsync(C.c_void_p(local.data_ptr()), C.c_void_p(acc_ptr), C.c_size_t(nslots * 16), 3, C.c_void_p(stream.cuda_stream))
-                dist.gather(local, gathered, dst=0)
-                if rank == 0:
-                    torch.cat(gathered, out=allb)
-                    L.gcore_resolve_gathered_device(C.c_void_p(allb.data_ptr()), rt.GetSPP(), None, C.c_void_p(d_ldr.data_ptr()))
-                launches += 2 if rank == 0 else 1
-            ev[k][2].record(stream)
+            launches += tr.Render_Pass(events=ev[k])     # render kernels, NCCL gather of the accumulators, resolve on rank 0
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if sampler else None
     c1 = pkg.get_counters()
     step_ms = sum(a.elapsed_time(c) for a, _, c in ev)
     kern_ms = sum(a.elapsed_time(b) for a, b, _ in ev)
-    rays_local, mesh_local, bounce_local, hoisted_local = (c1[i] - c0[i] for i in range(4))
+    rays_local, mesh_local, bounce_local, _unused = (c1[i] - c0[i] for i in range(4))
     t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([rays_local, mesh_local, bounce_local, launches, hoisted_local], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([rays_local, mesh_local, bounce_local, launches], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     step_ms, kern_ms = float(t[0]), float(t[1])
-    rays, mesh_q, bounces, launches_all, hoisted = (float(x) for x in cnt)
+    rays, mesh_q, bounces, launches_all = (float(x) for x in cnt)
     value = rays / (step_ms * 1e-3) / 1e6
 
-    # ---------------------------------------------------------------- e2e: C-ABI call with host buffers
+    # ---------------------------------------------------------------- e2e: the public call with HOST buffers, every step:
+    # scene description host -> device, fresh viewport, render, (gather,) resolve, frame device -> pinned host memory
     cfg = rt._cfg()
     ldr_host = torch.empty(npx, dtype=torch.int32).pin_memory()
-    d = ge.load_package()
-    desc_scene = None
-    h2d = d2h = 0
+    h2d = 12 * 1024                                     # sizeof(DeviceScene): the scene block is re-sent each step
+    d2h = 4 * npx + (24 if world == 1 else 0)
     e2e_rays = 0.0
     e2e_s = 0.0
-    if world == 1:
-        st = pkg.RenderStats()
-        h2d = 12 * 1024                                 # sizeof(DeviceScene): the scene block is re-sent each step
-        d2h = 4 * npx + 24
-        for k in range(2 + args.steps):
-            barrier()
-            t0 = time.perf_counter()
-            scene.Init()                                # scene description from host data -> device (dirty => re-upload)
+    st = pkg.RenderStats()
+    for k in range(2 + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        scene.Init()                                    # scene description from host data -> device (dirty => re-upload)
+        if world == 1:                                  # the reference-facing one-shot C-ABI call
             rc = L.gcore_render(C.byref(cfg), width, height, units, None, C.c_void_p(ldr_host.data_ptr()), C.byref(st))
             if rc != 0:
                 raise RuntimeError(pkg.last_error())
             dt = time.perf_counter() - t0
-            if k >= 2:
-                e2e_s += dt; e2e_rays += st.rays
-    else:
-        # N > 1: every rank renders its tiles from a fresh viewport, accumulators gathered with NCCL, rank 0 resolves and
-        # copies the frame to pinned host memory
-        h2d = 12 * 1024; d2h = 4 * npx
-        for k in range(2 + args.steps):
-            barrier()
-            t0 = time.perf_counter()
-            scene.Init()
-            rt.Resize_Viewport(width, height)
-            cc0 = pkg.get_counters()
-            with torch.cuda.stream(stream):
-                L.gcore_render_units(units, None)
-                cudart.cudaMemcpyAsync(C.c_void_p(local.data_ptr()), C.c_void_p(pkg.accum_device_ptr()[0]), C.c_size_t(nslots * 16), 3, C.c_void_p(stream.cuda_stream))
-                dist.gather(local, gathered, dst=0)
-                if rank == 0:
-                    torch.cat(gathered, out=allb)
-                    L.gcore_resolve_gathered_device(C.c_void_p(allb.data_ptr()), rt.GetSPP(), None, C.c_void_p(d_ldr.data_ptr()))
-                    ldr_host.copy_(d_ldr, non_blocking=True)
+            r_step = float(st.rays)
+        else:
+            tr.Resize_Viewport(width, height)           # clears the accumulator and the counters
+            tr.Render_Pass(host_ldr=ldr_host)
             barrier()
             dt = time.perf_counter() - t0
-            cc1 = pkg.get_counters()
-            r = torch.tensor([cc1[0] - cc0[0], dt], dtype=torch.float64, device="cuda")
+            r = torch.tensor([float(pkg.get_counters()[0]), dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(r[0:1], op=dist.ReduceOp.SUM); dist.all_reduce(r[1:2], op=dist.ReduceOp.MAX)
-            if k >= 2:
-                e2e_rays += float(r[0]); e2e_s += float(r[1])
+            r_step, dt = float(r[0]), float(r[1])
+        if k >= 2:
+            e2e_s += dt; e2e_rays += r_step
     e2e_value = e2e_rays / e2e_s / 1e6
 
     if rank == 0:
@@ -314,13 +258,22 @@ def main():
         kern_s = kern_ms * 1e-3 / args.steps
         achieved = flop_per_launch / kern_s / 1e12
         peak = sms * 128 * sm_mhz * 1e6 / 1e12          # one non-FMA FP32 op per lane per cycle at the clock seen under load
+        traffic = None
+        try:                                            # dram bytes per launch of the same workload from the committed ncu capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tj.get("workload") == args.workload and world == 1:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        hbm_bytes = (2 * units + 2) * 16.0 * npx / world   # per-pass colours written + read back by the fold, accumulator read + write
         roofline = {"bound": "fp32_issue", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None,
-                    "note": "analytic scene lives in constant memory: HBM traffic is the 16 B/pixel accumulator only, so the bound "
-                            "is FP32 instruction issue (SURVEY 8d), not hbm/tensor; peak = SMs x 128 lanes x SM clock sampled during "
-                            "the run (no measured FP32 peak in MEASURED_PEAKS.json; -fmad=false => 1 flop per lane-instruction)",
-                    "kernel": "render_kernel<PT_MIS>", "kernel_ms_per_launch": kern_ms / args.steps,
-                    "hbm_view": {"achieved_GBs": 2 * 16.0 * npx / world / kern_s / 1e9, "peak_GBs": peaks.get("hbm_gbs", 6650.0),
+                    "traffic": traffic,
+                    "note": "analytic scene lives in constant memory: HBM traffic is only the per-pass colour buffer, so the bound "
+                            "is FP32 instruction issue (SURVEY 8d), not hbm/tensor; achieved = algorithmic flops of the reference "
+                            "(564 / 140 per scene query, 200 per bounce) / kernel time; peak = SMs x 128 lanes x SM clock sampled "
+                            "during the run (no measured FP32 peak in MEASURED_PEAKS.json; -fmad=false => 1 flop per lane-instruction)",
+                    "kernel": "render_wave_kernel<%s> + fold_kernel" % rtype, "kernel_ms_per_launch": kern_ms / args.steps,
+                    "hbm_view": {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_GBs": hbm_bytes / kern_s / 1e9, "peak_GBs": peaks.get("hbm_gbs", 6650.0),
                                  "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"}}
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
@@ -338,8 +291,7 @@ def main():
                            "l2": "256 MiB buffer written between timed steps (outside the per-step CUDA events); inputs are < L2",
                            "numerics": "bit-exact mode (-fmad=false, IEEE div/sqrt), identical to the CPU oracle"},
                 "msamples_per_s": (npx * units * (4 if aa else 1)) / (step_ms / args.steps * 1e-3) / 1e6,
-                "rays_per_step": rays / args.steps, "hoisted_rays_per_step": hoisted / args.steps,
-                "reference_equivalent_mrays_per_s": (rays + hoisted) / (step_ms * 1e-3) / 1e6, "wall_s": wall,
+                "rays_per_step": rays / args.steps, "wall_s": wall,
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                           "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": int(launches_all), "roofline": roofline, "cpu_baseline": cpu_baseline}
