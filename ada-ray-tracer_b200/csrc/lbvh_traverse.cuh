@@ -33,7 +33,7 @@ ART_D bool slab_hit(float bminx, float bminy, float bminz, float bmaxx, float bm
 }
 
 ART_D void bvh_leaf_test(const BvhView& bv, int first, int count, f3 o, f3 d, float t_min,
-                         float& best_t, int& best_prim, float& best_u, float& best_v) {
+                         float& best_t, int& best_prim, float& best_u, float& best_v, int& best_slot) {
 #pragma unroll 1
   for (int s = first; s < first + count; s++) {
     float4 a  = __ldg(&bv.tris[3 * s + 0]);
@@ -43,17 +43,18 @@ ART_D void bvh_leaf_test(const BvhView& bv, int first, int count, f3 o, f3 d, fl
     float t, u, v;
     // closed upper bound so that equal-t candidates reach the tie rule: test against nextafter(best_t)
     if (intersect_triangle(o, d, mk3(a.x, a.y, a.z), mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z), t_min, ART_FLT_LAST, t, u, v)) {
-      if (t < best_t || (t == best_t && best_prim >= 0 && prim < best_prim)) { best_t = t; best_prim = prim; best_u = u; best_v = v; }
+      if (t < best_t || (t == best_t && best_prim >= 0 && prim < best_prim)) { best_t = t; best_prim = prim; best_u = u; best_v = v; best_slot = s; }
     }
   }
 }
 
-// closest hit; prim = -1 when nothing is hit inside (t_min, t_max)
-ART_D void bvh_closest(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, float t_max, int& prim_o, float& t_o, float& u_o, float& v_o) {
-  float best_t = t_max; int best_prim = -1; float best_u = 0.0f, best_v = 0.0f;
+// closest hit; prim = -1 when nothing is hit inside (t_min, t_max); slot = position of the winner in the Morton-ordered
+// triangle array (for callers that want its edges)
+ART_D void bvh_closest_slot(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, float t_max, int& prim_o, float& t_o, float& u_o, float& v_o, int& slot_o) {
+  float best_t = t_max; int best_prim = -1; float best_u = 0.0f, best_v = 0.0f; int best_slot = -1;
   if (bv.ntris > 0) {
     if (bv.root < 0) {
-      bvh_leaf_test(bv, 0, bv.ntris, o, d, t_min, best_t, best_prim, best_u, best_v);
+      bvh_leaf_test(bv, 0, bv.ntris, o, d, t_min, best_t, best_prim, best_u, best_v, best_slot);
     } else {
       int stack[LBVH_STACK];
       int sp = 0;
@@ -67,8 +68,8 @@ ART_D void bvh_closest(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, float
         float e0, e1;
         bool h0 = slab_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, best_t, e0);
         bool h1 = slab_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, best_t, e1);
-        if (h0 && c0 < 0) { bvh_leaf_test(bv, ~c0, __float_as_int(n3.z), o, d, t_min, best_t, best_prim, best_u, best_v); h0 = false; }
-        if (h1 && c1 < 0) { bvh_leaf_test(bv, ~c1, __float_as_int(n3.w), o, d, t_min, best_t, best_prim, best_u, best_v); h1 = false; }
+        if (h0 && c0 < 0) { bvh_leaf_test(bv, ~c0, __float_as_int(n3.z), o, d, t_min, best_t, best_prim, best_u, best_v, best_slot); h0 = false; }
+        if (h1 && c1 < 0) { bvh_leaf_test(bv, ~c1, __float_as_int(n3.w), o, d, t_min, best_t, best_prim, best_u, best_v, best_slot); h1 = false; }
         if (h0 && h1) {
           // near child first, far child on the stack
           if (e1 < e0) { int t = c0; c0 = c1; c1 = t; }
@@ -82,7 +83,12 @@ ART_D void bvh_closest(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, float
   }
   prim_o = (best_t < t_max || best_prim >= 0) ? best_prim : -1;
   if (best_prim < 0) prim_o = -1;
-  t_o = best_t; u_o = best_u; v_o = best_v;
+  t_o = best_t; u_o = best_u; v_o = best_v; slot_o = best_slot;
+}
+
+ART_D void bvh_closest(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, float t_max, int& prim_o, float& t_o, float& u_o, float& v_o) {
+  int slot;
+  bvh_closest_slot(bv, o, d, inv, t_min, t_max, prim_o, t_o, u_o, v_o, slot);
 }
 
 }  // namespace art

@@ -126,14 +126,16 @@ __global__ void __launch_bounds__(RENDER_BLOCK) bvh_batch_kernel(int n, const gc
                                                                  gcore_HitCpp* __restrict__ hits, int* __restrict__ found) {
   const int i = blockIdx.x * RENDER_BLOCK + threadIdx.x;
   if (i >= n) return;
-  int prim; float t, u, v;
+  int prim, slot; float t, u, v;
   const f3 o = ld3(rays[i].origin), d = ld3(rays[i].direction);
-  bvh_closest(g_scn.bvh_legacy, o, d, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), t_near, t_far, prim, t, u, v);
+  bvh_closest_slot(g_scn.bvh_legacy, o, d, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), t_near, t_far, prim, t, u, v, slot);
   found[i] = (prim >= 0) ? 1 : 0;
   if (prim >= 0) {
     gcore_HitCpp hc;
     hc.primIndex = prim; hc.geomIndex = 0; hc.instIndex = 0; hc.t = t;
-    hc.normal[0] = 0.f; hc.normal[1] = 0.f; hc.normal[2] = 0.f;
+    const float4 e1 = __ldg(&g_scn.bvh_legacy.tris[3 * slot + 1]), e2 = __ldg(&g_scn.bvh_legacy.tris[3 * slot + 2]);
+    const f3 ng = cross(mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z));       // Ng = (B - A) x (C - A), unnormalised like Embree's
+    hc.normal[0] = ng.x; hc.normal[1] = ng.y; hc.normal[2] = ng.z;
     hc.texCoord[0] = v; hc.texCoord[1] = u;                 // reference v weighs B, u weighs C (geometry.adb:245-246, 301)
     hits[i] = hc;
   }

@@ -56,6 +56,15 @@ def _check(found, hits, prim, t, u, v):
     assert np.all(hits["primIndex"][~m] == -1)                         # records are only written on a hit
 
 
+def _check_ng(hits, prim, verts, tris):
+    """HitCpp.normal = unnormalised geometric normal (B - A) x (C - A) of the hit triangle, like Embree's Ng"""
+    m = prim >= 0
+    A, B, C = verts[tris[prim[m], 0]], verts[tris[prim[m], 1]], verts[tris[prim[m], 2]]
+    e1, e2 = (B - A).astype(np.float32), (C - A).astype(np.float32)
+    ng = np.stack([e1[:, 1] * e2[:, 2] - e2[:, 1] * e1[:, 2], e1[:, 2] * e2[:, 0] - e2[:, 2] * e1[:, 0], e1[:, 0] * e2[:, 1] - e2[:, 0] * e1[:, 1]], 1)
+    assert np.array_equal(_bits(hits["normal"][m]), _bits(ng))
+
+
 @pytest.mark.parametrize("ntris", [1, 2, 3, 17, 2000])
 def test_legacy_seam_random_soup(pkg, ob, ntris):
     rng = np.random.default_rng(100 + ntris)
@@ -68,6 +77,7 @@ def test_legacy_seam_random_soup(pkg, ob, ntris):
     found, hits = gc.closest_hit_batch(rays, 0.0, 100000.0)
     prim, t, u, v = _brute(ob, verts, tris, rays, 0.0, 100000.0)
     _check(found, hits, prim, t, u, v)
+    _check_ng(hits, prim, verts, tris)
     if ntris >= 17:
         assert (prim >= 0).sum() > 50
     info = gc.bvh_info()
