@@ -63,7 +63,7 @@ EXPORTS = [
     "gcore_bvh_closest_hit_batch", "gcore_set_device", "gcore_set_partition", "gcore_init_render",
     "gcore_resize_viewport", "gcore_render_units", "gcore_get_counters", "gcore_get_spp", "gcore_read_frame", "gcore_render",
     "gcore_primary_hits", "gcore_accum_device_ptr", "gcore_resolve_device", "gcore_resolve_gathered_device",
-    "gcore_stream", "gcore_synchronize", "gcore_last_error", "gcore_bvh_info", "gcore_kernel_regs",
+    "gcore_stream", "gcore_synchronize", "gcore_last_error", "gcore_bvh_info", "gcore_kernel_regs", "gcore_bvh_bench",
 ]
 
 _lib = None
@@ -113,6 +113,7 @@ def lib():
     L.gcore_last_error.argtypes = [C.c_char_p, i32]
     L.gcore_bvh_info.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(f32)]
     L.gcore_kernel_regs.argtypes = [i32]
+    L.gcore_bvh_bench.argtypes = [i32, vp, f32, f32, i32, i32, C.POINTER(f32), vp]
     _lib = L
     return L
 
@@ -366,6 +367,17 @@ class Bitmap:
         with open(a_fileName, "wb") as f:
             f.write(hdr.tobytes())
             f.write(body.tobytes())
+
+
+def bvh_bench(rays, which=1, repeat=5, t_near=0.0, t_far=1000000.0):
+    """traversal micro-benchmark: -> dict(ms, mrays_s, nodes_per_ray, tris_per_ray, bytes_per_ray, hit_rate)"""
+    rays = np.ascontiguousarray(rays, ray_dt)
+    ms = C.c_float(); st = np.zeros(3, np.uint64)
+    _ck(lib().gcore_bvh_bench(len(rays), _p(rays), t_near, t_far, which, repeat, C.byref(ms), _p(st)))
+    n = float(len(rays))
+    nodes, tris = st[0] / n, st[1] / n
+    return {"ms": ms.value, "mrays_s": n / (ms.value * 1e-3) / 1e6, "nodes_per_ray": float(nodes), "tris_per_ray": float(tris),
+            "bytes_per_ray": float(64.0 * nodes + 48.0 * tris + 24 + 40), "hit_rate": float(st[2] / n)}
 
 
 def set_device(device):

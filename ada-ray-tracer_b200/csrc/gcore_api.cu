@@ -142,12 +142,12 @@ int alloc_accum() {
 #define GC_COLBUF_CAP_BYTES ((size_t)2 << 30)
 int ensure_wave_buffers(size_t items) {
   State& s = S();
-  if (!s.wave.grid) {
+  if (!s.wave.sm_count) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, s.device), "cudaGetDeviceProperties");
     s.sm_count = prop.multiProcessorCount;
-    s.wave.grid = s.sm_count * gcore_dev::wave_blocks_per_sm();             // persistent: one wave of resident blocks
-    const size_t total_slots = (size_t)s.wave.grid * gcore_dev::wave_slots_per_block();
+    s.wave.sm_count = s.sm_count;
+    const size_t total_slots = (size_t)gcore_dev::wave_total_slots(s.sm_count);
     CU(cudaMalloc(&s.wave.stackA, sizeof(float4) * total_slots * gcore_dev::wave_max_depth()), "cudaMalloc stackA");
     CU(cudaMalloc(&s.wave.stackB, sizeof(float2) * total_slots * gcore_dev::wave_max_depth()), "cudaMalloc stackB");
     CU(cudaMalloc(&s.wave.next_item, sizeof(unsigned int)), "cudaMalloc next_item");
@@ -540,6 +540,34 @@ int gcore_bvh_closest_hit_batch(int n, const gcore_ray* rays, float t_near, floa
     int flat = hits[i].primIndex;
     if (flat >= 0 && flat < (int)s.h_legacy_prim.size()) { hits[i].primIndex = s.h_legacy_prim[flat]; hits[i].instIndex = s.h_legacy_inst[flat]; hits[i].geomIndex = 0; }
   }
+  return 0;
+}
+
+int gcore_bvh_bench(int n, const gcore_ray* rays, float t_near, float t_far, int which, int repeat, float* ms_per_launch, uint64_t* stats3) {
+  State& s = S();
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  if (n <= 0 || !rays || repeat < 1 || which < 0 || which > 1) return fail(GCORE_E_ARG, "gcore_bvh_bench: bad arguments");
+  if (int rc = sync_scene()) return rc;
+  if ((which ? s.mesh_bvh.ntris : s.legacy_bvh.ntris) <= 0) return fail(GCORE_E_STATE, "gcore_bvh_bench: no LBVH of that kind is built");
+  gcore_ray* d_r = nullptr; gcore_HitCpp* d_h = nullptr; int* d_f = nullptr; unsigned long long* d_c = nullptr;
+  auto cleanup = [&]() { cudaFree(d_r); cudaFree(d_h); cudaFree(d_f); cudaFree(d_c); };
+  cudaError_t e;
+  if ((e = cudaMalloc(&d_r, sizeof(gcore_ray) * (size_t)n)) != cudaSuccess || (e = cudaMalloc(&d_h, sizeof(gcore_HitCpp) * (size_t)n)) != cudaSuccess ||
+      (e = cudaMalloc(&d_f, 4 * (size_t)n)) != cudaSuccess || (e = cudaMalloc(&d_c, 24)) != cudaSuccess) { cleanup(); return fail_cuda(e, "cudaMalloc bvh bench"); }
+  cudaMemcpyAsync(d_r, rays, sizeof(gcore_ray) * (size_t)n, cudaMemcpyHostToDevice, s.stream);
+  cudaMemsetAsync(d_c, 0, 24, s.stream);
+  e = gcore_dev::launch_bvh_batch_which(n, d_r, t_near, t_far, d_h, d_f, which, d_c, s.stream);          // counting pass (also the warm-up)
+  unsigned long long c[3] = {0, 0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c, d_c, 24, cudaMemcpyDeviceToHost, s.stream);
+  if (e == cudaSuccess) e = cudaEventRecord(s.ev0, s.stream);
+  for (int k = 0; k < repeat && e == cudaSuccess; k++) e = gcore_dev::launch_bvh_batch_which(n, d_r, t_near, t_far, d_h, d_f, which, nullptr, s.stream);
+  if (e == cudaSuccess) e = cudaEventRecord(s.ev1, s.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+  cleanup();
+  if (e != cudaSuccess) return fail_cuda(e, "bvh bench");
+  float ms = 0.f; cudaEventElapsedTime(&ms, s.ev0, s.ev1);
+  if (ms_per_launch) *ms_per_launch = ms / (float)repeat;
+  if (stats3) { stats3[0] = c[0]; stats3[1] = c[1]; stats3[2] = c[2]; }
   return 0;
 }
 

@@ -35,6 +35,10 @@ cudaError_t launch_primary_hits(int mesh_kind, const RenderArgs& a, gcore_hit* d
 cudaError_t launch_closest_batch(int mesh_kind, int n, const gcore_ray* d_rays, gcore_hit* d_hits, cudaStream_t s);
 // pure triangle query on the committed LBVH (legacy gcore_closest_hit semantics)
 cudaError_t launch_bvh_batch(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, cudaStream_t s);
+// the same kernel on either LBVH (which: 0 legacy scene, 1 shaded mesh); d_counters != null: also count nodes visited,
+// triangle slots tested and hits into d_counters[0..2]
+cudaError_t launch_bvh_batch_which(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, int which,
+                                   unsigned long long* d_counters, cudaStream_t s);
 // slot-major accumulator -> row-major outputs; either pointer may be null.
 // hdr4[y*W+x] = (r,g,b,spp), ldr[y*W+x] = R | G<<8 | B<<16 (ray_tracer.adb:281-291, 19-57)
 cudaError_t launch_resolve(const RenderArgs& a, int spp, float4* d_hdr4, uint32_t* d_ldr, cudaStream_t s);
@@ -46,13 +50,12 @@ int render_kernel_regs(int render_type);
 struct WaveBuffers {
   float4* colbuf = nullptr;              // [units][nslots] colour of every (pass, pixel) work item
   size_t  colbuf_items = 0;
-  float4* stackA = nullptr;              // [max_depth][grid * slots_per_block] per-bounce (explicit.xyz, weight.x)
+  float4* stackA = nullptr;              // [max_depth][wave_total_slots] per-bounce (explicit.xyz, weight.x)
   float2* stackB = nullptr;              //                                                (weight.y, weight.z)
   unsigned int* next_item = nullptr;     // global work counter
-  int     grid = 0;
+  int     sm_count = 0;
 };
-int wave_slots_per_block();
-int wave_blocks_per_sm();
+int wave_total_slots(int sm_count);      // path slots resident on the device (grid * slots per block)
 int wave_max_depth();
 // `units` DoPass units over this rank's slots (units * nslots < 2^31): wavefront kernel + fold into a.accum
 cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, cudaStream_t s);

@@ -32,6 +32,8 @@ ART_D bool slab_hit(float bminx, float bminy, float bminz, float bmaxx, float bm
   return tn <= tf * 1.00001f + 1.0e-6f;
 }
 
+struct BvhStats { unsigned int nodes, tris; };     // nodes visited (64 B each), triangle slots tested (48 B each)
+
 ART_D void bvh_leaf_test(const BvhView& bv, int first, int count, f3 o, f3 d, float t_min,
                          float& best_t, int& best_prim, float& best_u, float& best_v, int& best_slot) {
 #pragma unroll 1
@@ -50,7 +52,9 @@ ART_D void bvh_leaf_test(const BvhView& bv, int first, int count, f3 o, f3 d, fl
 
 // closest hit; prim = -1 when nothing is hit inside (t_min, t_max); slot = position of the winner in the Morton-ordered
 // triangle array (for callers that want its edges)
-ART_D void bvh_closest_slot(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, float t_max, int& prim_o, float& t_o, float& u_o, float& v_o, int& slot_o) {
+template <bool STATS>
+ART_D void bvh_closest_slot_t(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, float t_max, int& prim_o, float& t_o, float& u_o, float& v_o, int& slot_o,
+                              BvhStats& st) {
   float best_t = t_max; int best_prim = -1; float best_u = 0.0f, best_v = 0.0f; int best_slot = -1;
   if (bv.ntris > 0) {
     if (bv.root < 0) {
@@ -60,6 +64,7 @@ ART_D void bvh_closest_slot(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, 
       int sp = 0;
       int node = bv.root;
       for (;;) {
+        if (STATS) st.nodes++;
         float4 n0 = __ldg(&bv.nodes[4 * node + 0]);
         float4 n1 = __ldg(&bv.nodes[4 * node + 1]);
         float4 n2 = __ldg(&bv.nodes[4 * node + 2]);
@@ -68,6 +73,7 @@ ART_D void bvh_closest_slot(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, 
         float e0, e1;
         bool h0 = slab_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, best_t, e0);
         bool h1 = slab_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, best_t, e1);
+        if (STATS) { if (h0 && c0 < 0) st.tris += __float_as_int(n3.z); if (h1 && c1 < 0) st.tris += __float_as_int(n3.w); }
         if (h0 && c0 < 0) { bvh_leaf_test(bv, ~c0, __float_as_int(n3.z), o, d, t_min, best_t, best_prim, best_u, best_v, best_slot); h0 = false; }
         if (h1 && c1 < 0) { bvh_leaf_test(bv, ~c1, __float_as_int(n3.w), o, d, t_min, best_t, best_prim, best_u, best_v, best_slot); h1 = false; }
         if (h0 && h1) {
@@ -84,6 +90,11 @@ ART_D void bvh_closest_slot(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, 
   prim_o = (best_t < t_max || best_prim >= 0) ? best_prim : -1;
   if (best_prim < 0) prim_o = -1;
   t_o = best_t; u_o = best_u; v_o = best_v; slot_o = best_slot;
+}
+
+ART_D void bvh_closest_slot(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, float t_max, int& prim_o, float& t_o, float& u_o, float& v_o, int& slot_o) {
+  BvhStats st;
+  bvh_closest_slot_t<false>(bv, o, d, inv, t_min, t_max, prim_o, t_o, u_o, v_o, slot_o, st);
 }
 
 ART_D void bvh_closest(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, float t_max, int& prim_o, float& t_o, float& u_o, float& v_o) {

@@ -122,18 +122,32 @@ __global__ void __launch_bounds__(RENDER_BLOCK) closest_kernel(int n, const gcor
   store_hit(&hits[i], h);
 }
 
+// STATS: also count the nodes visited / triangle slots tested (counters[0], [1]) and the hits ([2]); which: 0 = the scene
+// committed through the legacy seam, 1 = the shaded mesh of the renderer
+template <bool STATS>
 __global__ void __launch_bounds__(RENDER_BLOCK) bvh_batch_kernel(int n, const gcore_ray* __restrict__ rays, float t_near, float t_far,
-                                                                 gcore_HitCpp* __restrict__ hits, int* __restrict__ found) {
+                                                                 gcore_HitCpp* __restrict__ hits, int* __restrict__ found, int which,
+                                                                 unsigned long long* __restrict__ counters) {
   const int i = blockIdx.x * RENDER_BLOCK + threadIdx.x;
+  const BvhView& bv = which ? g_scn.bvh : g_scn.bvh_legacy;
+  int prim = -1, slot = -1; float t = 0.f, u = 0.f, v = 0.f;
+  BvhStats st; st.nodes = 0; st.tris = 0;
+  f3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f);
+  if (i < n) {
+    o = ld3(rays[i].origin); d = ld3(rays[i].direction);
+    bvh_closest_slot_t<STATS>(bv, o, d, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), t_near, t_far, prim, t, u, v, slot, st);
+  }
+  if (STATS) {
+    unsigned int a = __reduce_add_sync(0xffffffffu, st.nodes), b = __reduce_add_sync(0xffffffffu, st.tris);
+    unsigned int c = __reduce_add_sync(0xffffffffu, (unsigned int)(prim >= 0));
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&counters[0], (unsigned long long)a); atomicAdd(&counters[1], (unsigned long long)b); atomicAdd(&counters[2], (unsigned long long)c); }
+  }
   if (i >= n) return;
-  int prim, slot; float t, u, v;
-  const f3 o = ld3(rays[i].origin), d = ld3(rays[i].direction);
-  bvh_closest_slot(g_scn.bvh_legacy, o, d, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), t_near, t_far, prim, t, u, v, slot);
   found[i] = (prim >= 0) ? 1 : 0;
   if (prim >= 0) {
     gcore_HitCpp hc;
     hc.primIndex = prim; hc.geomIndex = 0; hc.instIndex = 0; hc.t = t;
-    const float4 e1 = __ldg(&g_scn.bvh_legacy.tris[3 * slot + 1]), e2 = __ldg(&g_scn.bvh_legacy.tris[3 * slot + 2]);
+    const float4 e1 = __ldg(&bv.tris[3 * slot + 1]), e2 = __ldg(&bv.tris[3 * slot + 2]);
     const f3 ng = cross(mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z));       // Ng = (B - A) x (C - A), unnormalised like Embree's
     hc.normal[0] = ng.x; hc.normal[1] = ng.y; hc.normal[2] = ng.z;
     hc.texCoord[0] = v; hc.texCoord[1] = u;                 // reference v weighs B, u weighs C (geometry.adb:245-246, 301)
@@ -201,7 +215,15 @@ cudaError_t launch_closest_batch(int mesh_kind, int n, const gcore_ray* d_rays, 
 
 cudaError_t launch_bvh_batch(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  bvh_batch_kernel<<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, d_hits, d_found);
+  bvh_batch_kernel<false><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, d_hits, d_found, 0, nullptr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bvh_batch_which(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, int which,
+                                   unsigned long long* d_counters, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  if (d_counters) bvh_batch_kernel<true><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, d_hits, d_found, which, d_counters);
+  else bvh_batch_kernel<false><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, d_hits, d_found, which, nullptr);
   return cudaGetLastError();
 }
 
@@ -218,30 +240,37 @@ cudaError_t launch_resolve_gathered(const RenderArgs& a, const float4* d_all, in
 }
 
 // ---- block-synchronous wavefront render (render_wave.cuh) ----
-template <int RT, int MESHK>
-static cudaError_t launch_wave_t(const art::WaveArgs& wa, int grid, cudaStream_t s) {
+template <int RT, int MESHK, int NT>
+static cudaError_t launch_wave_t(const art::WaveArgs& wa, int sm_count, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(art::render_wave_kernel<RT, MESHK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(art::WaveSmem));
+    cudaError_t e = cudaFuncSetAttribute(art::render_wave_kernel<RT, MESHK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(art::WaveSmem<NT>));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  art::render_wave_kernel<RT, MESHK><<<grid, WAVE_THREADS, sizeof(art::WaveSmem), s>>>(wa);
+  const int grid = sm_count * (WAVE_TOTAL_THREADS / NT);                     // persistent: one wave of resident blocks
+  art::render_wave_kernel<RT, MESHK, NT><<<grid, NT, sizeof(art::WaveSmem<NT>), s>>>(wa);
   return cudaGetLastError();
 }
 
-template <int MESHK>
-static cudaError_t launch_wave_m(int render_type, const art::WaveArgs& wa, int grid, cudaStream_t s) {
+template <int MESHK, int NT>
+static cudaError_t launch_wave_m(int render_type, const art::WaveArgs& wa, int sm_count, cudaStream_t s) {
   switch (render_type) {
-    case GCORE_PT_STUPID: return launch_wave_t<GCORE_PT_STUPID, MESHK>(wa, grid, s);
-    case GCORE_PT_SHADOW: return launch_wave_t<GCORE_PT_SHADOW, MESHK>(wa, grid, s);
-    case GCORE_PT_MIS:    return launch_wave_t<GCORE_PT_MIS, MESHK>(wa, grid, s);
+    case GCORE_PT_STUPID: return launch_wave_t<GCORE_PT_STUPID, MESHK, NT>(wa, sm_count, s);
+    case GCORE_PT_SHADOW: return launch_wave_t<GCORE_PT_SHADOW, MESHK, NT>(wa, sm_count, s);
+    case GCORE_PT_MIS:    return launch_wave_t<GCORE_PT_MIS, MESHK, NT>(wa, sm_count, s);
     default: return cudaErrorInvalidValue;
   }
 }
 
-int wave_slots_per_block() { return WAVE_NS; }
-int wave_blocks_per_sm() { return WAVE_MINB; }
+#ifndef WAVE_NT_CONST
+#define WAVE_NT_CONST 1024
+#endif
+#ifndef WAVE_NT_BVH
+#define WAVE_NT_BVH 128
+#endif
+
+int wave_total_slots(int sm_count) { return sm_count * WAVE_TOTAL_THREADS; }   // the same for every block shape
 int wave_max_depth() { return WAVE_MAX_DEPTH; }
 
 cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, cudaStream_t s) {
@@ -250,7 +279,8 @@ cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs&
   wa.r = a; wa.colbuf = wb.colbuf; wa.stackA = wb.stackA; wa.stackB = wb.stackB; wa.next_item = wb.next_item; wa.units = units;
   cudaError_t e = cudaMemsetAsync(wb.next_item, 0, sizeof(unsigned int), s);
   if (e != cudaSuccess) return e;
-  e = (mesh_kind == 2) ? launch_wave_m<MESHK_BVH>(render_type, wa, wb.grid, s) : launch_wave_m<MESHK_CONST>(render_type, wa, wb.grid, s);
+  e = (mesh_kind == 2) ? launch_wave_m<MESHK_BVH, WAVE_NT_BVH>(render_type, wa, wb.sm_count, s)
+                       : launch_wave_m<MESHK_CONST, WAVE_NT_CONST>(render_type, wa, wb.sm_count, s);
   if (e != cudaSuccess) return e;
   art::fold_kernel<<<blocks_for(a.nslots, 256), 256, 0, s>>>(a, wb.colbuf, units);
   return cudaGetLastError();
@@ -260,9 +290,9 @@ int render_kernel_regs(int render_type) {
   cudaFuncAttributes at;
   cudaError_t e;
   switch (render_type) {
-    case GCORE_PT_STUPID: e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_STUPID, MESHK_CONST>); break;
-    case GCORE_PT_SHADOW: e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_SHADOW, MESHK_CONST>); break;
-    default:              e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_MIS, MESHK_CONST>); break;
+    case GCORE_PT_STUPID: e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_STUPID, MESHK_CONST, WAVE_NT_CONST>); break;
+    case GCORE_PT_SHADOW: e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_SHADOW, MESHK_CONST, WAVE_NT_CONST>); break;
+    default:              e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_MIS, MESHK_CONST, WAVE_NT_CONST>); break;
   }
   if (e != cudaSuccess) { cudaGetLastError(); return -1; }
   return at.numRegs;

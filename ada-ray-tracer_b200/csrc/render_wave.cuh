@@ -35,38 +35,36 @@
 
 namespace art {
 
-#ifndef WAVE_THREADS
-#define WAVE_THREADS 1024
-#endif
-#ifndef WAVE_MINB
-#define WAVE_MINB 1
-#endif
-#define WAVE_NS WAVE_THREADS              // path slots per block
-#define WAVE_BATCH (2 * WAVE_NS)          // work items fetched from the global counter at a time
+// Block shape: NT threads = NT path slots per block, 1024 / NT blocks per SM (template parameter of the kernel).
+//   constant-memory meshes: 1024 x 1 -- the biggest slot pool wins (measured 256x4 105 ms, 384x3 93, 512x2 85.5, 1024x1 77.4)
+//   LBVH meshes:            128 x 8 -- the traversal stages are long and latency-bound, so several smaller
+//                           blocks per SM overlap one block's traversal with the others' stages (C5: 1024x1 4199 ms, 512x2 3746, 256x4 3309, 128x8 2908)
+#define WAVE_TOTAL_THREADS 1024
 #define WAVE_MAX_DEPTH 16
 
 #define WAVE_PAIR_TRIS 8                  // constant-memory meshes up to this size are tested as (ray, triangle) pairs
 
 enum { ST_DEPTH_MASK = 31, ST_SUB_SHIFT = 5, ST_SPEC = 1 << 7, ST_HASRAY = 1 << 8, ST_FOLD = 1 << 9, ST_SURF = 1 << 10 };
 
+template <int NT>
 struct WaveSmem {
   // path ray
-  float ox[WAVE_NS], oy[WAVE_NS], oz[WAVE_NS], dx[WAVE_NS], dy[WAVE_NS], dz[WAVE_NS];
+  float ox[NT], oy[NT], oz[NT], dx[NT], dy[NT], dz[NT];
   // surface hit + light sample of the current bounce (X -> Y)
-  float ht[WAVE_NS], nx[WAVE_NS], ny[WAVE_NS], nz[WAVE_NS];
-  float sx[WAVE_NS], sy[WAVE_NS], sz[WAVE_NS], ls_pdf[WAVE_NS], sh_thi[WAVE_NS];
-  float r1[WAVE_NS], r2[WAVE_NS];
-  float prev_pdf[WAVE_NS];
+  float ht[NT], nx[NT], ny[NT], nz[NT];
+  float sx[NT], sy[NT], sz[NT], ls_pdf[NT], sh_thi[NT];
+  float r1[NT], r2[NT];
+  float prev_pdf[NT];
   // colour of the work item so far / radiance at the end of the path
-  float cr[WAVE_NS], cg[WAVE_NS], cb[WAVE_NS], lx[WAVE_NS], ly[WAVE_NS], lz[WAVE_NS];
-  int   item[WAVE_NS];                    // unit * nslots + q, or -1: no item
-  unsigned int pixel[WAVE_NS], sample[WAVE_NS];   // Philox key word 1 / counter word 0 of the current path
-  int   state[WAVE_NS];                   // depth | sub << 5 | flags
+  float cr[NT], cg[NT], cb[NT], lx[NT], ly[NT], lz[NT];
+  int   item[NT];                    // unit * nslots + q, or -1: no item
+  unsigned int pixel[NT], sample[NT];   // Philox key word 1 / counter word 0 of the current path
+  int   state[NT];                   // depth | sub << 5 | flags
   // mesh stage results per candidate (see wave_mesh_stage)
-  float mesh_res[WAVE_PAIR_TRIS * WAVE_NS];
-  short cand[WAVE_NS];                    // candidate index of the slot's pending ray in the mesh stage, -1: none
-  short hmat[WAVE_NS];
-  short q_r[2][WAVE_NS], q_cs[WAVE_NS], q_cp[WAVE_NS], q_m[5][WAVE_NS];
+  float mesh_res[WAVE_PAIR_TRIS * NT];
+  short cand[NT];                    // candidate index of the slot's pending ray in the mesh stage, -1: none
+  short hmat[NT];
+  short q_r[2][NT], q_cs[NT], q_cp[NT], q_m[5][NT];
   int   cnt_r[2], cnt_cs, cnt_cp, cnt_m[5];
   int   pool_next, pool_end, exhausted, retired;
 };
@@ -262,12 +260,12 @@ ART_D void triangle_tuv(f3 o, f3 d, f3 A, f3 edge1, f3 edge2, float& t, float& u
 // meshes of up to WAVE_PAIR_TRIS triangles are tested as (ray, triangle) pairs, one triangle test per thread, so the
 // stage is as short as one triangle test (nothing else runs on the SM meanwhile): mesh_res[c * ntris + i] = t of
 // triangle i if its (u, v) test passes, NaN otherwise.  Bigger meshes: one ray per thread, mesh_res[4c..] = t, u, v, id.
-template <int MESHK, bool SHADOW>
-ART_D void wave_mesh_stage(WaveSmem& S, const short* q_c, int n_c, int tid) {
+template <int MESHK, bool SHADOW, int NT>
+ART_D void wave_mesh_stage(WaveSmem<NT>& S, const short* q_c, int n_c, int tid) {
   const int ntris = g_scn.ntris_bf;
   const bool pair_mode = (MESHK == MESHK_CONST) && (g_scn.pair_group != 0);
   const int work = pair_mode ? n_c * ntris : n_c;
-  for (int j = tid; j < work; j += WAVE_THREADS) {
+  for (int j = tid; j < work; j += NT) {
     const int c = pair_mode ? j / ntris : j;
     const int i = pair_mode ? j - c * ntris : 0;
     const int s = q_c[c];
@@ -295,8 +293,8 @@ ART_D void wave_mesh_stage(WaveSmem& S, const short* q_c, int n_c, int tid) {
 // the mesh candidate of a ray out of mesh_res: the window walk of IntersectMeshBF (geometry.adb:276-296) over the pair
 // results in triangle order (u, v of the selected triangle are re-derived when the caller needs them), or the stored
 // per-ray result
-template <int MESHK>
-ART_D void wave_mesh_result(const WaveSmem& S, int c, f3 o, f3 d, bool want_uv, int& id, float& t, float& u, float& v) {
+template <int MESHK, int NT>
+ART_D void wave_mesh_result(const WaveSmem<NT>& S, int c, f3 o, f3 d, bool want_uv, int& id, float& t, float& u, float& v) {
   id = -1; t = 0.0f; u = 0.0f; v = 0.0f;
   if (c < 0) return;
   const bool pair_mode = (MESHK == MESHK_CONST) && (g_scn.pair_group != 0);
@@ -321,25 +319,26 @@ ART_D void wave_mesh_result(const WaveSmem& S, int c, f3 o, f3 d, bool want_uv, 
   }
 }
 
-template <int RT, int MESHK>
-__global__ void __launch_bounds__(WAVE_THREADS, WAVE_MINB) render_wave_kernel(const __grid_constant__ WaveArgs wa) {
+template <int RT, int MESHK, int NT>
+__global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kernel(const __grid_constant__ WaveArgs wa) {
+  constexpr int WAVE_BATCH = 2 * NT;        // work items fetched from the global counter at a time
   extern __shared__ __align__(16) unsigned char wave_smem_raw[];
-  WaveSmem& S = *reinterpret_cast<WaveSmem*>(wave_smem_raw);
+  WaveSmem<NT>& S = *reinterpret_cast<WaveSmem<NT>*>(wave_smem_raw);
   const gcore_dev::RenderArgs& a = wa.r;
   const int tid = threadIdx.x;
-  const int gslot0 = blockIdx.x * WAVE_NS;
-  const int total_slots = gridDim.x * WAVE_NS;
+  const int gslot0 = blockIdx.x * NT;
+  const int total_slots = gridDim.x * NT;
   const unsigned int total_items = (unsigned int)wa.units * (unsigned int)a.nslots;
   const int aa = a.anti_aliasing;
   const int max_depth = a.max_depth;
   const f3 bg = mk3(a.bg[0], a.bg[1], a.bg[2]);
   unsigned int nrays = 0, nmesh = 0, nbounce = 0;
 
-  for (int s = tid; s < WAVE_NS; s += WAVE_THREADS) {
+  for (int s = tid; s < NT; s += NT) {
     S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s; S.cand[s] = -1;
   }
   if (tid == 0) {
-    S.cnt_r[0] = WAVE_NS; S.cnt_r[1] = 0; S.cnt_cs = 0; S.cnt_cp = 0; S.retired = 0; S.exhausted = 0;
+    S.cnt_r[0] = NT; S.cnt_r[1] = 0; S.cnt_cs = 0; S.cnt_cp = 0; S.retired = 0; S.exhausted = 0;
     for (int b = 0; b < 5; b++) S.cnt_m[b] = 0;
     unsigned int base = atomicAdd(wa.next_item, (unsigned int)WAVE_BATCH);
     if (base >= total_items) { S.exhausted = 1; S.pool_next = 0; S.pool_end = 0; }
@@ -358,7 +357,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MINB) render_wave_kernel(co
         else { S.pool_next = (int)base; S.pool_end = (int)min(base + (unsigned int)WAVE_BATCH, total_items); }
       }
     }
-    for (int s = tid; s < WAVE_NS; s += WAVE_THREADS) {
+    for (int s = tid; s < NT; s += NT) {
       int st = S.state[s];
       const bool on = (st & ST_HASRAY) != 0;
       bool ended = false, push_cs = false;
@@ -367,7 +366,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MINB) render_wave_kernel(co
         const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
         const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
         int tri_id; float tri_t, tri_u, tri_v;
-        wave_mesh_result<MESHK>(S, S.cand[s], o, d, true, tri_id, tri_t, tri_u, tri_v);
+        wave_mesh_result<MESHK, NT>(S, S.cand[s], o, d, true, tri_id, tri_t, tri_u, tri_v);
         DHit h;
         closest_with_mesh<MESHK>(o, d, inv, tri_id, tri_t, tri_u, tri_v, true, h);
         nrays++;
@@ -435,7 +434,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MINB) render_wave_kernel(co
 
     // ================================================================= M1: mesh stage of the shadow rays
     if (RT != GCORE_PT_STUPID) {
-      wave_mesh_stage<MESHK, true>(S, S.q_cs, S.cnt_cs, tid);
+      wave_mesh_stage<MESHK, true, NT>(S, S.q_cs, S.cnt_cs, tid);
       __syncthreads();
     }
 
@@ -447,7 +446,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MINB) render_wave_kernel(co
       const int n_m = o4 + ((c4 + 31) & ~31);
       const int n_r = S.cnt_r[par];
       const int n_all = n_m + ((n_r + 31) & ~31);
-      for (int i = tid; i < n_all; i += WAVE_THREADS) {
+      for (int i = tid; i < n_all; i += NT) {
         bool ended = false, push_cp = false, starved = false, retire = false, newray = false;
         int s = 0;
         if (i < n_m) {
@@ -473,7 +472,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MINB) render_wave_kernel(co
               epsilon = max2(epsilon, 1.0e-30f);
               const f3 so = hpos + sdir * epsilon;
               int tri_id; float tri_t, tri_u, tri_v;
-              wave_mesh_result<MESHK>(S, S.cand[s], so, sdir, false, tri_id, tri_t, tri_u, tri_v);
+              wave_mesh_result<MESHK, NT>(S, S.cand[s], so, sdir, false, tri_id, tri_t, tri_u, tri_v);
               DHit hs;                                                        // closest hit; only is_hit / t are read (ray_tracer.adb:117-122)
               closest_with_mesh<MESHK>(so, sdir, mk3(1.0f / sdir.x, 1.0f / sdir.y, 1.0f / sdir.z), tri_id, tri_t, 0.0f, 0.0f, false, hs);
               nrays++;
@@ -615,12 +614,12 @@ __global__ void __launch_bounds__(WAVE_THREADS, WAVE_MINB) render_wave_kernel(co
       }
     }
     __syncthreads();
-    if (S.retired >= WAVE_NS) break;          // uniform: `retired` only changes in Y, which the barrier above closes
+    if (S.retired >= NT) break;          // uniform: `retired` only changes in Y, which the barrier above closes
 
     // ================================================================= M2: mesh stage of the new path rays
     if (tid == 0) S.cnt_r[par] = 0;
     if (tid < 5) S.cnt_m[tid] = 0;
-    wave_mesh_stage<MESHK, false>(S, S.q_cp, S.cnt_cp, tid);
+    wave_mesh_stage<MESHK, false, NT>(S, S.q_cp, S.cnt_cp, tid);
     par ^= 1;
     __syncthreads();
   }

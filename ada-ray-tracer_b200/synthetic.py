@@ -87,3 +87,32 @@ def c5_spheres(count=64, seed=SEED_C5, box_min=(-2.5, 0.0, 0.0), box_max=(2.5, 5
         c = lo + r + w[i, :3] * (hi - lo - 2 * r)
         out.append((c.astype(np.float32), np.float32(r), mats[i % 4]))
     return out
+
+
+def c5_analytic(count=64, seed=SEED_C5):
+    """(spheres, cornell) as structured arrays with the layouts of include/gcore.h: the 64 Philox spheres followed by the
+    sphere light of scene.adb:116-144 (centre (0, 4.5, 1), r 0.5, material 4), and the Cornell box of scene.ads:75-80"""
+    sphere_dt = np.dtype([("pos", "<f4", 3), ("r", "<f4"), ("mat", "<i4")])
+    cornell_dt = np.dtype([("bmin", "<f4", 3), ("bmax", "<f4", 3), ("mat_indices", "<i4", 6), ("normals", "<f4", 18)])
+    sp = np.zeros(count + 1, sphere_dt)
+    for i, (c, r, m) in enumerate(c5_spheres(count, seed)):
+        sp[i] = (c, r, m)
+    sp[count] = ((0.0, 4.5, 1.0), 0.5, 4)
+    box = np.zeros(1, cornell_dt)
+    box["bmin"] = (-2.5, 0.0, 0.0); box["bmax"] = (2.5, 5.0, 5.0)
+    box["mat_indices"] = (2, 3, 1, 1, 8, 1)
+    box["normals"] = (1, 0, 0, -1, 0, 0, 0, 1, 0, 0, -1, 0, 0, 0, 1, 0, 0, -1)
+    return sp, box
+
+
+def install_c5(scene, n=913, oracle_scene=None):
+    """Configure `scene` (package Scene, already Init()-ed: materials, light, camera of scene.adb) as BASELINE config C5;
+    optionally mirror it into an oracle scene (tests).  Returns (pos, nrm, tris)."""
+    pos, nrm, tris = cube_sphere(n)
+    sp, box = c5_analytic()
+    scene.set_analytic(sp, box)
+    scene.set_mesh(pos, nrm, tris, mesh_mode=1)          # MESH_NEAREST -> LBVH
+    if oracle_scene is not None:
+        oracle_scene.set_spheres(sp)
+        oracle_scene.set_mesh(pos, nrm, tris)
+    return pos, nrm, tris

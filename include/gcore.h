@@ -204,6 +204,11 @@ enum { GCORE_OK = 0, GCORE_E_CUDA = -1, GCORE_E_ARG = -2, GCORE_E_STATE = -3, GC
 GCORE_API int gcore_last_error(char* buf, int n);
 /* LBVH facts of the committed/active mesh: triangles, nodes, bytes, build milliseconds */
 GCORE_API int gcore_bvh_info(int64_t* ntris, int64_t* nnodes, int64_t* bytes, float* build_ms);
+/* traversal micro-benchmark (K4 roofline): n HOST rays against the legacy scene (which = 0) or the shaded mesh
+ * (which = 1); one counting launch fills stats3 = {nodes visited (64 B each), triangle slots tested (48 B each), hits},
+ * then `repeat` plain launches are timed with CUDA events -> ms_per_launch */
+GCORE_API int gcore_bvh_bench(int n, const gcore_ray* rays, float t_near, float t_far, int which, int repeat,
+                              float* ms_per_launch, uint64_t* stats3);
 /* registers per thread of the render kernel for a render type (from cudaFuncGetAttributes) */
 GCORE_API int gcore_kernel_regs(int render_type);
 

@@ -1,0 +1,88 @@
+"""BASELINE config C5: Cornell box + sphere light + 64 analytic spheres + a 10 002 828-triangle displaced
+cube-sphere through the GPU LBVH.  Acceptance: triangle ids and t/u/v of random + primary rays equal the oracle's CPU BVH
+exactly; a small render of the full scene equals the oracle's bit for bit."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _syn(pkg):
+    spec = importlib.util.spec_from_file_location("ada_ray_tracer_b200_synthetic", os.path.join(os.path.dirname(pkg.__file__), "synthetic.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a, np.float32)
+    b = a.view(np.uint32).copy(); b[np.isnan(a)] = 0x7FC00000
+    return b
+
+
+@pytest.fixture(scope="module")
+def c5(pkg, ob):
+    syn = _syn(pkg)
+    pkg.set_partition(0, 1)
+    gs = pkg.Scene(); gs.Init()
+    osc = ob.OracleScene()
+    pos, nrm, tris = syn.install_c5(gs, 913, osc)
+    assert len(tris) == 10_002_828
+    yield gs, osc, np.ascontiguousarray(pos), np.ascontiguousarray(tris)
+    gs.Init()                                                         # back to the pyramid2 scene for the other tests
+
+
+def test_c5_scene_queries_match_oracle(c5, pkg, ob):
+    """Find_Closest_Hit over the whole C5 scene: 3840x2160 primary rays (every 7th pixel) + 300 k bounce-like rays"""
+    gs, osc, pos, tris = c5
+    w, h = 3840, 2160
+    ys, xs = np.meshgrid(np.arange(0, h, 7), np.arange(0, w, 7), indexing="ij")
+    rays = np.zeros(xs.size, ob.ray_dt)
+    for i, (x, y) in enumerate(zip(xs.ravel()[::97], ys.ravel()[::97])):      # spot-check the ray generator itself
+        r = osc.eye_ray(w, h, int(x), int(y))
+        rays[i * 97] = r
+    # all primary rays through the product's own primary cast would need the full frame; use the batch query on oracle rays
+    idx = np.arange(0, xs.size, 97)
+    rng = np.random.default_rng(8)
+    n = 300_000
+    rr = np.zeros(n, ob.ray_dt)
+    rr["origin"] = rng.uniform([-2.4, 0.1, 0.1], [2.4, 4.9, 12.0], (n, 3)).astype(np.float32)
+    target = np.array([0.0, 1.6, 2.5]) + rng.normal(size=(n, 3)) * 1.2
+    d = target - rr["origin"]; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rr["direction"] = d.astype(np.float32)
+    allr = np.concatenate([rays[idx], rr])
+    g = gs.Find_Closest_Hit(allr.view(pkg.ray_dt))
+    o = osc.closest_hit_batch(allr, mesh_mode=ob.MESH_NEAREST)
+    for f in g.dtype.names:
+        a, b = g[f], o[f]
+        if a.dtype.kind == "f":
+            a, b = _bits(a), _bits(b)
+        assert np.array_equal(a, b), f
+    tri = (g["prim_type"] == 2) & (g["is_hit"] == 1)
+    assert tri.sum() > 50_000 and len(np.unique(g["prim_index"][tri])) > 20_000
+
+
+def test_c5_primary_hits_and_small_render_bit_exact(c5, pkg, ob):
+    gs, osc, pos, tris = c5
+    w, h = 192, 108
+    g = gs.primary_hits(w, h); o = osc.primary_hits(w, h, mesh_mode=ob.MESH_NEAREST)
+    for f in g.dtype.names:
+        a, b = g[f], o[f]
+        if a.dtype.kind == "f":
+            a, b = _bits(a), _bits(b)
+        assert np.array_equal(a, b), f
+    rt = pkg.Ray_Tracer(); rt.Threads_Num = 1; rt.seed = 0x5EED0005
+    rt.Init_Render(pkg.PT_MIS); rt.Resize_Viewport(w, h)
+    hdr = rt.Render_Pass(read_hdr=True)
+    acc, rays = osc.render(ob.make_params(w, h, ob.PT_MIS, passes=1, seed=0x5EED0005, mesh_mode=ob.MESH_NEAREST))
+    assert np.array_equal(_bits(hdr[..., :3]), _bits(acc))
+    assert int(rt.last_stats.rays) == rays
+
+
+def test_c5_bvh_facts(c5, pkg):
+    gc = pkg.GeometryCore()
+    info = gc.bvh_info()
+    assert info["ntris"] == 10_002_828 and info["nnodes"] == 10_002_827
+    assert info["bytes"] == 10_002_828 * (48 + 36) + 10_002_827 * 64
