@@ -270,7 +270,7 @@ static cudaError_t launch_wave_m(int render_type, const art::WaveArgs& wa, int s
 #define WAVE_NT_BVH 128
 #endif
 
-int wave_total_slots(int sm_count) { return sm_count * WAVE_TOTAL_THREADS; }   // the same for every block shape
+int wave_total_slots(int sm_count) { return sm_count * WAVE_TOTAL_THREADS; }   // upper bound for every block shape
 int wave_max_depth() { return WAVE_MAX_DEPTH; }
 
 cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, cudaStream_t s) {

@@ -40,11 +40,19 @@ namespace art {
 //   LBVH meshes:            128 x 8 -- the traversal stages are long and latency-bound, so several smaller
 //                           blocks per SM overlap one block's traversal with the others' stages (C5: 1024x1 4199 ms, 512x2 3746, 256x4 3309, 128x8 2908)
 #define WAVE_TOTAL_THREADS 1024
+// path slots of a block of NT threads.  Stage Y handles surface slots + regenerated slots (<= NS) plus at most 31 lanes
+// of padding between the two groups; with one block per SM nothing hides a second, nearly empty pass over the block, so
+// the 1024-thread shape keeps NS + 31 <= NT.  Smaller blocks overlap each other instead and use every thread.
+#ifndef WAVE_RESERVE
+#define WAVE_RESERVE 0
+#endif
+#define WAVE_SLOTS(NT) ((NT) >= 1024 ? (NT) - WAVE_RESERVE : (NT))
 #define WAVE_MAX_DEPTH 16
 
 #define WAVE_PAIR_TRIS 8                  // constant-memory meshes up to this size are tested as (ray, triangle) pairs
 
-enum { ST_DEPTH_MASK = 31, ST_SUB_SHIFT = 5, ST_SPEC = 1 << 7, ST_HASRAY = 1 << 8, ST_FOLD = 1 << 9, ST_SURF = 1 << 10 };
+enum { ST_DEPTH_MASK = 31, ST_SUB_SHIFT = 5, ST_SPEC = 1 << 7, ST_HASRAY = 1 << 8, ST_FOLD = 1 << 9, ST_SURF = 1 << 10,
+       ST_BUCKET_SHIFT = 11 /* 3 bits: material bucket of a surface slot */ };
 
 template <int NT>
 struct WaveSmem {
@@ -64,7 +72,8 @@ struct WaveSmem {
   float mesh_res[WAVE_PAIR_TRIS * NT];
   short cand[NT];                    // candidate index of the slot's pending ray in the mesh stage, -1: none
   short hmat[NT];
-  short q_r[2][NT], q_cs[NT], q_cp[NT], q_m[5][NT];
+  short mrank[NT];                   // position of a surface slot inside its material bucket (counting sort X -> M1 -> Y)
+  short q_r[2][NT], q_cs[NT], q_cp[NT], q_s[NT];
   int   cnt_r[2], cnt_cs, cnt_cp, cnt_m[5];
   int   pool_next, pool_end, exhausted, retired;
 };
@@ -321,7 +330,8 @@ ART_D void wave_mesh_result(const WaveSmem<NT>& S, int c, f3 o, f3 d, bool want_
 
 template <int RT, int MESHK, int NT>
 __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kernel(const __grid_constant__ WaveArgs wa) {
-  constexpr int WAVE_BATCH = 2 * NT;        // work items fetched from the global counter at a time
+  constexpr int NS = WAVE_SLOTS(NT);        // path slots of this block
+  constexpr int WAVE_BATCH = 2 * NS;        // work items fetched from the global counter at a time
   extern __shared__ __align__(16) unsigned char wave_smem_raw[];
   WaveSmem<NT>& S = *reinterpret_cast<WaveSmem<NT>*>(wave_smem_raw);
   const gcore_dev::RenderArgs& a = wa.r;
@@ -334,11 +344,11 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
   const f3 bg = mk3(a.bg[0], a.bg[1], a.bg[2]);
   unsigned int nrays = 0, nmesh = 0, nbounce = 0;
 
-  for (int s = tid; s < NT; s += NT) {
+  for (int s = tid; s < NS; s += NT) {
     S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s; S.cand[s] = -1;
   }
   if (tid == 0) {
-    S.cnt_r[0] = NT; S.cnt_r[1] = 0; S.cnt_cs = 0; S.cnt_cp = 0; S.retired = 0; S.exhausted = 0;
+    S.cnt_r[0] = NS; S.cnt_r[1] = 0; S.cnt_cs = 0; S.cnt_cp = 0; S.retired = 0; S.exhausted = 0;
     for (int b = 0; b < 5; b++) S.cnt_m[b] = 0;
     unsigned int base = atomicAdd(wa.next_item, (unsigned int)WAVE_BATCH);
     if (base >= total_items) { S.exhausted = 1; S.pool_next = 0; S.pool_end = 0; }
@@ -357,7 +367,7 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
         else { S.pool_next = (int)base; S.pool_end = (int)min(base + (unsigned int)WAVE_BATCH, total_items); }
       }
     }
-    for (int s = tid; s < NT; s += NT) {
+    for (int s = tid; s < NS; s += NT) {
       int st = S.state[s];
       const bool on = (st & ST_HASRAY) != 0;
       bool ended = false, push_cs = false;
@@ -370,7 +380,7 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
         DHit h;
         closest_with_mesh<MESHK>(o, d, inv, tri_id, tri_t, tri_u, tri_v, true, h);
         nrays++;
-        st &= ~ST_SURF;
+        st &= ~(ST_SURF | (7 << ST_BUCKET_SHIFT));
         f3 Lterm = mk3(0.f, 0.f, 0.f);
         if (!h.is_hit) {                                                      // integrators.adb:98,151,218
           ended = true;
@@ -419,31 +429,42 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
         const int c = queue_push(push_cs, S.q_cs, &S.cnt_cs, s);
         if (on) S.cand[s] = (short)c;                                         // -1 when the shadow ray skips the mesh
       }
-      {                                                                       // append to the queue of the material type
+      {                                                                       // counting sort by material type: rank inside the bucket
         const unsigned m = __match_any_sync(0xffffffffu, bucket);
         if (bucket >= 0) {
           const int lane = tid & 31, leader = __ffs(m) - 1;
           int base = 0;
           if (lane == leader) base = atomicAdd(&S.cnt_m[bucket], __popc(m));
           base = __shfl_sync(m, base, leader);
-          S.q_m[bucket][base + __popc(m & ((1u << lane) - 1u))] = (short)s;
+          S.mrank[s] = (short)(base + __popc(m & ((1u << lane) - 1u)));
+          S.state[s] = st | (bucket << ST_BUCKET_SHIFT);
         }
       }
     }
     __syncthreads();
 
-    // ================================================================= M1: mesh stage of the shadow rays
-    if (RT != GCORE_PT_STUPID) {
-      wave_mesh_stage<MESHK, true, NT>(S, S.q_cs, S.cnt_cs, tid);
-      __syncthreads();
+    // ================================================================= M1: scatter of the material sort + mesh stage of the shadow rays
+    {
+      const int c0 = S.cnt_m[0], c1 = S.cnt_m[1], c2 = S.cnt_m[2], c3 = S.cnt_m[3];
+      for (int s = tid; s < NS; s += NT) {
+        const int st = S.state[s];
+        if ((st & (ST_SURF | ST_HASRAY)) == (ST_SURF | ST_HASRAY)) {
+          const int b = (st >> ST_BUCKET_SHIFT) & 7;
+          const int off_b = (b == 0) ? 0 : (b == 1) ? c0 : (b == 2) ? c0 + c1 : (b == 3) ? c0 + c1 + c2 : c0 + c1 + c2 + c3;
+          S.q_s[off_b + S.mrank[s]] = (short)s;
+        }
+      }
+      if (RT != GCORE_PT_STUPID) wave_mesh_stage<MESHK, true, NT>(S, S.q_cs, S.cnt_cs, tid);
     }
+    __syncthreads();
 
     // ================================================================= Y: shade (slots sorted by material) + regenerate (queue R)
     {
       if (tid == 0) S.cnt_cs = 0;
-      const int c0 = S.cnt_m[0], c1 = S.cnt_m[1], c2 = S.cnt_m[2], c3 = S.cnt_m[3], c4 = S.cnt_m[4];
-      const int o1 = (c0 + 31) & ~31, o2 = o1 + ((c1 + 31) & ~31), o3 = o2 + ((c2 + 31) & ~31), o4 = o3 + ((c3 + 31) & ~31);
-      const int n_m = o4 + ((c4 + 31) & ~31);
+      // surface slots sorted by material type (buckets back to back: only the warps on a bucket boundary see two types),
+      // one padding gap, then queue R
+      const int n_surf = S.cnt_m[0] + S.cnt_m[1] + S.cnt_m[2] + S.cnt_m[3] + S.cnt_m[4];
+      const int n_m = (n_surf + 31) & ~31;
       const int n_r = S.cnt_r[par];
       const int n_all = n_m + ((n_r + 31) & ~31);
       for (int i = tid; i < n_all; i += NT) {
@@ -451,13 +472,9 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
         int s = 0;
         if (i < n_m) {
           // ------------------------------------------------------------- shade
-          // warp-uniform: segments are multiples of 32
-          const int b = (i >= o1) + (i >= o2) + (i >= o3) + (i >= o4);
-          const int off_b = (b == 0) ? 0 : (b == 1) ? o1 : (b == 2) ? o2 : (b == 3) ? o3 : o4;
-          const int cnt_b = (b == 0) ? c0 : (b == 1) ? c1 : (b == 2) ? c2 : (b == 3) ? c3 : c4;
-          const bool on = (i - off_b) < cnt_b;
+          const bool on = i < n_surf;
           if (on) {
-            s = S.q_m[b][i - off_b];
+            s = S.q_s[i];
             int st = S.state[s];
             const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
             const float ht = S.ht[s];
@@ -614,7 +631,7 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
       }
     }
     __syncthreads();
-    if (S.retired >= NT) break;          // uniform: `retired` only changes in Y, which the barrier above closes
+    if (S.retired >= NS) break;          // uniform: `retired` only changes in Y, which the barrier above closes
 
     // ================================================================= M2: mesh stage of the new path rays
     if (tid == 0) S.cnt_r[par] = 0;
