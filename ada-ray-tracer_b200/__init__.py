@@ -63,7 +63,7 @@ EXPORTS = [
     "gcore_bvh_closest_hit_batch", "gcore_set_device", "gcore_set_partition", "gcore_init_render",
     "gcore_resize_viewport", "gcore_render_units", "gcore_get_counters", "gcore_get_spp", "gcore_read_frame", "gcore_render",
     "gcore_primary_hits", "gcore_accum_device_ptr", "gcore_resolve_device", "gcore_resolve_gathered_device",
-    "gcore_stream", "gcore_synchronize", "gcore_last_error", "gcore_bvh_info", "gcore_kernel_regs", "gcore_bvh_bench",
+    "gcore_stream", "gcore_synchronize", "gcore_last_error", "gcore_bvh_info", "gcore_kernel_regs", "gcore_bvh_bench", "gcore_load_frame",
 ]
 
 _lib = None
@@ -104,6 +104,7 @@ def lib():
     L.gcore_render_units.argtypes = [i32, C.POINTER(RenderStats)]
     L.gcore_get_counters.argtypes = [vp]
     L.gcore_read_frame.argtypes = [vp, vp]
+    L.gcore_load_frame.argtypes = [vp, i32]
     L.gcore_render.argtypes = [C.POINTER(RenderConfig), i32, i32, i32, vp, vp, C.POINTER(RenderStats)]
     L.gcore_primary_hits.argtypes = [i32, i32, vp]
     L.gcore_accum_device_ptr.argtypes = [C.POINTER(vp), C.POINTER(C.c_int64)]
@@ -311,6 +312,18 @@ class Ray_Tracer:
 
     def GetSPP(self):
         return self.L.gcore_get_spp()
+
+    def save_checkpoint(self, path):
+        """progressive-render checkpoint: HDR accumulator + spp (np.savez)"""
+        hdr = np.zeros((self.height, self.width, 4), np.float32)
+        _ck(self.L.gcore_read_frame(_p(hdr), None))
+        np.savez(path, hdr=hdr, spp=self.GetSPP(), width=self.width, height=self.height)
+
+    def load_checkpoint(self, path):
+        z = np.load(path)
+        self.Resize_Viewport(int(z["width"]), int(z["height"]))
+        hdr = np.ascontiguousarray(z["hdr"], np.float32)
+        _ck(self.L.gcore_load_frame(_p(hdr), int(z["spp"])))
 
     def Finished(self):
         return self.g_finish

@@ -831,6 +831,21 @@ int gcore_render(const gcore_render_config* cfg, int width, int height, int unit
   return 0;
 }
 
+int gcore_load_frame(const float* hdr4, int spp) {
+  State& s = S();
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  if (!hdr4 || spp < 0) return fail(GCORE_E_ARG, "gcore_load_frame: bad arguments");
+  if (!s.d_accum) return fail(GCORE_E_STATE, "gcore_load_frame: no viewport");
+  if (int rc = ensure_out_buffers(true, false)) return rc;
+  size_t px = (size_t)s.width * s.height;
+  CU(cudaMemcpyAsync(s.d_hdr, hdr4, sizeof(float4) * px, cudaMemcpyHostToDevice, s.stream), "memcpy hdr");
+  RenderArgs a = make_args();
+  CU(gcore_dev::launch_load_accum(a, s.d_hdr, s.stream), "load_accum_kernel");
+  CU(cudaStreamSynchronize(s.stream), "load_frame sync");
+  s.spp = spp;
+  return 0;
+}
+
 int gcore_primary_hits(int width, int height, gcore_hit* hits) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);

@@ -11,6 +11,16 @@ namespace art { struct DeviceScene; struct BvhView; }
 namespace gcore_dev {
 
 #define GC_TILE 32                       // tile edge in pixels; one tile = 1024 accumulator slots
+// Tile order: the tiles of row ty are numbered ty * tiles_x + (tx + GC_TILE_SKEW * ty) % tiles_x, and tile number t belongs
+// to rank t % world.  The rotation keeps a rank from owning whole tile columns when tiles_x is a multiple of world (a plain
+// t % world then gives every rank the same x positions in every row, e.g. a rank with nothing but background).
+#define GC_TILE_SKEW 3
+__host__ __device__ inline void gc_tile_to_xy(int tile, int tiles_x, int& tx, int& ty) {
+  ty = tile / tiles_x;
+  int r = tile - ty * tiles_x - (GC_TILE_SKEW * ty) % tiles_x;
+  tx = r < 0 ? r + tiles_x : r;
+}
+__host__ __device__ inline int gc_xy_to_tile(int tx, int ty, int tiles_x) { return ty * tiles_x + (tx + GC_TILE_SKEW * ty) % tiles_x; }
 
 struct RenderArgs {
   int      width, height;
@@ -45,6 +55,8 @@ cudaError_t launch_resolve(const RenderArgs& a, int spp, float4* d_hdr4, uint32_
 // gather variant for multi-GPU: `all` holds world slot-major buffers back to back (rank r at r*nslots)
 cudaError_t launch_resolve_gathered(const RenderArgs& a, const float4* d_all, int spp, float4* d_hdr4, uint32_t* d_ldr, cudaStream_t s);
 int render_kernel_regs(int render_type);
+// row-major HDR frame (device) -> this rank's slot-major accumulator (checkpoint / resume)
+cudaError_t launch_load_accum(const RenderArgs& a, const float4* d_hdr4, cudaStream_t s);
 
 // ---- block-synchronous wavefront render (render_wave.cuh): persistent grid of `grid` blocks ----
 struct WaveBuffers {

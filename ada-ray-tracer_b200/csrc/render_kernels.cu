@@ -30,7 +30,7 @@ struct PixelId { int x, y, active; };
 __device__ __forceinline__ PixelId slot_to_pixel(const gcore_dev::RenderArgs& a, int slot, int rank) {
   int tile_local = slot >> 10, q = slot & 1023;
   int tile = tile_local * a.world + rank;
-  int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+  int tx, ty; gcore_dev::gc_tile_to_xy(tile, a.tiles_x, tx, ty);
   int w = q >> 5, l = q & 31;
   PixelId p;
   p.x = tx * GC_TILE + (w & 3) * 8 + (l & 7);
@@ -42,7 +42,7 @@ __device__ __forceinline__ PixelId slot_to_pixel(const gcore_dev::RenderArgs& a,
 // pixel -> (rank, slot) for the resolve
 __device__ __forceinline__ void pixel_to_slot(const gcore_dev::RenderArgs& a, int x, int y, int& rank, int& slot) {
   int tx = x / GC_TILE, ty = y / GC_TILE, lx = x % GC_TILE, ly = y % GC_TILE;
-  int tile = ty * a.tiles_x + tx;
+  int tile = gcore_dev::gc_xy_to_tile(tx, ty, a.tiles_x);
   rank = tile % a.world;
   int tile_local = tile / a.world;
   int w = (ly >> 2) * 4 + (lx >> 3), l = (ly & 3) * 8 + (lx & 7);
@@ -182,9 +182,26 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ gc
   }
 }
 
+// checkpoint / resume: row-major HDR frame (gcore_read_frame) -> this rank's slot-major accumulator
+__global__ void __launch_bounds__(256) load_accum_kernel(const __grid_constant__ gcore_dev::RenderArgs a, const float4* __restrict__ hdr4) {
+  const int slot = blockIdx.x * 256 + threadIdx.x;
+  if (slot >= a.nslots) return;
+  const PixelId px = slot_to_pixel(a, slot, a.rank);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (px.active) { v = hdr4[(size_t)px.y * a.width + px.x]; v.w = 0.f; }
+  a.accum[slot] = v;
+}
+
 }  // namespace
 
 namespace gcore_dev {
+
+cudaError_t launch_load_accum(const RenderArgs& a, const float4* d_hdr4, cudaStream_t s) {
+  if (a.nslots <= 0) return cudaSuccess;
+  load_accum_kernel<<<(a.nslots + 255) / 256, 256, 0, s>>>(a, d_hdr4);
+  return cudaGetLastError();
+}
+
 
 cudaError_t upload_scene(const art::DeviceScene* host_copy, cudaStream_t s) {
   return cudaMemcpyToSymbolAsync(g_scn, host_copy, sizeof(art::DeviceScene), 0, cudaMemcpyHostToDevice, s);

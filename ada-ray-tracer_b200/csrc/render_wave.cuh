@@ -228,7 +228,7 @@ struct WavePixel { int x, y, active; };
 ART_D WavePixel wave_slot_to_pixel(const gcore_dev::RenderArgs& a, int q) {
   int tile_local = q >> 10, r = q & 1023;
   int tile = tile_local * a.world + a.rank;
-  int tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+  int tx, ty; gcore_dev::gc_tile_to_xy(tile, a.tiles_x, tx, ty);
   int w = r >> 5, l = r & 31;
   WavePixel p;
   p.x = tx * GC_TILE + (w & 3) * 8 + (l & 7);

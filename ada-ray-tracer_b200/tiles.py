@@ -5,8 +5,10 @@ the image is cut into 32x32-pixel tiles, tile t belongs to rank t % world, every
 only its tiles into a *slot-major* accumulator (one float4 per slot):
 
     slot q of rank r:  tile_local = q // 1024,  tile = tile_local * world + r,  w = (q % 1024) // 32,  l = q % 32
-                       x = (tile %  tiles_x) * 32 + (w % 4) * 8 + (l % 8)
-                       y = (tile // tiles_x) * 32 + (w // 4) * 4 + (l // 8)
+                       ty = tile // tiles_x,  tx = (tile % tiles_x - 3 * ty) mod tiles_x      (rows are rotated by 3 tiles each, so that
+                                                                                                a rank does not own whole tile columns)
+                       x = tx * 32 + (w % 4) * 8 + (l % 8)
+                       y = ty * 32 + (w // 4) * 4 + (l // 8)
 
 (32 consecutive slots = one 8x4 pixel block, so a warp's accumulator traffic is one 512-byte line).  Every rank owns
 ceil(ntiles / world) tiles' worth of slots -- the padding slots of the last ranks are inactive -- so the buffers gathered
@@ -22,6 +24,7 @@ import numpy as np
 
 TILE = 32
 TILE_SLOTS = TILE * TILE
+TILE_SKEW = 3                      # GC_TILE_SKEW of csrc/gcore_internal.h
 
 
 def tile_grid(width, height):
@@ -44,8 +47,10 @@ def slot_to_pixel(q, rank, world, width, height):
     tile = (q // TILE_SLOTS) * world + rank
     r = q % TILE_SLOTS
     w, l = r // 32, r % 32
-    x = (tile % tiles_x) * TILE + (w % 4) * 8 + (l % 8)
-    y = (tile // tiles_x) * TILE + (w // 4) * 4 + (l // 8)
+    ty = tile // tiles_x
+    tx = (tile % tiles_x - TILE_SKEW * ty) % tiles_x
+    x = tx * TILE + (w % 4) * 8 + (l % 8)
+    y = ty * TILE + (w // 4) * 4 + (l // 8)
     active = (tile < tiles_x * tiles_y) & (x < width) & (y < height)
     return x, y, active
 
@@ -54,7 +59,7 @@ def pixel_to_slot(x, y, world, width, height):
     """-> (rank, slot) for pixel coordinates (arrays)"""
     x = np.asarray(x, np.int64); y = np.asarray(y, np.int64)
     tiles_x, _ = tile_grid(width, height)
-    tile = (y // TILE) * tiles_x + (x // TILE)
+    tile = (y // TILE) * tiles_x + (x // TILE + TILE_SKEW * (y // TILE)) % tiles_x
     lx, ly = x % TILE, y % TILE
     w = (ly // 4) * 4 + (lx // 8)
     l = (ly % 4) * 8 + (lx % 8)

@@ -35,7 +35,7 @@ WORKLOADS = {
     # name: (width, height, render_type, aa, max_depth, units per step, description)
     "C4_1024": (1024, 1024, "PT_MIS", 1, 8, 64, "pyramid2 Cornell scene, PT_MIS depth 8, AA 4 fixed sub-pixels, 1024x1024, 256 spp per step"),
     "C1": (1024, 768, "PT_MIS", 1, 8, 28, "reference default: 1024x768 PT_MIS depth 8, 28 units (112 spp) per Render_Pass"),
-    "C2": (1024, 1024, "PT_STUPID", 0, 1, 1, "primary rays only, 1024x1024, 1 spp (pixel centres)"),
+    "C2": (1024, 1024, "RT_DEBUG", 0, 1, 1, "primary-ray cast only (Debug_Ray_Tracing), 1024x1024, 1 spp (pixel centres)"),
     "C3": (1024, 1024, "PT_SHADOW", 1, 1, 4, "direct lighting with shadow rays, 1024x1024, 16 spp"),
     "C4": (2048, 2048, "PT_MIS", 1, 8, 64, "multi-bounce PT_MIS depth 8, 2048x2048, 256 spp per step"),
     "C5": (3840, 2160, "PT_MIS", 1, 8, 16, "synthetic 10 002 828-triangle cube-sphere (GPU LBVH) + 64 analytic spheres in the Cornell box, PT_MIS depth 8, 3840x2160, 64 spp per step"),

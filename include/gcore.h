@@ -178,6 +178,10 @@ GCORE_API int gcore_get_spp(void);
 /* resolve the accumulator (ray_tracer.adb:281-291) and copy to HOST buffers, row-major [y*W+x];
  * hdr4 = float4 (r,g,b,spp) per pixel, ldr = R | G<<8 | B<<16.  Either may be NULL.  Only valid with world == 1. */
 GCORE_API int gcore_read_frame(float* hdr4, uint32_t* ldr);
+/* checkpoint / resume (the reference only keeps the accumulator in memory and rewrites the BMP every pass, test.adb:63-69):
+ * load a frame saved with gcore_read_frame (row-major float4, HOST) into the accumulator of the current viewport and
+ * continue at sample index `spp`; every rank loads its own tiles of the same full frame */
+GCORE_API int gcore_load_frame(const float* hdr4, int spp);
 /* one-shot: resize + render `units` + read back to host buffers (the end-to-end call) */
 GCORE_API int gcore_render(const gcore_render_config* cfg, int width, int height, int units,
                            float* hdr4, uint32_t* ldr, gcore_render_stats* stats);

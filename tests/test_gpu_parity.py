@@ -232,3 +232,22 @@ def test_partition_independence(gscene, pkg):
         assert np.array_equal(_bits(got[..., :3]), _bits(ref[..., :3])), "world=%d" % world
         assert np.array_equal(ldr.cpu().numpy().view(np.uint32).reshape(h, w), ref_ldr)
     pkg.set_partition(0, 1)
+
+
+def test_checkpoint_resume(gscene, pkg, tmp_path):
+    """2 passes + save + fresh viewport + load + 2 passes == 4 passes straight (sample indices continue at spp)"""
+    w, h = 100, 60
+    rt = pkg.Ray_Tracer(); rt.Threads_Num = 2; rt.seed = 4242
+    rt.Init_Render(pkg.PT_MIS); rt.Resize_Viewport(w, h)
+    rt.Render_Pass(); ref = rt.Render_Pass(read_hdr=True).copy()
+    assert rt.GetSPP() == 16
+    rt.Resize_Viewport(w, h)
+    rt.Render_Pass()
+    ck = str(tmp_path / "ck.npz")
+    rt.save_checkpoint(ck)
+    rt2 = pkg.Ray_Tracer(); rt2.Threads_Num = 2; rt2.seed = 4242
+    rt2.Init_Render(pkg.PT_MIS)
+    rt2.load_checkpoint(ck)
+    assert rt2.GetSPP() == 8
+    got = rt2.Render_Pass(read_hdr=True)
+    assert rt2.GetSPP() == 16 and np.array_equal(_bits(got), _bits(ref))
