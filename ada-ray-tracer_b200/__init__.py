@@ -63,7 +63,7 @@ EXPORTS = [
     "gcore_bvh_closest_hit_batch", "gcore_set_device", "gcore_set_partition", "gcore_init_render",
     "gcore_resize_viewport", "gcore_render_units", "gcore_get_counters", "gcore_get_spp", "gcore_read_frame", "gcore_render",
     "gcore_primary_hits", "gcore_accum_device_ptr", "gcore_resolve_device", "gcore_resolve_gathered_device",
-    "gcore_stream", "gcore_synchronize", "gcore_last_error", "gcore_bvh_info", "gcore_kernel_regs", "gcore_bvh_bench", "gcore_load_frame",
+    "gcore_stream", "gcore_synchronize", "gcore_last_error", "gcore_bvh_info", "gcore_kernel_regs", "gcore_bvh_bench", "gcore_load_frame", "gcore_set_stats_level",
 ]
 
 _lib = None
@@ -105,6 +105,7 @@ def lib():
     L.gcore_get_counters.argtypes = [vp]
     L.gcore_read_frame.argtypes = [vp, vp]
     L.gcore_load_frame.argtypes = [vp, i32]
+    L.gcore_set_stats_level.argtypes = [i32]
     L.gcore_render.argtypes = [C.POINTER(RenderConfig), i32, i32, i32, vp, vp, C.POINTER(RenderStats)]
     L.gcore_primary_hits.argtypes = [i32, i32, vp]
     L.gcore_accum_device_ptr.argtypes = [C.POINTER(vp), C.POINTER(C.c_int64)]
@@ -391,6 +392,11 @@ def bvh_bench(rays, which=1, repeat=5, t_near=0.0, t_far=1000000.0):
     nodes, tris = st[0] / n, st[1] / n
     return {"ms": ms.value, "mrays_s": n / (ms.value * 1e-3) / 1e6, "nodes_per_ray": float(nodes), "tris_per_ray": float(tris),
             "bytes_per_ray": float(64.0 * nodes + 48.0 * tris + 24 + 40), "hit_rate": float(st[2] / n)}
+
+
+def set_stats_level(level):
+    """1: fast counters; 2: mesh_queries = rays entering the reference's mesh bbox (for the roofline's flop count)"""
+    _ck(lib().gcore_set_stats_level(int(level)))
 
 
 def set_device(device):

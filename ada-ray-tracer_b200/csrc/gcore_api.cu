@@ -53,6 +53,7 @@ struct State {
   unsigned long long last_counters[4] = {0, 0, 0, 0};
   float4* d_hdr = nullptr; uint32_t* d_ldr = nullptr; size_t out_pixels = 0;
   WaveBuffers wave;                          // work buffers of the wavefront render kernel
+  int stats_level = 1;
   int sm_count = 0;
 
   int  err_code = 0;
@@ -325,7 +326,7 @@ int render_units_locked(int units, gcore_render_stats* stats) {
     for (int done = 0; done < units; done += (int)chunk) {
       const int n = (units - done < (int)chunk) ? (units - done) : (int)chunk;
       a.passes = n; a.first_sample = s.spp;
-      CU(gcore_dev::launch_render_wave(s.cfg.render_type, s.hs.mesh_kind, a, s.wave, n, s.stream), "render_wave_kernel");
+      CU(gcore_dev::launch_render_wave(s.cfg.render_type, s.hs.mesh_kind, a, s.wave, n, s.stats_level >= 2 ? 1 : 0, s.stream), "render_wave_kernel");
       launches += 2;
       s.spp += n * per;                                                  // ray_tracer.adb:168-176
     }
@@ -792,6 +793,14 @@ int gcore_get_counters(uint64_t* out3) {
   CU(cudaMemcpyAsync(c, s.d_rays, sizeof(c), cudaMemcpyDeviceToHost, s.stream), "memcpy counters");
   CU(cudaStreamSynchronize(s.stream), "counters sync");
   out3[0] = c[0]; out3[1] = c[1]; out3[2] = c[2]; out3[3] = c[3];
+  return 0;
+}
+
+int gcore_set_stats_level(int level) {
+  State& s = S();
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  if (level < 1 || level > 2) return fail(GCORE_E_ARG, "gcore_set_stats_level: 1 or 2");
+  s.stats_level = level;
   return 0;
 }
 

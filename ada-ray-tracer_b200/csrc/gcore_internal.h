@@ -70,7 +70,8 @@ struct WaveBuffers {
 int wave_total_slots(int sm_count);      // path slots resident on the device (grid * slots per block)
 int wave_max_depth();
 // `units` DoPass units over this rank's slots (units * nslots < 2^31): wavefront kernel + fold into a.accum
-cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, cudaStream_t s);
+// count_mesh: statistics level 2 (counters[1] = rays entering the reference's mesh bbox; otherwise = rays that ran the mesh stage)
+cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, int count_mesh, cudaStream_t s);
 
 // ---- lbvh_build.cu ----
 struct LbvhBuffers {                     // device allocations owned by the builder

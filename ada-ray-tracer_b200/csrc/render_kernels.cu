@@ -290,10 +290,10 @@ static cudaError_t launch_wave_m(int render_type, const art::WaveArgs& wa, int s
 int wave_total_slots(int sm_count) { return sm_count * WAVE_TOTAL_THREADS; }   // upper bound for every block shape
 int wave_max_depth() { return WAVE_MAX_DEPTH; }
 
-cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, cudaStream_t s) {
+cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, int count_mesh, cudaStream_t s) {
   if (a.nslots <= 0 || units <= 0) return cudaSuccess;
   art::WaveArgs wa;
-  wa.r = a; wa.colbuf = wb.colbuf; wa.stackA = wb.stackA; wa.stackB = wb.stackB; wa.next_item = wb.next_item; wa.units = units;
+  wa.r = a; wa.colbuf = wb.colbuf; wa.stackA = wb.stackA; wa.stackB = wb.stackB; wa.next_item = wb.next_item; wa.units = units; wa.count_mesh = count_mesh;
   cudaError_t e = cudaMemsetAsync(wb.next_item, 0, sizeof(unsigned int), s);
   if (e != cudaSuccess) return e;
   e = (mesh_kind == 2) ? launch_wave_m<MESHK_BVH, WAVE_NT_BVH>(render_type, wa, wb.sm_count, s)

@@ -40,6 +40,10 @@ namespace art {
 //   LBVH meshes:            128 x 8 -- the traversal stages are long and latency-bound, so several smaller
 //                           blocks per SM overlap one block's traversal with the others' stages (C5: 1024x1 4199 ms, 512x2 3746, 256x4 3309, 128x8 2908)
 #define WAVE_TOTAL_THREADS 1024
+#ifndef SPH_UNROLL
+#define SPH_UNROLL 1
+#endif
+constexpr int kSphereUnroll = SPH_UNROLL;     // unroll factor of the sphere loop of IntersectAllSpheres
 // path slots of a block of NT threads.  Stage Y handles surface slots + regenerated slots (<= NS) plus at most 31 lanes
 // of padding between the two groups; with one block per SM nothing hides a second, nearly empty pass over the block, so
 // the 1024-thread shape keeps NS + 31 <= NT.  Smaller blocks overlap each other instead and use every thread.
@@ -63,6 +67,7 @@ struct WaveSmem {
   float sx[NT], sy[NT], sz[NT], ls_pdf[NT], sh_thi[NT];
   float r1[NT], r2[NT];
   float prev_pdf[NT];
+  float ix[NT], iy[NT], iz[NT];       // 1 / direction of the slot's pending ray: the path ray (Y -> X), then the shadow ray (X -> Y)
   // colour of the work item so far / radiance at the end of the path
   float cr[NT], cg[NT], cb[NT], lx[NT], ly[NT], lz[NT];
   int   item[NT];                    // unit * nslots + q, or -1: no item
@@ -99,24 +104,29 @@ struct WaveArgs {
   float2* stackB;                         // [WAVE_MAX_DEPTH][total_slots]  (W.y, W.z)
   unsigned int* next_item;                // global work counter
   int     units;
+  int     count_mesh;                     // statistics level 2: count reference-bbox entries (see mesh_candidate)
 };
 
-// does the ray need the mesh stage?  Counts the reference's bbox entries (the 564-flop queries of SURVEY 8d).
+// does the ray need the mesh stage?  count: also count the rays that enter the reference's mesh bbox (the 564-flop queries
+// of SURVEY 8d) -- a statistic that needs the bbox test for every ray; without it the cheap cull goes first and the
+// reference's test runs for the few rays that survive it (the decision is the same: both tests must pass)
 template <int MESHK>
-ART_D bool mesh_candidate(f3 o, f3 inv, unsigned int& mesh_queries) {
-  if (MESHK == MESHK_CONST) {
-    if (g_scn.ntris_bf <= 0) return false;
-    if (g_scn.mesh_mode == MESH_REFERENCE_BF) {                              // IntersectMeshBF bbox reject, geometry.adb:272-274
-      float t0, t1;
-      if (!intersect_box_inv(o, inv, g_scn.mesh_bmin, g_scn.mesh_bmax, t0, t1)) return false;
-    }
-  } else {
-    if (g_scn.bvh.ntris <= 0) return false;
+ART_D bool mesh_candidate(f3 o, f3 inv, bool count, unsigned int& mesh_queries) {
+  if (MESHK == MESHK_CONST) { if (g_scn.ntris_bf <= 0) return false; }
+  else { if (g_scn.bvh.ntris <= 0) return false; }
+  const bool ref_box = (MESHK == MESHK_CONST) && (g_scn.mesh_mode == MESH_REFERENCE_BF);   // IntersectMeshBF bbox reject, geometry.adb:272-274
+  float t0, t1;
+  if (count) {
+    if (ref_box && !intersect_box_inv(o, inv, g_scn.mesh_bmin, g_scn.mesh_bmax, t0, t1)) return false;
+    mesh_queries++;
+    return cull_box_pass(o, inv, g_scn.mesh_tight_min, g_scn.mesh_tight_max);
   }
-  mesh_queries++;
   // the reference's bbox also spans the origin (never reset, geometry.adb:593-603): rays that miss the padded tight box
   // of the vertices cannot pass any triangle test
-  return cull_box_pass(o, inv, g_scn.mesh_tight_min, g_scn.mesh_tight_max);
+  if (!cull_box_pass(o, inv, g_scn.mesh_tight_min, g_scn.mesh_tight_max)) return false;
+  if (ref_box && !intersect_box_inv(o, inv, g_scn.mesh_bmin, g_scn.mesh_bmax, t0, t1)) return false;
+  mesh_queries++;
+  return true;
 }
 
 template <int MESHK>
@@ -147,7 +157,7 @@ template <int MESHK>
 ART_D void closest_with_mesh(f3 o, f3 d, f3 inv, int tri_id, float tri_t, float tri_u, float tri_v, bool want_record, DHit& h) {
   float min_t = ART_FLT_LAST;                                                 // IntersectAllSpheres, geometry.adb:48-115
   int   min_i = 0;
-#pragma unroll 1
+#pragma unroll kSphereUnroll
   for (int i = 0; i < g_scn.nspheres; i++) {
     f3 k = mk3(o.x - g_scn.sph[i][0], o.y - g_scn.sph[i][1], o.z - g_scn.sph[i][2]);
     float b = dot(k, d);
@@ -343,6 +353,7 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
   const int max_depth = a.max_depth;
   const f3 bg = mk3(a.bg[0], a.bg[1], a.bg[2]);
   unsigned int nrays = 0, nmesh = 0, nbounce = 0;
+  const bool cnt = wa.count_mesh != 0;
 
   for (int s = tid; s < NS; s += NT) {
     S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s; S.cand[s] = -1;
@@ -374,7 +385,7 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
       int bucket = -1 - (tid & 31);                                           // distinct per lane: no peers in the match below
       if (on) {
         const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
-        const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        const f3 inv = mk3(S.ix[s], S.iy[s], S.iz[s]);                        // 1.0/direction (geometry.adb:154-156), computed when the ray was made
         int tri_id; float tri_t, tri_u, tri_v;
         wave_mesh_result<MESHK, NT>(S, S.cand[s], o, d, true, tri_id, tri_t, tri_u, tri_v);
         DHit h;
@@ -413,7 +424,9 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
             float maxDist  = length(hpos - ls.pos);
             float epsilon2 = max2(maxDist * 0.000001f, 1.0e-30f);
             S.sx[s] = sdir.x; S.sy[s] = sdir.y; S.sz[s] = sdir.z; S.ls_pdf[s] = ls.pdf; S.sh_thi[s] = maxDist - epsilon2;
-            push_cs = mesh_candidate<MESHK>(so, mk3(1.0f / sdir.x, 1.0f / sdir.y, 1.0f / sdir.z), nmesh);
+            const f3 sinv = mk3(1.0f / sdir.x, 1.0f / sdir.y, 1.0f / sdir.z);
+            S.ix[s] = sinv.x; S.iy[s] = sinv.y; S.iz[s] = sinv.z;
+            push_cs = mesh_candidate<MESHK>(so, sinv, cnt, nmesh);
           }
           const int type = g_scn.mats[h.mat].type;
           bucket = (type == MAT_LAMBERT) ? 0 : (type == MAT_PHONG) ? 1 : (type == MAT_GLASS) ? 2 : (type == MAT_MIRROR) ? 3 : 4;
@@ -481,7 +494,8 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
             const f3 hn = mk3(S.nx[s], S.ny[s], S.nz[s]);
             const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
             const DMaterial& m = g_scn.mats[S.hmat[s]];
-            const f3 refl = reflect(d, hn);       // shared by Phong eval/sample, mirror, glass (materials.adb:251,313,371,394)
+            // reflect(ray_dir, normal): Phong eval/sample, mirror, glass (materials.adb:251,313,371,394); Lambert never reads it
+            const f3 refl = (m.type == MAT_LAMBERT) ? hn : reflect(d, hn);
             f3 explicitColor = mk3(0.f, 0.f, 0.f);
             if (RT != GCORE_PT_STUPID) {
               const f3 sdir = mk3(S.sx[s], S.sy[s], S.sz[s]);
@@ -491,7 +505,7 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
               int tri_id; float tri_t, tri_u, tri_v;
               wave_mesh_result<MESHK, NT>(S, S.cand[s], so, sdir, false, tri_id, tri_t, tri_u, tri_v);
               DHit hs;                                                        // closest hit; only is_hit / t are read (ray_tracer.adb:117-122)
-              closest_with_mesh<MESHK>(so, sdir, mk3(1.0f / sdir.x, 1.0f / sdir.y, 1.0f / sdir.z), tri_id, tri_t, 0.0f, 0.0f, false, hs);
+              closest_with_mesh<MESHK>(so, sdir, mk3(S.ix[s], S.iy[s], S.iz[s]), tri_id, tri_t, 0.0f, 0.0f, false, hs);
               nrays++;
               const bool shadowed = hs.is_hit && (hs.t < S.sh_thi[s] && hs.t > 10.0f * epsilon);
               if (!shadowed) {
@@ -528,7 +542,9 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
               ended = true;
             } else {
               newray = true;
-              push_cp = mesh_candidate<MESHK>(no, mk3(1.0f / nd.x, 1.0f / nd.y, 1.0f / nd.z), nmesh);
+              const f3 ninv = mk3(1.0f / nd.x, 1.0f / nd.y, 1.0f / nd.z);
+              S.ix[s] = ninv.x; S.iy[s] = ninv.y; S.iz[s] = ninv.z;
+              push_cp = mesh_candidate<MESHK>(no, ninv, cnt, nmesh);
             }
             S.state[s] = st;
           }
@@ -614,7 +630,9 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
               S.prev_pdf[s] = 1.0f;                                           // StartSample, materials.ads:25
               st = (st & (3 << ST_SUB_SHIFT)) | ST_SPEC | ST_HASRAY;          // depth 0
               newray = true;
-              push_cp = mesh_candidate<MESHK>(o, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), nmesh);
+              const f3 cinv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+              S.ix[s] = cinv.x; S.iy[s] = cinv.y; S.iz[s] = cinv.z;
+              push_cp = mesh_candidate<MESHK>(o, cinv, cnt, nmesh);
             } else {
               st &= ~(ST_HASRAY | ST_FOLD);
               retire = (S.exhausted != 0) && !padded;                         // no work left anywhere: the slot retires

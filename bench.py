@@ -186,6 +186,18 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- value: device-resident, CUDA events
+    # one untimed counting pass (statistics level 2): the share of scene queries that enter the reference's mesh bounding box
+    # (564 instead of 140 algorithmic flop); the timed passes run with the cheap counters
+    pkg.set_stats_level(2)
+    cc0 = pkg.get_counters()
+    tr.Render_Pass()
+    barrier()
+    cc1 = pkg.get_counters()
+    mesh_share = torch.tensor([cc1[1] - cc0[1], cc1[0] - cc0[0]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(mesh_share, op=dist.ReduceOp.SUM)
+    mesh_share = float(mesh_share[0] / torch.clamp(mesh_share[1], min=1.0))
+    pkg.set_stats_level(1)
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             flush.fill_(1); tr.Render_Pass()
@@ -214,7 +226,8 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     step_ms, kern_ms = float(t[0]), float(t[1])
-    rays, mesh_q, bounces, launches_all = (float(x) for x in cnt)
+    rays, _mesh_stage_rays, bounces, launches_all = (float(x) for x in cnt)
+    mesh_q = mesh_share * rays                           # reference-bbox entries among the timed rays (share from the counting pass)
     value = rays / (step_ms * 1e-3) / 1e6
 
     # ---------------------------------------------------------------- e2e: the public call with HOST buffers, every step:

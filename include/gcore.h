@@ -148,11 +148,9 @@ typedef struct gcore_render_config {          /* the package-level variables of 
 typedef struct gcore_render_stats {
   uint64_t rays;            /* scene queries TRACED by the last render call (primary + bounce + shadow)  */
   uint64_t samples;         /* pixel samples added by the last render call                             */
-  uint64_t mesh_queries;    /* of `rays`, those that entered the mesh bounding box (triangle loop run)  */
+  uint64_t mesh_queries;    /* of `rays`, those that ran the mesh stage (statistics level 2: that entered the reference's mesh bbox) */
   uint64_t bounces;         /* shaded (non-light) surface interactions of the last render call         */
-  uint64_t hoisted_rays;    /* camera-ray queries NOT traced: loop-invariant over the passes of the call (a fixed sub-pixel
-                               ray that misses / ends on a light does so in every pass); rays + hoisted_rays is the
-                               number of Find_Closest_Hit calls the reference makes for the same samples */
+  uint64_t hoisted_rays;    /* always 0: every Find_Closest_Hit call of the reference is traced (field kept for layout) */
   float    kernel_ms;       /* device time of the render kernel(s), CUDA events                        */
   float    total_ms;        /* device time including resolve and copies                                */
   int32_t  spp;             /* samples per pixel accumulated so far                                    */
@@ -173,6 +171,10 @@ GCORE_API int gcore_render_units(int units, gcore_render_stats* stats);
 /* counters accumulated since the last gcore_resize_viewport (rays, mesh_queries, bounces, hoisted_rays): lets a caller
  * enqueue many gcore_render_units(units, NULL) calls without a host sync and read the totals once.  out4 = 4 x uint64 */
 GCORE_API int gcore_get_counters(uint64_t* out4);
+/* statistics level of the render kernel: 1 (default) rays / bounces are exact and mesh_queries = rays that ran the mesh
+ * stage; 2 = mesh_queries counts the rays that enter the reference's mesh bounding box (geometry.adb:272-274; the 564-flop
+ * queries of the roofline), which costs a bbox test per ray -- use it for an untimed counting pass */
+GCORE_API int gcore_set_stats_level(int level);
 /* GetSPP */
 GCORE_API int gcore_get_spp(void);
 /* resolve the accumulator (ray_tracer.adb:281-291) and copy to HOST buffers, row-major [y*W+x];
