@@ -102,4 +102,50 @@ ART_D void bvh_closest(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, float
   bvh_closest_slot(bv, o, d, inv, t_min, t_max, prim_o, t_o, u_o, v_o, slot);
 }
 
+// ---- resumable closest-hit traversal: the same walk in slices of at most `max_steps` nodes.  The render kernel advances
+// every pending ray by one slice per stage, so that no stage waits for the longest ray of the block.
+struct BvhCursor {
+  int   node;                       // next node to visit; -1: traversal finished
+  int   sp;
+  float best_t; int best_prim; float best_u, best_v;
+};
+
+ART_D void bvh_cursor_begin(const BvhView& bv, float t_max, BvhCursor& c) {
+  c.node = (bv.ntris > 0 && bv.root >= 0) ? bv.root : ((bv.ntris > 0) ? -2 : -1);   // -2: single-leaf tree
+  c.sp = 0; c.best_t = t_max; c.best_prim = -1; c.best_u = 0.0f; c.best_v = 0.0f;
+}
+
+// returns true when the traversal is complete (c.best_* hold the answer; best_prim < 0: nothing hit)
+ART_D bool bvh_cursor_advance(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, int max_steps, BvhCursor& c, int* stack) {
+  int dummy_slot;
+  if (c.node == -2) { bvh_leaf_test(bv, 0, bv.ntris, o, d, t_min, c.best_t, c.best_prim, c.best_u, c.best_v, dummy_slot); c.node = -1; }
+  if (c.node < 0) return true;
+  int node = c.node, sp = c.sp;
+  float best_t = c.best_t, best_u = c.best_u, best_v = c.best_v; int best_prim = c.best_prim;
+  bool done = false;
+#pragma unroll 1
+  for (int step = 0; step < max_steps; step++) {
+    float4 n0 = __ldg(&bv.nodes[4 * node + 0]);
+    float4 n1 = __ldg(&bv.nodes[4 * node + 1]);
+    float4 n2 = __ldg(&bv.nodes[4 * node + 2]);
+    float4 n3 = __ldg(&bv.nodes[4 * node + 3]);
+    int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+    float e0, e1;
+    bool h0 = slab_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, best_t, e0);
+    bool h1 = slab_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, best_t, e1);
+    if (h0 && c0 < 0) { bvh_leaf_test(bv, ~c0, __float_as_int(n3.z), o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h0 = false; }
+    if (h1 && c1 < 0) { bvh_leaf_test(bv, ~c1, __float_as_int(n3.w), o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h1 = false; }
+    if (h0 && h1) {
+      if (e1 < e0) { int t = c0; c0 = c1; c1 = t; }                    // near child first, far child on the stack
+      if (sp < LBVH_STACK) stack[sp++] = c1;
+      node = c0;
+    } else if (h0) node = c0;
+    else if (h1) node = c1;
+    else { if (sp == 0) { done = true; break; } node = stack[--sp]; }
+  }
+  c.node = done ? -1 : node; c.sp = sp;
+  c.best_t = best_t; c.best_prim = best_prim; c.best_u = best_u; c.best_v = best_v;
+  return done;
+}
+
 }  // namespace art

@@ -56,7 +56,11 @@ constexpr int kSphereUnroll = SPH_UNROLL;     // unroll factor of the sphere loo
 #define WAVE_PAIR_TRIS 8                  // constant-memory meshes up to this size are tested as (ray, triangle) pairs
 
 enum { ST_DEPTH_MASK = 31, ST_SUB_SHIFT = 5, ST_SPEC = 1 << 7, ST_HASRAY = 1 << 8, ST_FOLD = 1 << 9, ST_SURF = 1 << 10,
-       ST_BUCKET_SHIFT = 11 /* 3 bits: material bucket of a surface slot */ };
+       ST_BUCKET_SHIFT = 11 /* 3 bits: material bucket of a surface slot */, ST_READY = 1 << 14 /* LBVH scenes: ranked for this round's Y */ };
+
+#ifndef WAVE_BVH_SLICE
+#define WAVE_BVH_SLICE 16                 // LBVH scenes: nodes a pending ray advances per mesh stage
+#endif
 
 template <int NT>
 struct WaveSmem {
@@ -77,6 +81,7 @@ struct WaveSmem {
   float mesh_res[WAVE_PAIR_TRIS * NT];
   short cand[NT];                    // candidate index of the slot's pending ray in the mesh stage, -1: none
   short hmat[NT];
+  short pend[NT];                    // LBVH scenes: traversal in flight for the slot's 1 = path ray, 2 = shadow ray (+4: not started yet)
   short mrank[NT];                   // position of a surface slot inside its material bucket (counting sort X -> M1 -> Y)
   short q_r[2][NT], q_cs[NT], q_cp[NT], q_s[NT];
   int   cnt_r[2], cnt_cs, cnt_cp, cnt_m[5];
@@ -355,8 +360,35 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
   unsigned int nrays = 0, nmesh = 0, nbounce = 0;
   const bool cnt = wa.count_mesh != 0;
 
+  // LBVH scenes: thread t owns the traversal of slot t's pending ray; cursor and stack survive from stage to stage
+  constexpr bool BVH = (MESHK == MESHK_BVH);
+  static_assert(!BVH || NS == NT, "LBVH scenes: one slot per thread");
+  BvhCursor cur; cur.node = -1; cur.sp = 0; cur.best_t = 0.f; cur.best_prim = -1; cur.best_u = 0.f; cur.best_v = 0.f;
+  int tv_stack[BVH ? LBVH_STACK : 1];
+  // one slice of the owner's pending traversal (M1 and M2 of LBVH scenes); rb = ray buffer of the path ray
+  auto bvh_slice = [&](int s) {
+    const int p = S.pend[s];
+    if (p == 0) return;
+    f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
+    if ((p & 3) == 2) {                                                       // shadow ray of Compute_Shadow, ray_tracer.adb:109-113
+      const float ht = S.ht[s];
+      const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
+      d = mk3(S.sx[s], S.sy[s], S.sz[s]);
+      float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
+      epsilon = max2(epsilon, 1.0e-30f);
+      o = hpos + d * epsilon;
+    }
+    if (p & 4) bvh_cursor_begin(g_scn.bvh, 1000000.0f, cur);
+    const bool done = bvh_cursor_advance(g_scn.bvh, o, d, mk3(S.ix[s], S.iy[s], S.iz[s]), 0.0f, WAVE_BVH_SLICE, cur, tv_stack);
+    if (done) {
+      S.mesh_res[4 * s + 0] = cur.best_t; S.mesh_res[4 * s + 1] = cur.best_u; S.mesh_res[4 * s + 2] = cur.best_v;
+      S.mesh_res[4 * s + 3] = __int_as_float(cur.best_prim);
+      S.pend[s] = 0;
+    } else S.pend[s] = (short)(p & 3);
+  };
+
   for (int s = tid; s < NS; s += NT) {
-    S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s; S.cand[s] = -1;
+    S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s; S.cand[s] = -1; S.pend[s] = 0;
   }
   if (tid == 0) {
     S.cnt_r[0] = NS; S.cnt_r[1] = 0; S.cnt_cs = 0; S.cnt_cp = 0; S.retired = 0; S.exhausted = 0;
@@ -380,14 +412,15 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
     }
     for (int s = tid; s < NS; s += NT) {
       int st = S.state[s];
-      const bool on = (st & ST_HASRAY) != 0;
+      // LBVH scenes: a slot whose path ray is still being traversed, or that waits for Y (shadow ray in flight), sits this X out
+      const bool on = BVH ? ((st & (ST_HASRAY | ST_SURF)) == ST_HASRAY && S.pend[s] == 0) : ((st & ST_HASRAY) != 0);
       bool ended = false, push_cs = false;
       int bucket = -1 - (tid & 31);                                           // distinct per lane: no peers in the match below
       if (on) {
         const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
         const f3 inv = mk3(S.ix[s], S.iy[s], S.iz[s]);                        // 1.0/direction (geometry.adb:154-156), computed when the ray was made
         int tri_id; float tri_t, tri_u, tri_v;
-        wave_mesh_result<MESHK, NT>(S, S.cand[s], o, d, true, tri_id, tri_t, tri_u, tri_v);
+        wave_mesh_result<MESHK, NT>(S, BVH ? s : (int)S.cand[s], o, d, true, tri_id, tri_t, tri_u, tri_v);
         DHit h;
         closest_with_mesh<MESHK>(o, d, inv, tri_id, tri_t, tri_u, tri_v, true, h);
         nrays++;
@@ -430,6 +463,7 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
           }
           const int type = g_scn.mats[h.mat].type;
           bucket = (type == MAT_LAMBERT) ? 0 : (type == MAT_PHONG) ? 1 : (type == MAT_GLASS) ? 2 : (type == MAT_MIRROR) ? 3 : 4;
+          st |= bucket << ST_BUCKET_SHIFT;
         }
         if (ended) {
           S.lx[s] = Lterm.x; S.ly[s] = Lterm.y; S.lz[s] = Lterm.z;
@@ -439,10 +473,14 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
       }
       queue_push(ended, S.q_r[par], &S.cnt_r[par], s);
       if (RT != GCORE_PT_STUPID) {
-        const int c = queue_push(push_cs, S.q_cs, &S.cnt_cs, s);
-        if (on) S.cand[s] = (short)c;                                         // -1 when the shadow ray skips the mesh
+        if (BVH) {
+          if (on && (st & ST_SURF)) { if (push_cs) S.pend[s] = 2 | 4; else S.mesh_res[4 * s + 3] = __int_as_float(-1); }
+        } else {
+          const int c = queue_push(push_cs, S.q_cs, &S.cnt_cs, s);
+          if (on) S.cand[s] = (short)c;                                       // -1 when the shadow ray skips the mesh
+        }
       }
-      {                                                                       // counting sort by material type: rank inside the bucket
+      if (!BVH) {                                                             // counting sort by material type: rank inside the bucket
         const unsigned m = __match_any_sync(0xffffffffu, bucket);
         if (bucket >= 0) {
           const int lane = tid & 31, leader = __ffs(m) - 1;
@@ -450,24 +488,42 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
           if (lane == leader) base = atomicAdd(&S.cnt_m[bucket], __popc(m));
           base = __shfl_sync(m, base, leader);
           S.mrank[s] = (short)(base + __popc(m & ((1u << lane) - 1u)));
-          S.state[s] = st | (bucket << ST_BUCKET_SHIFT);
         }
       }
     }
     __syncthreads();
 
     // ================================================================= M1: scatter of the material sort + mesh stage of the shadow rays
+    if (BVH) {
+      // LBVH scenes: advance the pending traversals by one slice, then rank the surface slots whose shadow ray is resolved
+      for (int s = tid; s < NS; s += NT) {
+        bvh_slice(s);
+        int st = S.state[s];
+        const bool ready = ((st & (ST_SURF | ST_HASRAY)) == (ST_SURF | ST_HASRAY)) && S.pend[s] == 0;
+        const int bucket = ready ? ((st >> ST_BUCKET_SHIFT) & 7) : (-1 - (tid & 31));
+        const unsigned m = __match_any_sync(0xffffffffu, bucket);
+        if (ready) {
+          const int lane = tid & 31, leader = __ffs(m) - 1;
+          int base = 0;
+          if (lane == leader) base = atomicAdd(&S.cnt_m[bucket], __popc(m));
+          base = __shfl_sync(m, base, leader);
+          S.mrank[s] = (short)(base + __popc(m & ((1u << lane) - 1u)));
+          S.state[s] = st | ST_READY;
+        }
+      }
+      __syncthreads();
+    }
     {
       const int c0 = S.cnt_m[0], c1 = S.cnt_m[1], c2 = S.cnt_m[2], c3 = S.cnt_m[3];
       for (int s = tid; s < NS; s += NT) {
         const int st = S.state[s];
-        if ((st & (ST_SURF | ST_HASRAY)) == (ST_SURF | ST_HASRAY)) {
+        if (BVH ? ((st & ST_READY) != 0) : ((st & (ST_SURF | ST_HASRAY)) == (ST_SURF | ST_HASRAY))) {
           const int b = (st >> ST_BUCKET_SHIFT) & 7;
           const int off_b = (b == 0) ? 0 : (b == 1) ? c0 : (b == 2) ? c0 + c1 : (b == 3) ? c0 + c1 + c2 : c0 + c1 + c2 + c3;
           S.q_s[off_b + S.mrank[s]] = (short)s;
         }
       }
-      if (RT != GCORE_PT_STUPID) wave_mesh_stage<MESHK, true, NT>(S, S.q_cs, S.cnt_cs, tid);
+      if (!BVH && RT != GCORE_PT_STUPID) wave_mesh_stage<MESHK, true, NT>(S, S.q_cs, S.cnt_cs, tid);
     }
     __syncthreads();
 
@@ -503,7 +559,7 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
               epsilon = max2(epsilon, 1.0e-30f);
               const f3 so = hpos + sdir * epsilon;
               int tri_id; float tri_t, tri_u, tri_v;
-              wave_mesh_result<MESHK, NT>(S, S.cand[s], so, sdir, false, tri_id, tri_t, tri_u, tri_v);
+              wave_mesh_result<MESHK, NT>(S, BVH ? s : (int)S.cand[s], so, sdir, false, tri_id, tri_t, tri_u, tri_v);
               DHit hs;                                                        // closest hit; only is_hit / t are read (ray_tracer.adb:117-122)
               closest_with_mesh<MESHK>(so, sdir, mk3(S.ix[s], S.iy[s], S.iz[s]), tri_id, tri_t, 0.0f, 0.0f, false, hs);
               nrays++;
@@ -535,7 +591,7 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
             const f3 no = hpos + off3, nd = ms.direction;
             S.ox[s] = no.x; S.oy[s] = no.y; S.oz[s] = no.z; S.dx[s] = nd.x; S.dy[s] = nd.y; S.dz[s] = nd.z;
             S.prev_pdf[s] = ms.pdf;
-            st = (st & ~(ST_DEPTH_MASK | ST_SPEC | ST_SURF)) | depth | (ms.pureSpecular ? ST_SPEC : 0);
+            st = (st & ~(ST_DEPTH_MASK | ST_SPEC | ST_SURF | ST_READY)) | depth | (ms.pureSpecular ? ST_SPEC : 0);
             if (depth == max_depth) {                                         // recursion_level = 0 -> (0,0,0)
               S.lx[s] = 0.f; S.ly[s] = 0.f; S.lz[s] = 0.f;
               st = (st & ~ST_HASRAY) | ST_FOLD;
@@ -640,8 +696,12 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
             S.state[s] = st;
           }
         }
-        const int c = queue_push(push_cp, S.q_cp, &S.cnt_cp, s);
-        if (newray) S.cand[s] = (short)c;
+        if (BVH) {
+          if (newray) { if (push_cp) S.pend[s] = 1 | 4; else S.mesh_res[4 * s + 3] = __int_as_float(-1); }
+        } else {
+          const int c = queue_push(push_cp, S.q_cp, &S.cnt_cp, s);
+          if (newray) S.cand[s] = (short)c;
+        }
         // paths that reached Max_Trace_Depth and starved slots wait for the next round's regenerate
         queue_push(ended || (starved && !retire), S.q_r[par ^ 1], &S.cnt_r[par ^ 1], s);
         const unsigned rm = __ballot_sync(0xffffffffu, retire);
@@ -654,7 +714,8 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
     // ================================================================= M2: mesh stage of the new path rays
     if (tid == 0) S.cnt_r[par] = 0;
     if (tid < 5) S.cnt_m[tid] = 0;
-    wave_mesh_stage<MESHK, false, NT>(S, S.q_cp, S.cnt_cp, tid);
+    if (BVH) { for (int s = tid; s < NS; s += NT) bvh_slice(s); }
+    else wave_mesh_stage<MESHK, false, NT>(S, S.q_cp, S.cnt_cp, tid);
     par ^= 1;
     __syncthreads();
   }
