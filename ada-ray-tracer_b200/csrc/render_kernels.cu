@@ -284,7 +284,7 @@ static cudaError_t launch_wave_m(int render_type, const art::WaveArgs& wa, int s
 #define WAVE_NT_CONST 1024
 #endif
 #ifndef WAVE_NT_BVH
-#define WAVE_NT_BVH 128
+#define WAVE_NT_BVH 256
 #endif
 
 int wave_total_slots(int sm_count) { return sm_count * WAVE_TOTAL_THREADS; }   // upper bound for every block shape
