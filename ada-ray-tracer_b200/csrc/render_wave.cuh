@@ -37,8 +37,8 @@ namespace art {
 
 // Block shape: NT threads = NT path slots per block, 1024 / NT blocks per SM (template parameter of the kernel).
 //   constant-memory meshes: 1024 x 1 -- the biggest slot pool wins (measured 256x4 105 ms, 384x3 93, 512x2 85.5, 1024x1 77.4)
-//   LBVH meshes:            128 x 8 -- the traversal stages are long and latency-bound, so several smaller
-//                           blocks per SM overlap one block's traversal with the others' stages (C5: 1024x1 4199 ms, 512x2 3746, 256x4 3309, 128x8 2908)
+//   LBVH meshes:            256 x 4 -- the traversal slices are latency-bound, several blocks per SM overlap them with the
+//                           other blocks' stages (C5 with 16-node slices: 128x8 1738 ms, 256x4 1535, 512x2 1582)
 #define WAVE_TOTAL_THREADS 1024
 #ifndef SPH_UNROLL
 #define SPH_UNROLL 1
