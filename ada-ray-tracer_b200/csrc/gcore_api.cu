@@ -468,6 +468,7 @@ int gcore_add_mesh_3f(const float* a_vertices3f, int a_vertexNum, const int* a_i
 void gcore_instance_meshes(int a_geomId, const float* a_matrices16f, int a_matrixNum) {   // :147-184
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  s.err_code = 0; s.err_text.clear();
   if (a_geomId < 0 || a_geomId >= (int)s.meshes.size() || !a_matrices16f) { fail(GCORE_E_ARG, "gcore_instance_meshes: bad meshId"); return; }
   for (int k = 0; k < a_matrixNum; k++) {
     LegacyInstance in; in.mesh = a_geomId;
@@ -479,6 +480,7 @@ void gcore_instance_meshes(int a_geomId, const float* a_matrices16f, int a_matri
 void gcore_commit_scene(void) {                                        // :241-244
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  s.err_code = 0; s.err_text.clear();                                  // void signature: gcore_last_error() afterwards speaks for this call
   if (ensure_device()) return;
   free_legacy_device();
   std::vector<LegacyInstance> inst = s.instances;

@@ -251,3 +251,58 @@ def test_checkpoint_resume(gscene, pkg, tmp_path):
     assert rt2.GetSPP() == 8
     got = rt2.Render_Pass(read_hdr=True)
     assert rt2.GetSPP() == 16 and np.array_equal(_bits(got), _bits(ref))
+
+
+def test_c_harness_replays_test_adb(gscene, oscene, pkg, ob, tmp_path):
+    """tests/c_harness/replay_test_adb.c: the call sequence of the reference's main program (test.adb:20-79) from plain C
+    through dlopen -- no Python between the caller and the C ABI.  The BMP it writes equals the oracle's frame."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "replay_test_adb")
+    subprocess.run(["gcc", "-O2", "-o", exe, os.path.join(root, "tests", "c_harness", "replay_test_adb.c"), "-ldl"], check=True)
+    w, h, units, passes = 160, 120, 3, 2
+    bmp = str(tmp_path / "ART_render.bmp")
+    r = subprocess.run([exe, pkg.LIB_PATH, os.path.join(root, "data", "pyramid2.vsgf"), bmp, str(w), str(h), str(units), str(passes)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    spp, rays, _ms = r.stdout.split()
+    acc, orays = oscene.render(ob.make_params(w, h, ob.PT_MIS, passes=units * passes, seed=0x5EED0003))
+    assert int(spp) == 4 * units * passes and int(rays) == orays
+    ref = str(tmp_path / "ref.bmp")
+    ldr = np.ascontiguousarray(ob.resolve(acc, int(spp)).reshape(-1))
+    assert ob.lib().ao_save_bmp(ref.encode(), ldr.ctypes.data, w, h) == 0
+    assert open(bmp, "rb").read() == open(ref, "rb").read()
+
+
+def test_argument_and_state_errors(pkg):
+    """error behaviour of the ABI: negative codes + text, nothing throws (embree_connect.cpp exits on errors, :28-49)"""
+    L = pkg.lib()
+    st = pkg.RenderStats()
+    cfg = pkg.make_config(max_depth=17)
+    assert L.gcore_init_render(C.byref(cfg)) == -2 and "max_depth" in pkg.last_error()[1]
+    cfg = pkg.make_config(render_type=9)
+    assert L.gcore_init_render(C.byref(cfg)) == -2
+    assert L.gcore_resize_viewport(0, 10) == -2 and L.gcore_resize_viewport(-5, 10) == -2
+    assert L.gcore_render_units(-1, C.byref(st)) == -2
+    assert L.gcore_set_partition(3, 2) == -2
+    assert L.gcore_closest_hit_batch(-1, None, None) == -2
+    assert L.gcore_closest_hit_batch(0, None, None) == 0
+    assert L.gcore_load_frame(None, 4) == -2
+    gc = pkg.GeometryCore(); gc.init_and_clear()
+    assert gc.add_mesh_3f(np.zeros((0, 3), np.float32), np.zeros(0, np.int32)) == -1      # the reference returns an ambiguous 0
+    gc.commit_scene()                                                                      # empty scene: nothing to build, nothing hit
+    ok, h = gc.closest_hit([0, 0, 0], [0, 0, 1])
+    assert not ok and h["primIndex"] == -1
+    gc.destroy()
+
+
+def test_tiny_viewports_and_zero_units(gscene, oscene, pkg, ob):
+    for w, h in ((1, 1), (2, 3), (31, 1), (1, 33)):
+        rt = pkg.Ray_Tracer(); rt.Threads_Num = 2; rt.seed = 17
+        rt.Init_Render(pkg.PT_MIS); rt.Resize_Viewport(w, h)
+        hdr = rt.Render_Pass(read_hdr=True)
+        acc, rays = oscene.render(ob.make_params(w, h, ob.PT_MIS, passes=2, seed=17))
+        assert np.array_equal(_bits(hdr[..., :3]), _bits(acc)) and int(rt.last_stats.rays) == rays
+    st = pkg.RenderStats()
+    assert pkg.lib().gcore_render_units(0, C.byref(st)) == 0 and st.rays == 0 and st.samples == 0
