@@ -63,7 +63,7 @@ EXPORTS = [
     "gcore_bvh_closest_hit_batch", "gcore_set_device", "gcore_set_partition", "gcore_init_render",
     "gcore_resize_viewport", "gcore_render_units", "gcore_get_counters", "gcore_get_spp", "gcore_read_frame", "gcore_render",
     "gcore_primary_hits", "gcore_accum_device_ptr", "gcore_resolve_device", "gcore_resolve_gathered_device",
-    "gcore_stream", "gcore_synchronize", "gcore_last_error", "gcore_bvh_info", "gcore_kernel_regs", "gcore_bvh_bench", "gcore_load_frame", "gcore_set_stats_level",
+    "gcore_stream", "gcore_synchronize", "gcore_last_error", "gcore_bvh_info", "gcore_kernel_regs", "gcore_bvh_bench", "gcore_load_frame", "gcore_set_stats_level", "gcore_get_bvh_counters",
 ]
 
 _lib = None
@@ -103,6 +103,7 @@ def lib():
     L.gcore_resize_viewport.argtypes = [i32, i32]
     L.gcore_render_units.argtypes = [i32, C.POINTER(RenderStats)]
     L.gcore_get_counters.argtypes = [vp]
+    L.gcore_get_bvh_counters.argtypes = [vp]
     L.gcore_read_frame.argtypes = [vp, vp]
     L.gcore_load_frame.argtypes = [vp, i32]
     L.gcore_set_stats_level.argtypes = [i32]
@@ -420,10 +421,17 @@ def stream_handle():
 
 
 def get_counters():
-    """(rays traced, mesh_queries, bounces, hoisted camera rays) accumulated since the last Resize_Viewport"""
+    """(rays traced, mesh_queries, bounces, LBVH nodes visited) accumulated since the last Resize_Viewport"""
     c = np.zeros(4, np.uint64)
     _ck(lib().gcore_get_counters(_p(c)))
     return int(c[0]), int(c[1]), int(c[2]), int(c[3])
+
+
+def get_bvh_counters():
+    """(LBVH nodes visited, triangle slots tested, traversals started) by the render kernel since the last Resize_Viewport"""
+    c = np.zeros(3, np.uint64)
+    _ck(lib().gcore_get_bvh_counters(_p(c)))
+    return int(c[0]), int(c[1]), int(c[2])
 
 
 def synchronize():

@@ -83,8 +83,8 @@ int ensure_device() {
   CU(cudaSetDevice(s.device), "cudaSetDevice");
   CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
   CU(cudaEventCreate(&s.ev0), "cudaEventCreate"); CU(cudaEventCreate(&s.ev1), "cudaEventCreate"); CU(cudaEventCreate(&s.ev2), "cudaEventCreate");
-  CU(cudaMalloc(&s.d_rays, 4 * sizeof(unsigned long long)), "cudaMalloc");
-  CU(cudaMemset(s.d_rays, 0, 4 * sizeof(unsigned long long)), "cudaMemset");
+  CU(cudaMalloc(&s.d_rays, 6 * sizeof(unsigned long long)), "cudaMalloc");
+  CU(cudaMemset(s.d_rays, 0, 6 * sizeof(unsigned long long)), "cudaMemset");
   s.dev_ready = true;
   s.scene_dirty = true;
   return 0;
@@ -133,7 +133,7 @@ int alloc_accum() {
     s.nslots = nslots;
   }
   CU(cudaMemsetAsync(s.d_accum, 0, sizeof(float4) * (size_t)s.nslots, s.stream), "memset accum");
-  CU(cudaMemsetAsync(s.d_rays, 0, 4 * sizeof(unsigned long long), s.stream), "memset counters");
+  CU(cudaMemsetAsync(s.d_rays, 0, 6 * sizeof(unsigned long long), s.stream), "memset counters");
   s.last_counters[0] = s.last_counters[1] = s.last_counters[2] = s.last_counters[3] = 0;
   s.spp = 0;
   return 0;
@@ -339,7 +339,7 @@ int render_units_locked(int units, gcore_render_stats* stats) {
     CU(cudaStreamSynchronize(s.stream), "render sync");
     float ms = 0.f; cudaEventElapsedTime(&ms, s.ev0, s.ev1);
     stats->rays = c[0] - s.last_counters[0]; stats->mesh_queries = c[1] - s.last_counters[1]; stats->bounces = c[2] - s.last_counters[2];
-    stats->hoisted_rays = c[3] - s.last_counters[3];
+    stats->hoisted_rays = 0;
     s.last_counters[0] = c[0]; s.last_counters[1] = c[1]; s.last_counters[2] = c[2]; s.last_counters[3] = c[3];
     stats->samples = samples; stats->kernel_ms = ms; stats->total_ms = ms; stats->spp = s.spp;
     stats->kernel_launches = launches;
@@ -806,6 +806,18 @@ int gcore_set_stats_level(int level) {
   return 0;
 }
 
+int gcore_get_bvh_counters(uint64_t* out3) {
+  State& s = S();
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  if (!out3) return fail(GCORE_E_ARG, "gcore_get_bvh_counters: null");
+  if (int rc = ensure_device()) return rc;
+  unsigned long long c[6] = {0, 0, 0, 0, 0, 0};
+  CU(cudaMemcpyAsync(c, s.d_rays, sizeof(c), cudaMemcpyDeviceToHost, s.stream), "memcpy counters");
+  CU(cudaStreamSynchronize(s.stream), "counters sync");
+  out3[0] = c[3]; out3[1] = c[4]; out3[2] = c[5];
+  return 0;
+}
+
 int gcore_get_spp(void) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
@@ -826,7 +838,7 @@ int gcore_render(const gcore_render_config* cfg, int width, int height, int unit
   if (width != s.width || height != s.height || !s.d_accum) { if ((rc = gcore_resize_viewport(width, height))) return rc; }
   else {                                                               // same viewport: clear like Resize_Viewport does
     CU(cudaMemsetAsync(s.d_accum, 0, sizeof(float4) * (size_t)s.nslots, s.stream), "memset accum");
-    CU(cudaMemsetAsync(s.d_rays, 0, 4 * sizeof(unsigned long long), s.stream), "memset counters");
+    CU(cudaMemsetAsync(s.d_rays, 0, 6 * sizeof(unsigned long long), s.stream), "memset counters");
     s.last_counters[0] = s.last_counters[1] = s.last_counters[2] = s.last_counters[3] = 0;
     s.spp = 0;
   }

@@ -34,7 +34,7 @@ struct RenderArgs {
   float    zdir;                         // -float(width) / safe_tan(fov/2)   (ray_tracer.adb:67)
   float    half_w, half_h;               // float(width)/2, float(height)/2
   float4*  accum;                        // slot-major accumulator (rgb, unused)
-  unsigned long long* counters;          // [0] += scene queries, [1] += queries inside the mesh bbox, [2] += shaded bounces, [3] unused
+  unsigned long long* counters;          // [0] += scene queries, [1] += queries inside the mesh bbox, [2] += shaded bounces, [3] += LBVH nodes visited, [4] += LBVH triangle slots tested, [5] += LBVH traversals (6 counters)
 };
 
 cudaError_t upload_scene(const art::DeviceScene* host_copy, cudaStream_t s);

@@ -116,7 +116,7 @@ ART_D void bvh_cursor_begin(const BvhView& bv, float t_max, BvhCursor& c) {
 }
 
 // returns true when the traversal is complete (c.best_* hold the answer; best_prim < 0: nothing hit)
-ART_D bool bvh_cursor_advance(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, int max_steps, BvhCursor& c, int* stack) {
+ART_D bool bvh_cursor_advance(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, int max_steps, BvhCursor& c, int* stack, BvhStats& st) {
   int dummy_slot;
   if (c.node == -2) { bvh_leaf_test(bv, 0, bv.ntris, o, d, t_min, c.best_t, c.best_prim, c.best_u, c.best_v, dummy_slot); c.node = -1; }
   if (c.node < 0) return true;
@@ -125,6 +125,7 @@ ART_D bool bvh_cursor_advance(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min
   bool done = false;
 #pragma unroll 1
   for (int step = 0; step < max_steps; step++) {
+    st.nodes++;
     float4 n0 = __ldg(&bv.nodes[4 * node + 0]);
     float4 n1 = __ldg(&bv.nodes[4 * node + 1]);
     float4 n2 = __ldg(&bv.nodes[4 * node + 2]);
@@ -133,8 +134,8 @@ ART_D bool bvh_cursor_advance(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min
     float e0, e1;
     bool h0 = slab_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, best_t, e0);
     bool h1 = slab_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, best_t, e1);
-    if (h0 && c0 < 0) { bvh_leaf_test(bv, ~c0, __float_as_int(n3.z), o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h0 = false; }
-    if (h1 && c1 < 0) { bvh_leaf_test(bv, ~c1, __float_as_int(n3.w), o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h1 = false; }
+    if (h0 && c0 < 0) { st.tris += __float_as_int(n3.z); bvh_leaf_test(bv, ~c0, __float_as_int(n3.z), o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h0 = false; }
+    if (h1 && c1 < 0) { st.tris += __float_as_int(n3.w); bvh_leaf_test(bv, ~c1, __float_as_int(n3.w), o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h1 = false; }
     if (h0 && h1) {
       if (e1 < e0) { int t = c0; c0 = c1; c1 = t; }                    // near child first, far child on the stack
       if (sp < LBVH_STACK) stack[sp++] = c1;

@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
   // LBVH scenes: thread t owns the traversal of slot t's pending ray; cursor and stack survive from stage to stage
   constexpr bool BVH = (MESHK == MESHK_BVH);
   static_assert(!BVH || NS == NT, "LBVH scenes: one slot per thread");
+  BvhStats tstat; tstat.nodes = 0; tstat.tris = 0; unsigned int ntrav = 0;      // LBVH nodes visited / triangle slots tested / traversals
   BvhCursor cur; cur.node = -1; cur.sp = 0; cur.best_t = 0.f; cur.best_prim = -1; cur.best_u = 0.f; cur.best_v = 0.f;
   int tv_stack[BVH ? LBVH_STACK : 1];
   // one slice of the owner's pending traversal (M1 and M2 of LBVH scenes); rb = ray buffer of the path ray
@@ -378,8 +379,8 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
       epsilon = max2(epsilon, 1.0e-30f);
       o = hpos + d * epsilon;
     }
-    if (p & 4) bvh_cursor_begin(g_scn.bvh, 1000000.0f, cur);
-    const bool done = bvh_cursor_advance(g_scn.bvh, o, d, mk3(S.ix[s], S.iy[s], S.iz[s]), 0.0f, WAVE_BVH_SLICE, cur, tv_stack);
+    if (p & 4) { bvh_cursor_begin(g_scn.bvh, 1000000.0f, cur); ntrav++; }
+    const bool done = bvh_cursor_advance(g_scn.bvh, o, d, mk3(S.ix[s], S.iy[s], S.iz[s]), 0.0f, WAVE_BVH_SLICE, cur, tv_stack, tstat);
     if (done) {
       S.mesh_res[4 * s + 0] = cur.best_t; S.mesh_res[4 * s + 1] = cur.best_u; S.mesh_res[4 * s + 2] = cur.best_v;
       S.mesh_res[4 * s + 3] = __int_as_float(cur.best_prim);
@@ -728,6 +729,12 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
     atomicAdd(&a.counters[0], (unsigned long long)total_rays);
     atomicAdd(&a.counters[1], (unsigned long long)total_mesh);
     atomicAdd(&a.counters[2], (unsigned long long)total_bnc);
+  }
+  if (BVH) {
+    unsigned int tn = __reduce_add_sync(0xffffffffu, tstat.nodes), tt = __reduce_add_sync(0xffffffffu, tstat.tris), tv = __reduce_add_sync(0xffffffffu, ntrav);
+    if ((threadIdx.x & 31) == 0 && tn) {
+      atomicAdd(&a.counters[3], (unsigned long long)tn); atomicAdd(&a.counters[4], (unsigned long long)tt); atomicAdd(&a.counters[5], (unsigned long long)tv);
+    }
   }
 }
 

@@ -96,17 +96,37 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def oracle_run(width, height, rtype, aa, depth, units, threads, seed=SEED, first_sample=0):
+_ORACLE_SCENES = {}
+
+
+def oracle_scene(workload):
+    """the CPU oracle's scene for a workload (the C5 scenes carry the 10 002 828-triangle mesh + 64 spheres; the oracle then
+    uses its own CPU BVH -- a binned-SAH restatement, not Embree)"""
     ob = ge.load_oracle()
-    global _ORACLE_SCENE
-    try:
-        _ORACLE_SCENE
-    except NameError:
-        _ORACLE_SCENE = ob.OracleScene()
+    key = "C5" if workload.startswith("C5") else "cornell"
+    if key not in _ORACLE_SCENES:
+        sc = ob.OracleScene()
+        if key == "C5":
+            import importlib
+            syn = importlib.import_module(ge.load_package().__name__ + ".synthetic")
+            sp, _box = syn.c5_analytic()
+            pos, nrm, tris = syn.cube_sphere(913)
+            sc.set_spheres(sp); sc.set_mesh(pos, nrm, tris)
+            # build the CPU BVH outside any timed region (it is built lazily by the first query)
+            sc.render(ob.make_params(8, 8, ob.PT_MIS, passes=1, mesh_mode=ob.MESH_NEAREST))
+        _ORACLE_SCENES[key] = sc
+    return _ORACLE_SCENES[key]
+
+
+def oracle_run(width, height, rtype, aa, depth, units, threads, seed=SEED, first_sample=0, workload="C4_1024", rows=None):
+    ob = ge.load_oracle()
+    sc = oracle_scene(workload)
+    mesh_mode = ob.MESH_NEAREST if workload.startswith("C5") else ob.MESH_REFERENCE_BF
+    y0, y1 = rows if rows else (0, 0)
     p = ob.make_params(width, height, getattr(ob, rtype), aa=aa, max_depth=depth, passes=units, seed=seed,
-                       first_sample=first_sample, threads=threads)
+                       first_sample=first_sample, threads=threads, mesh_mode=mesh_mode, y0=y0, y1=y1)
     t0 = time.perf_counter()
-    _, rays = _ORACLE_SCENE.render(p)
+    _, rays = sc.render(p)
     return rays, time.perf_counter() - t0
 
 
@@ -119,11 +139,13 @@ def run_reference(args, wl):
     width, height, rtype, aa, depth, units, desc = wl
     cores = host_cores()
     sample_units = 1                                    # 4 spp of the full image per step
+    if args.workload == "C5":                           # 8.3 Mpixel x 10 M triangles on the CPU: sample at half resolution (same scene, same camera)
+        width, height = width // 2, height // 2
     for _ in range(max(args.warmup, 1)):
-        oracle_run(width, height, rtype, aa, depth, sample_units, cores)
+        oracle_run(width, height, rtype, aa, depth, sample_units, cores, workload=args.workload)
     rays_tot, t_tot = 0, 0.0
     for k in range(args.steps):
-        rays, dt = oracle_run(width, height, rtype, aa, depth, sample_units, cores, first_sample=4 * k)
+        rays, dt = oracle_run(width, height, rtype, aa, depth, sample_units, cores, first_sample=4 * k, workload=args.workload)
         rays_tot += rays; t_tot += dt
     v = rays_tot / t_tot / 1e6
     sample = "%dx%d %s depth %d, %d unit(s) (%d spp) of the full image per step" % (width, height, rtype, depth, sample_units,
@@ -131,7 +153,8 @@ def run_reference(args, wl):
     line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "sample": sample, "note": "CPU oracle port of the Ada renderer (C++ -O2, no FMA); not GNAT, not Embree: neither exists in this image"},
+            "config": {"workload": desc, "sample": sample, "note": "CPU oracle port of the Ada renderer (C++ -O2, no FMA); not GNAT, not Embree: neither exists in this image"
+                       + ("; the 10 M-triangle mesh goes through the oracle's own CPU BVH" if args.workload.startswith("C5") else "")},
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -204,6 +227,7 @@ def main():
             flush.fill_(1); tr.Render_Pass()
     barrier()
     c0 = pkg.get_counters()
+    bv0 = pkg.get_bvh_counters()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -219,15 +243,16 @@ def main():
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if sampler else None
     c1 = pkg.get_counters()
+    bv1 = pkg.get_bvh_counters()
     step_ms = sum(a.elapsed_time(c) for a, _, c in ev)
     kern_ms = sum(a.elapsed_time(b) for a, b, _ in ev)
     rays_local, mesh_local, bounce_local, _unused = (c1[i] - c0[i] for i in range(4))
     t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([rays_local, mesh_local, bounce_local, launches], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([rays_local, mesh_local, bounce_local, launches, bv1[0] - bv0[0], bv1[1] - bv0[1], bv1[2] - bv0[2]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     step_ms, kern_ms = float(t[0]), float(t[1])
-    rays, _mesh_stage_rays, bounces, launches_all = (float(x) for x in cnt)
+    rays, _mesh_stage_rays, bounces, launches_all, bvh_nodes, bvh_tris, bvh_trav = (float(x) for x in cnt)
     mesh_q = mesh_share * rays                           # reference-bbox entries among the timed rays (share from the counting pass)
     value = rays / (step_ms * 1e-3) / 1e6
 
@@ -280,8 +305,8 @@ def main():
         traffic = None
         try:                                            # dram bytes per launch of the same workload from the committed ncu capture
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if tj.get("workload") == args.workload and world == 1:
-                traffic = tj["dram_bytes_per_launch"]
+            if args.workload in tj and world == 1:
+                traffic = tj[args.workload]["dram_bytes_per_launch"]
         except Exception:
             pass
         hbm_bytes = (2 * units + 2) * 16.0 * npx / world   # per-pass colours written + read back by the fold, accumulator read + write
@@ -294,18 +319,36 @@ def main():
                     "kernel": "render_wave_kernel<%s> + fold_kernel" % rtype, "kernel_ms_per_launch": kern_ms / args.steps,
                     "hbm_view": {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_GBs": hbm_bytes / kern_s / 1e9, "peak_GBs": peaks.get("hbm_gbs", 6650.0),
                                  "peak_source": "measured" if "hbm_gbs" in peaks else "fallback"}}
+        if args.workload.startswith("C5"):
+            # LBVH scene: the mesh traversal is the dominant, bandwidth-bound part (SURVEY 8d ii).  Algorithmic bytes = 64 B per
+            # node visited + 48 B per triangle slot tested (both counted by the kernel) + 32 B ray in + 16 B hit out per traversal,
+            # + the colour buffer; against the measured HBM copy rate
+            trav_bytes = 64.0 * bvh_nodes + 48.0 * bvh_tris + 48.0 * bvh_trav
+            bytes_per_launch = (trav_bytes / args.steps + hbm_bytes * world) / world
+            gbs = bytes_per_launch / kern_s / 1e9
+            peak_hbm = peaks.get("hbm_gbs", 6650.0)
+            roofline = {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm, "traffic": traffic,
+                        "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
+                        "note": "algorithmic bytes: 64 B x LBVH nodes visited + 48 B x triangle slots tested (kernel counters) + ray/hit + colour buffer",
+                        "kernel": "render_wave_kernel<%s, LBVH> + fold_kernel" % rtype, "kernel_ms_per_launch": kern_ms / args.steps,
+                        "nodes_per_traversal": bvh_nodes / max(bvh_trav, 1.0), "tris_per_traversal": bvh_tris / max(bvh_trav, 1.0),
+                        "traversals_per_query": bvh_trav / max(rays, 1.0),
+                        "issue_view": {"achieved_TFLOPs": achieved, "peak_TFLOPs": peak, "frac": achieved / peak}}
         cpu_baseline = None
         if not args.no_cpu_baseline and world == 1:
             cores = host_cores()
-            r1, t1 = oracle_run(width, height, rtype, aa, depth, 1, cores)          # also warms the page cache
+            cw, ch = (width // 2, height // 2) if args.workload == "C5" else (width, height)     # C5: half resolution, same scene and camera
+            r1, t1 = oracle_run(cw, ch, rtype, aa, depth, 1, cores, workload=args.workload)          # also warms the page cache
             n_units = int(min(max(round(12.0 / max(t1, 1e-3)), 1), units))
-            r2, t2 = oracle_run(width, height, rtype, aa, depth, n_units, cores)
+            r2, t2 = oracle_run(cw, ch, rtype, aa, depth, n_units, cores, workload=args.workload)
             cpu_baseline = {"value": r2 / t2 / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                            "sample": "%d of the step's %d units (%d spp) of the full %dx%d image, %.1f s" % (n_units, units, n_units * (4 if aa else 1), width, height, t2)}
+                            "sample": "%d of the step's %d units (%d spp) of the %dx%d image%s, %.1f s" % (
+                                n_units, units, n_units * (4 if aa else 1), cw, ch, "" if (cw, ch) == (width, height) else " (half resolution)", t2)}
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc, "scene": "scene.adb Cornell box + 2 spheres + sphere light + data/pyramid2.vsgf",
+                "config": {"workload": desc, "scene": ("scene.adb Cornell box + sphere light + 64 Philox spheres + 10 002 828-triangle displaced cube-sphere (synthetic.py, SURVEY 8d C5)"
+                                                     if args.workload.startswith("C5") else "scene.adb Cornell box + 2 spheres + sphere light + data/pyramid2.vsgf"),
                            "seed": SEED, "parallelism": "tiles32x32_rr%d" % world,
                            "l2": "256 MiB buffer written between timed steps (outside the per-step CUDA events); inputs are < L2",
                            "numerics": "bit-exact mode (-fmad=false, IEEE div/sqrt), identical to the CPU oracle"},

@@ -168,9 +168,12 @@ GCORE_API int gcore_resize_viewport(int width, int height);
 /* `units` DoPass units on the device; each adds 4 (AA) or 1 spp, exactly like one Path_Trace_Thread doing one
  * pass (Render_Pass = Threads_Num units).  No host transfer. */
 GCORE_API int gcore_render_units(int units, gcore_render_stats* stats);
-/* counters accumulated since the last gcore_resize_viewport (rays, mesh_queries, bounces, hoisted_rays): lets a caller
+/* counters accumulated since the last gcore_resize_viewport (rays, mesh_queries, bounces, LBVH nodes visited): lets a caller
  * enqueue many gcore_render_units(units, NULL) calls without a host sync and read the totals once.  out4 = 4 x uint64 */
 GCORE_API int gcore_get_counters(uint64_t* out4);
+/* LBVH work of the render kernel since the last gcore_resize_viewport: out3 = {nodes visited (64 B each), triangle slots
+ * tested (48 B each), traversals started} -- the measured visit counts of the traversal roofline */
+GCORE_API int gcore_get_bvh_counters(uint64_t* out3);
 /* statistics level of the render kernel: 1 (default) rays / bounces are exact and mesh_queries = rays that ran the mesh
  * stage; 2 = mesh_queries counts the rays that enter the reference's mesh bounding box (geometry.adb:272-274; the 564-flop
  * queries of the roofline), which costs a bbox test per ray -- use it for an untimed counting pass */
