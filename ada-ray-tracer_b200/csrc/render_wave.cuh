@@ -346,7 +346,6 @@ ART_D void wave_mesh_result(const WaveSmem<NT>& S, int c, f3 o, f3 d, bool want_
 template <int RT, int MESHK, int NT>
 __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kernel(const __grid_constant__ WaveArgs wa) {
   constexpr int NS = WAVE_SLOTS(NT);        // path slots of this block
-  constexpr int WAVE_BATCH = 2 * NS;        // work items fetched from the global counter at a time
   extern __shared__ __align__(16) unsigned char wave_smem_raw[];
   WaveSmem<NT>& S = *reinterpret_cast<WaveSmem<NT>*>(wave_smem_raw);
   const gcore_dev::RenderArgs& a = wa.r;
@@ -354,6 +353,16 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
   const int gslot0 = blockIdx.x * NT;
   const int total_slots = gridDim.x * NT;
   const unsigned int total_items = (unsigned int)wa.units * (unsigned int)a.nslots;
+  // work items are fetched from the global counter in batches that shrink towards the end of the launch (guided
+  // self-scheduling): 2 NS while there is plenty, down to 64, so that the blocks run dry together
+  auto fetch_batch = [&](unsigned int& base, unsigned int& count) {
+    const unsigned int seen = *(volatile unsigned int*)wa.next_item;
+    const unsigned int rem = (seen < total_items) ? (total_items - seen) : 0u;
+    unsigned int want = rem / (2u * gridDim.x);
+    want = want < 64u ? 64u : (want > 2u * NS ? 2u * NS : want);
+    base = atomicAdd(wa.next_item, want);
+    count = want;
+  };
   const int aa = a.anti_aliasing;
   const int max_depth = a.max_depth;
   const f3 bg = mk3(a.bg[0], a.bg[1], a.bg[2]);
@@ -394,9 +403,10 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
   if (tid == 0) {
     S.cnt_r[0] = NS; S.cnt_r[1] = 0; S.cnt_cs = 0; S.cnt_cp = 0; S.retired = 0; S.exhausted = 0;
     for (int b = 0; b < 5; b++) S.cnt_m[b] = 0;
-    unsigned int base = atomicAdd(wa.next_item, (unsigned int)WAVE_BATCH);
+    unsigned int base, count;
+    fetch_batch(base, count);
     if (base >= total_items) { S.exhausted = 1; S.pool_next = 0; S.pool_end = 0; }
-    else { S.pool_next = (int)base; S.pool_end = (int)min(base + (unsigned int)WAVE_BATCH, total_items); }
+    else { S.pool_next = (int)base; S.pool_end = (int)min(base + count, total_items); }
   }
   __syncthreads();
 
@@ -406,9 +416,10 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
     if (tid == 0) {
       S.cnt_cp = 0;                                                           // consumed by M2 of the previous round
       if (!S.exhausted && S.pool_next >= S.pool_end) {                        // refill the item pool (fetched from in Y only)
-        unsigned int base = atomicAdd(wa.next_item, (unsigned int)WAVE_BATCH);
+        unsigned int base, count;
+        fetch_batch(base, count);
         if (base >= total_items) S.exhausted = 1;
-        else { S.pool_next = (int)base; S.pool_end = (int)min(base + (unsigned int)WAVE_BATCH, total_items); }
+        else { S.pool_next = (int)base; S.pool_end = (int)min(base + count, total_items); }
       }
     }
     for (int s = tid; s < NS; s += NT) {
