@@ -47,7 +47,7 @@ class RenderConfig(C.Structure):
 
 
 class RenderStats(C.Structure):
-    _fields_ = [("rays", C.c_uint64), ("samples", C.c_uint64), ("mesh_queries", C.c_uint64), ("bounces", C.c_uint64), ("hoisted_rays", C.c_uint64),
+    _fields_ = [("rays", C.c_uint64), ("samples", C.c_uint64), ("mesh_queries", C.c_uint64), ("bounces", C.c_uint64), ("reserved0", C.c_uint64),
                 ("kernel_ms", C.c_float), ("total_ms", C.c_float),
                 ("spp", C.c_int32), ("kernel_launches", C.c_int32)]
 

@@ -339,7 +339,7 @@ int render_units_locked(int units, gcore_render_stats* stats) {
     CU(cudaStreamSynchronize(s.stream), "render sync");
     float ms = 0.f; cudaEventElapsedTime(&ms, s.ev0, s.ev1);
     stats->rays = c[0] - s.last_counters[0]; stats->mesh_queries = c[1] - s.last_counters[1]; stats->bounces = c[2] - s.last_counters[2];
-    stats->hoisted_rays = 0;
+    stats->reserved0 = 0;
     s.last_counters[0] = c[0]; s.last_counters[1] = c[1]; s.last_counters[2] = c[2]; s.last_counters[3] = c[3];
     stats->samples = samples; stats->kernel_ms = ms; stats->total_ms = ms; stats->spp = s.spp;
     stats->kernel_launches = launches;

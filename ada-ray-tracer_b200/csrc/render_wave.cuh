@@ -4,7 +4,7 @@
 // Compute_Shadow) and the Ada task pool of ray_tracer.adb:142-194.
 //
 // Why this shape.  A one-thread-per-pixel megakernel of this path runs with 12.7 of 32 lanes active and spends 47 % of
-// its stall samples waiting for instructions (profiles/r01_render_megakernel.md): lanes of a warp sit on different
+// its stall samples waiting for instructions (profiles/r01_render.md): lanes of a warp sit on different
 // materials and bounce depths, the 8-triangle mesh loop runs for ~2 lanes, and 60 KB of inlined code thrash the 32 KB
 // instruction cache.  Here a persistent block owns NS path slots whose state lives in shared memory (SoA), and walks
 // all of them through two wide and two narrow stages per bounce, separated by __syncthreads().  Between stages slots
@@ -205,7 +205,7 @@ ART_D void closest_with_mesh(f3 o, f3 d, f3 inv, int tri_id, float tri_t, float 
     bool is_hit = (hp.x > g_scn.fl_min[0]) && (hp.x < g_scn.fl_max[0]) && (hp.z > g_scn.fl_min[2]) && (hp.z < g_scn.fl_max[2]) && (tmin >= 0.0f);
     if (is_hit && tmin < nearestHitDist) { winner = 2; nearestHitDist = tmin; }
   }
-  if (tri_id >= 0 && tri_t < nearestHitDist) { winner = 3; nearestHitDist = tri_t; }   // IntersectMeshBF result (S2 / S4)
+  if (tri_id >= 0 && tri_t < nearestHitDist) { winner = 3; nearestHitDist = tri_t; }   // IntersectMeshBF result (mesh stages M2 / M1)
 
   h.is_hit = (winner == 0) ? (sph_hit ? 1 : 0) : 1;
   h.t = (winner == 0) ? (sph_hit ? min_t : 1.0f) : nearestHitDist;

@@ -83,7 +83,7 @@ package GCore_B200 is
   pragma Convention (C, Gcore_Render_Config);
 
   type Gcore_Render_Stats is record
-    rays, samples, mesh_queries, bounces, hoisted_rays : Unsigned_64;
+    rays, samples, mesh_queries, bounces, reserved0 : Unsigned_64;
     kernel_ms, total_ms : Float;
     spp, kernel_launches : Integer_32;
   end record;

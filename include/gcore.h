@@ -150,7 +150,7 @@ typedef struct gcore_render_stats {
   uint64_t samples;         /* pixel samples added by the last render call                             */
   uint64_t mesh_queries;    /* of `rays`, those that ran the mesh stage (statistics level 2: that entered the reference's mesh bbox) */
   uint64_t bounces;         /* shaded (non-light) surface interactions of the last render call         */
-  uint64_t hoisted_rays;    /* always 0: every Find_Closest_Hit call of the reference is traced (field kept for layout) */
+  uint64_t reserved0;       /* 0 */
   float    kernel_ms;       /* device time of the render kernel(s), CUDA events                        */
   float    total_ms;        /* device time including resolve and copies                                */
   int32_t  spp;             /* samples per pixel accumulated so far                                    */

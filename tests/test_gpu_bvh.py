@@ -198,7 +198,7 @@ def test_render_with_nearest_mesh_bit_exact(pkg, ob, nseg):
     hdr = rt.Render_Pass(read_hdr=True)
     acc, rays = osc.render(ob.make_params(w, h, ob.PT_MIS, passes=2, seed=31, mesh_mode=ob.MESH_NEAREST))
     assert np.array_equal(_bits(hdr[..., :3]), _bits(acc))
-    assert int(rt.last_stats.rays + rt.last_stats.hoisted_rays) == rays
+    assert int(rt.last_stats.rays) == rays
 
 
 def test_reference_bf_mode_rejects_big_meshes(pkg, ob):

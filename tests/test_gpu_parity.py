@@ -101,7 +101,7 @@ def test_closest_hit_rect_light_scene(pkg, ob):
         hdr = rt.Render_Pass(read_hdr=True)
         acc, rays_o = osc.render(ob.make_params(64, 48, rtype, passes=1, seed=rt.seed))
         assert np.array_equal(_bits(hdr[..., :3]), _bits(acc))
-        assert int(rt.last_stats.rays + rt.last_stats.hoisted_rays) == rays_o
+        assert int(rt.last_stats.rays) == rays_o
 
 
 RENDER_CASES = [
@@ -129,7 +129,7 @@ def test_render_bit_exact(gscene, oscene, pkg, ob, rtype, aa, depth, units, w, h
     diff = (_bits(hdr[..., :3]) != _bits(acc)).any(-1)
     assert diff.sum() == 0, "%d of %d pixels differ; first at %s: gpu %s oracle %s" % (
         diff.sum(), w * h, np.argwhere(diff)[0], hdr[tuple(np.argwhere(diff)[0])], acc[tuple(np.argwhere(diff)[0])])
-    assert int(rt.last_stats.rays + rt.last_stats.hoisted_rays) == rays     # traced + loop-invariant camera rays
+    assert int(rt.last_stats.rays) == rays
     assert rt.GetSPP() == units * (4 if aa else 1)
     assert np.array_equal(rt.screen_buffer, ob.resolve(acc, rt.GetSPP()))
 
@@ -170,7 +170,7 @@ def test_one_shot_render_call(gscene, oscene, pkg, ob):
     acc, rays = oscene.render(ob.make_params(w, h, ob.PT_SHADOW, passes=2, seed=5))
     assert np.array_equal(_bits(hdr[..., :3]), _bits(acc))
     assert np.array_equal(ldr, ob.resolve(acc, 8))
-    assert st.rays + st.hoisted_rays == rays and st.spp == 8 and st.kernel_launches == 3 and st.samples == w * h * 8
+    assert st.rays == rays and st.spp == 8 and st.kernel_launches == 3 and st.samples == w * h * 8
 
 
 def test_full_size_properties(gscene, pkg):
@@ -181,10 +181,10 @@ def test_full_size_properties(gscene, pkg):
     rt.Init_Render(pkg.PT_MIS); rt.Resize_Viewport(w, h)
     a = rt.Render_Pass(read_hdr=True).copy()
     ldr_a = rt.screen_buffer.copy()
-    rays_a = int(rt.last_stats.rays + rt.last_stats.hoisted_rays)
+    rays_a = int(rt.last_stats.rays)
     rt.Resize_Viewport(w, h)
     b = rt.Render_Pass(read_hdr=True)
-    assert np.array_equal(_bits(a), _bits(b)) and int(rt.last_stats.rays + rt.last_stats.hoisted_rays) == rays_a      # idempotent / deterministic
+    assert np.array_equal(_bits(a), _bits(b)) and int(rt.last_stats.rays) == rays_a      # idempotent / deterministic
     assert np.isfinite(a).all() and (a[..., :3] >= 0).all()
     mean = a[..., :3].mean() / 4.0
     assert 0.02 < mean < 0.5
