@@ -52,6 +52,7 @@ struct State {
   unsigned long long* d_rays = nullptr;      // 3 cumulative counters: rays, mesh-bbox queries, bounces
   unsigned long long last_counters[4] = {0, 0, 0, 0};
   float4* d_hdr = nullptr; uint32_t* d_ldr = nullptr; size_t out_pixels = 0;
+  gcore_ray* d_batch_rays = nullptr; gcore_HitCpp* d_batch_hits = nullptr; int* d_batch_found = nullptr; size_t batch_cap = 0;
   WaveBuffers wave;                          // work buffers of the wavefront render kernel
   int stats_level = 1;
   int sm_count = 0;
@@ -519,24 +520,35 @@ void gcore_commit_scene(void) {                                        // :241-2
   s.scene_dirty = true;
 }
 
+// device staging of the batched seam queries: grown on demand and kept, so that the one-ray-per-call legacy entry point
+// (scene_hydra_embree.adb:426-446 calls it for every ray) costs a launch and two small copies, not six allocations
+static int ensure_batch_buffers(size_t n) {
+  State& s = S();
+  if (n <= s.batch_cap) return 0;
+  cudaFree(s.d_batch_rays); cudaFree(s.d_batch_hits); cudaFree(s.d_batch_found);
+  s.d_batch_rays = nullptr; s.d_batch_hits = nullptr; s.d_batch_found = nullptr; s.batch_cap = 0;
+  size_t cap = n < 256 ? 256 : n;
+  CU(cudaMalloc(&s.d_batch_rays, sizeof(gcore_ray) * cap), "cudaMalloc batch");
+  CU(cudaMalloc(&s.d_batch_hits, sizeof(gcore_HitCpp) * cap), "cudaMalloc batch");
+  CU(cudaMalloc(&s.d_batch_found, sizeof(int) * cap), "cudaMalloc batch");
+  s.batch_cap = cap;
+  return 0;
+}
+
 int gcore_bvh_closest_hit_batch(int n, const gcore_ray* rays, float t_near, float t_far, gcore_HitCpp* hits, int32_t* found) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
   if (n < 0 || (n > 0 && (!rays || !hits || !found))) return fail(GCORE_E_ARG, "gcore_bvh_closest_hit_batch: bad arguments");
   if (n == 0) return 0;
   if (int rc = sync_scene()) return rc;
-  gcore_ray* d_r = nullptr; gcore_HitCpp* d_h = nullptr; int* d_f = nullptr;
-  auto cleanup = [&]() { cudaFree(d_r); cudaFree(d_h); cudaFree(d_f); };
-  cudaError_t e;
-  if ((e = cudaMalloc(&d_r, sizeof(gcore_ray) * (size_t)n)) != cudaSuccess || (e = cudaMalloc(&d_h, sizeof(gcore_HitCpp) * (size_t)n)) != cudaSuccess ||
-      (e = cudaMalloc(&d_f, 4 * (size_t)n)) != cudaSuccess) { cleanup(); return fail_cuda(e, "cudaMalloc batch"); }
-  cudaMemcpyAsync(d_r, rays, sizeof(gcore_ray) * (size_t)n, cudaMemcpyHostToDevice, s.stream);
-  cudaMemcpyAsync(d_h, hits, sizeof(gcore_HitCpp) * (size_t)n, cudaMemcpyHostToDevice, s.stream);   // records are only written on a hit
-  e = gcore_dev::launch_bvh_batch(n, d_r, t_near, t_far, d_h, d_f, s.stream);
+  if (int rc = ensure_batch_buffers((size_t)n)) return rc;
+  gcore_ray* d_r = s.d_batch_rays; gcore_HitCpp* d_h = s.d_batch_hits; int* d_f = s.d_batch_found;
+  cudaError_t e = cudaMemcpyAsync(d_r, rays, sizeof(gcore_ray) * (size_t)n, cudaMemcpyHostToDevice, s.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_h, hits, sizeof(gcore_HitCpp) * (size_t)n, cudaMemcpyHostToDevice, s.stream);   // records are only written on a hit
+  if (e == cudaSuccess) e = gcore_dev::launch_bvh_batch(n, d_r, t_near, t_far, d_h, d_f, s.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_h, sizeof(gcore_HitCpp) * (size_t)n, cudaMemcpyDeviceToHost, s.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(found, d_f, 4 * (size_t)n, cudaMemcpyDeviceToHost, s.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
-  cleanup();
   if (e != cudaSuccess) return fail_cuda(e, "bvh batch");
   // flattened triangle id -> (primIndex inside its mesh, instIndex); Ng from the flattened world-space triangle
   for (int i = 0; i < n; i++) if (found[i]) {
