@@ -18,6 +18,8 @@
 
 namespace art {
 
+// One stack entry per level at most (the far child is pushed while descending).  A Karras tree over 63-bit Morton codes with the
+// sorted position as tie-break is at most 63 + 32 levels deep, so 96 entries cannot overflow; the guards below are belt and braces.
 #define LBVH_STACK 96
 
 ART_D bool slab_hit(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz,
