@@ -138,14 +138,14 @@ def run_reference(args, wl):
         return
     width, height, rtype, aa, depth, units, desc = wl
     cores = host_cores()
-    sample_units = 1                                    # 4 spp of the full image per step
+    sample_units = min(8, units)                        # up to 32 spp of the full image per step (~1-2 s of all host cores)
     if args.workload == "C5":                           # 8.3 Mpixel x 10 M triangles on the CPU: sample at half resolution (same scene, same camera)
-        width, height = width // 2, height // 2
+        width, height, sample_units = width // 2, height // 2, 1
     for _ in range(max(args.warmup, 1)):
         oracle_run(width, height, rtype, aa, depth, sample_units, cores, workload=args.workload)
     rays_tot, t_tot = 0, 0.0
     for k in range(args.steps):
-        rays, dt = oracle_run(width, height, rtype, aa, depth, sample_units, cores, first_sample=4 * k, workload=args.workload)
+        rays, dt = oracle_run(width, height, rtype, aa, depth, sample_units, cores, first_sample=4 * sample_units * k, workload=args.workload)
         rays_tot += rays; t_tot += dt
     v = rays_tot / t_tot / 1e6
     sample = "%dx%d %s depth %d, %d unit(s) (%d spp) of the full image per step" % (width, height, rtype, depth, sample_units,
