@@ -318,7 +318,9 @@ int render_units_locked(int units, gcore_render_stats* stats) {
   } else if (units > 0) {
     const int per = s.cfg.anti_aliasing ? 4 : 1;
     // the colour buffer holds one float4 per (pass, pixel): long renders go in chunks of passes
-    size_t chunk = GC_COLBUF_CAP_BYTES / (sizeof(float4) * (size_t)s.nslots);
+    size_t cap_bytes = GC_COLBUF_CAP_BYTES;
+    if (const char* e = getenv("GCORE_COLBUF_CAP_KB")) { long v = atol(e); if (v > 0) cap_bytes = (size_t)v << 10; }   // tests: force the chunked path on small frames
+    size_t chunk = cap_bytes / (sizeof(float4) * (size_t)s.nslots);
     if (chunk < 1) chunk = 1;
     if (chunk > (size_t)units) chunk = (size_t)units;
     while ((chunk * (size_t)s.nslots) >> 31) chunk >>= 1;

@@ -306,3 +306,26 @@ def test_tiny_viewports_and_zero_units(gscene, oscene, pkg, ob):
         assert np.array_equal(_bits(hdr[..., :3]), _bits(acc)) and int(rt.last_stats.rays) == rays
     st = pkg.RenderStats()
     assert pkg.lib().gcore_render_units(0, C.byref(st)) == 0 and st.rays == 0 and st.samples == 0
+
+
+def test_long_renders_go_in_chunks_of_passes(oscene, ob, tmp_path):
+    """the (pass, pixel) colour buffer is capped (2 GiB; C4 at 2048x2048 and C5 need 2+ launches per Render_Pass): with the cap
+    forced down to 64 KB a 64x48 frame of 7 units takes 4 launches of 2 + 2 + 2 + 1 passes -- same bits as the oracle.
+    Runs in a fresh process because the cap is read from the environment."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import __graft_entry__ as ge; pkg = ge.load_package(); "
+        "pkg.set_device(0); sc = pkg.Scene(); sc.Init(); rt = pkg.Ray_Tracer(); rt.Threads_Num = 7; rt.seed = 99; "
+        "rt.Init_Render(pkg.PT_MIS); rt.Resize_Viewport(64, 48); hdr = rt.Render_Pass(read_hdr=True); "
+        "np.save(%r, hdr); print(rt.last_stats.kernel_launches, rt.last_stats.rays)" % (root, str(tmp_path / "hdr.npy")))
+    env = dict(os.environ, GCORE_COLBUF_CAP_KB="128")                     # 128 KB / (4096 slots x 16 B) = 2 passes per launch
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    launches, rays = (int(x) for x in r.stdout.split())
+    hdr = np.load(str(tmp_path / "hdr.npy"))
+    acc, orays = oscene.render(ob.make_params(64, 48, ob.PT_MIS, passes=7, seed=99))
+    assert launches > 2 and rays == orays                                 # more than one (wavefront, fold) pair
+    assert np.array_equal(_bits(hdr[..., :3]), _bits(acc))
