@@ -329,3 +329,21 @@ def test_long_renders_go_in_chunks_of_passes(oscene, ob, tmp_path):
     acc, orays = oscene.render(ob.make_params(64, 48, ob.PT_MIS, passes=7, seed=99))
     assert launches > 2 and rays == orays                                 # more than one (wavefront, fold) pair
     assert np.array_equal(_bits(hdr[..., :3]), _bits(acc))
+
+
+@pytest.mark.parametrize("name,rtype,depth,units,w,h", [
+    ("C1", "PT_MIS", 8, 2, 1024, 768),        # the reference's default viewport and integrator, 8 of its 112 spp per pass
+    ("C3", "PT_SHADOW", 1, 4, 1024, 1024),    # BASELINE config C3 in full: direct lighting, 16 spp
+    ("C4", "PT_MIS", 8, 1, 2048, 2048),       # BASELINE config C4 at full resolution, 4 of its 256 spp
+])
+def test_baseline_configs_at_full_resolution_bit_exact(gscene, oscene, pkg, ob, name, rtype, depth, units, w, h):
+    """the BASELINE viewports in full (the multi-threaded oracle renders them in a second or two): every accumulator bit, the ray
+    count and the LDR frame"""
+    rt = pkg.Ray_Tracer()
+    rt.Threads_Num = units; rt.Max_Trace_Depth = depth; rt.seed = 0x5EED0003 if name == "C3" else 0x5EED0004
+    rt.Init_Render(getattr(pkg, rtype)); rt.Resize_Viewport(w, h)
+    hdr = rt.Render_Pass(read_hdr=True)
+    acc, rays = oscene.render(ob.make_params(w, h, getattr(ob, rtype), max_depth=depth, passes=units, seed=rt.seed))
+    assert int(rt.last_stats.rays) == rays
+    assert np.array_equal(_bits(hdr[..., :3]), _bits(acc))
+    assert np.array_equal(rt.screen_buffer, ob.resolve(acc, 4 * units))
