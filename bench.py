@@ -344,6 +344,14 @@ def main():
             cpu_baseline = {"value": r2 / t2 / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                             "sample": "%d of the step's %d units (%d spp) of the %dx%d image%s, %.1f s" % (
                                 n_units, units, n_units * (4 if aa else 1), cw, ch, "" if (cw, ch) == (width, height) else " (half resolution)", t2)}
+        if cpu_baseline is not None and args.workload == "C1":
+            # the reference's own scheme once, to show what its global lock costs: Threads_Num tasks x the full image, one lock per pixel add
+            ob = ge.load_oracle()
+            t0 = time.perf_counter()
+            _acc, r3 = ob.render_task_lock(oracle_scene(args.workload), ob.make_params(width, height, getattr(ob, rtype), aa=aa, max_depth=depth, passes=1, seed=SEED), units)
+            t3 = time.perf_counter() - t0
+            cpu_baseline["reference_tasking"] = {"value": r3 / t3 / 1e6, "unit": "Mrays/s", "tasks": units,
+                                                 "note": "Threads_Num tasks each rendering the full image, one process-wide lock per pixel add (ray_tracer.adb:142-194, integrators.adb:50-52)"}
         line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",

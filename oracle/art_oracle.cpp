@@ -31,6 +31,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <mutex>
 #include <thread>
 #include <vector>
 #include <algorithm>
@@ -1292,6 +1293,50 @@ uint64_t ao_render(const ao_scene* s, const ao_params* p, float* accum3) {
     for (int t = 0; t < T; t++) th.emplace_back(worker, t);
     for (auto& t : th) t.join();
   }
+  uint64_t total = 0; for (uint64_t r : rays) total += r;
+  return total;
+}
+
+// The reference's own parallel scheme, for TIMING ONLY (mode B): `tasks` workers, each renders the WHOLE
+// image for one pass with its own sample indices (task k = DoPass unit k, like Path_Trace_Thread k of ray_tracer.adb:142-194) and adds
+// every pixel into the shared accumulator under one process-wide lock (GNAT.Task_Lock, ray_tracer-integrators.adb:50-52).  The sum per
+// pixel is the same set of terms as ao_render with passes = tasks, added in a scheduling-dependent order.
+uint64_t ao_render_task_lock(const ao_scene* s, const ao_params* p, int tasks, float* accum3) {
+  ensure_bvh(s, p->mesh_mode);
+  if (tasks < 1) tasks = 1;
+  const int W = p->width, H = p->height;
+  static std::mutex task_lock;
+  std::vector<uint64_t> rays(tasks, 0);
+  auto worker = [&](int k) {
+    PathCtx pc; pc.cx.scn = s; pc.cx.mesh_mode = p->mesh_mode; pc.cx.rays = 0;
+    pc.seed = p->seed; pc.max_depth = p->max_depth; pc.render_type = p->render_type;
+    const float3 bg = f3(p->background);
+    for (int y = 0; y < H; y++) {
+      for (int x = 0; x < W; x++) {
+        pc.pixel = (uint32_t)(y * W + x);
+        float3 color;
+        if (p->anti_aliasing) {
+          color = bg;
+          for (int i = 0; i < 4; i++) {
+            Ray r = make_eye_ray(*s, W, H, x, y, i);
+            pc.sample = (uint32_t)(p->first_sample + k * 4 + i);
+            color = color + PathTrace(pc, r, StartSample, p->max_depth);
+          }
+        } else {
+          Ray r = make_eye_ray(*s, W, H, x, y, -1);
+          pc.sample = (uint32_t)(p->first_sample + k);
+          color = PathTrace(pc, r, StartSample, p->max_depth);
+        }
+        float* acc = accum3 + 3 * (size_t)(y * W + x);
+        std::lock_guard<std::mutex> lk(task_lock);                                                      // :50-52
+        acc[0] = color.x + acc[0]; acc[1] = color.y + acc[1]; acc[2] = color.z + acc[2];
+      }
+    }
+    rays[k] = pc.cx.rays;
+  };
+  std::vector<std::thread> th;
+  for (int k = 0; k < tasks; k++) th.emplace_back(worker, k);
+  for (auto& t : th) t.join();
   uint64_t total = 0; for (uint64_t r : rays) total += r;
   return total;
 }

@@ -128,6 +128,9 @@ int  ao_compute_shadow(const ao_scene*, int mesh_mode, const float hit_pos[3], c
 /* integrators.adb:25-71 DoPass x passes; accum3[(y*W+x)*3+c] += ... ; returns rays traced
  * (number of Find_Closest_Hit calls) */
 uint64_t ao_render(const ao_scene*, const ao_params*, float* accum3);
+/* the reference's own scheme, for timing only: `tasks` threads, each one full-image pass, one global lock per pixel add
+ * (ray_tracer.adb:142-194, 264-277; integrators.adb:50-52); same terms as ao_render with passes = tasks, order not deterministic */
+uint64_t ao_render_task_lock(const ao_scene*, const ao_params*, int tasks, float* accum3);
 /* ray_tracer.adb:281-291 + :19-57 ; ldr[y*W+x] = R | G<<8 | B<<16 */
 void ao_resolve(const float* accum3, int npixels, int spp, uint32_t* ldr);
 /* bitmap.adb:31-85 ; returns 0 on success */

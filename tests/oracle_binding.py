@@ -79,6 +79,8 @@ def lib():
         L.ao_compute_shadow.argtypes = [vp, C.c_int, vp, vp]
         L.ao_render.argtypes = [vp, C.POINTER(Params), vp]
         L.ao_render.restype = C.c_uint64
+        L.ao_render_task_lock.argtypes = [vp, C.POINTER(Params), C.c_int, vp]
+        L.ao_render_task_lock.restype = C.c_uint64
         L.ao_resolve.argtypes = [vp, C.c_int, C.c_int, vp]
         L.ao_save_bmp.argtypes = [C.c_char_p, vp, C.c_int, C.c_int]
         L.ao_philox4x32_10.argtypes = [vp, vp, vp]
@@ -180,6 +182,13 @@ class OracleScene:
             accum = np.zeros((params.height, params.width, 3), np.float32)
         rays = self.L.ao_render(self.h, C.byref(params), _p(accum))
         return accum, int(rays)
+
+
+def render_task_lock(scene, params, tasks):
+    """the reference's tasking scheme (T tasks x full image, one global lock): (accum, rays); timing leg only"""
+    accum = np.zeros((params.height, params.width, 3), np.float32)
+    rays = lib().ao_render_task_lock(scene.h, C.byref(params), int(tasks), _p(accum))
+    return accum, int(rays)
 
 
 def resolve(accum, spp):

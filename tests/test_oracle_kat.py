@@ -324,3 +324,14 @@ def test_bmp_writer_bytes(ob, tmp_path, pkg):
     assert struct.unpack("<HH", b1[26:30]) == (1, 24)
     px0 = int(data[0])
     assert tuple(b1[54:57]) == ((px0 >> 16) & 255, (px0 >> 8) & 255, px0 & 255)
+
+
+def test_reference_tasking_scheme_adds_the_same_terms(oscene, ob):
+    """ao_render_task_lock (the reference's T tasks x full image + global lock, a timing leg) sums the same per-pixel terms as the
+    striped renderer with passes = T; only the order of the float additions differs"""
+    w, h, tasks = 48, 36, 5
+    p = ob.make_params(w, h, ob.PT_MIS, passes=tasks, seed=3)
+    a, ra = oscene.render(p)
+    b, rb = ob.render_task_lock(oscene, ob.make_params(w, h, ob.PT_MIS, passes=1, seed=3), tasks)
+    assert ra == rb
+    assert np.allclose(a, b, rtol=2e-6, atol=1e-6)
