@@ -17,7 +17,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.environ.get("GCORE_B200_LIB", os.path.join(_HERE, "libgcore_b200.so"))   # override: tuning experiments only
+LIB_PATH = os.path.join(_HERE, "libgcore_b200.so")      # the one product library; experiment builds are loaded by profiles/tools/bench_variant.py
 DEFAULT_VSGF = os.path.join(ROOT, "data", "pyramid2.vsgf")
 
 # ---- POD layouts of include/gcore.h -------------------------------------------------------------------------------
@@ -492,7 +492,7 @@ class Tiled_Ray_Tracer:
         _ck(self.L.gcore_init_render(C.byref(cfg)))
         if events:
             events[0].record(self.stream)
-        _ck(self.L.gcore_render_units(rt.Threads_Num, None))
+        _ck(self.L.gcore_render_units(1 if rt.g_rend_type in (RT_DEBUG, RT_WHITTED) else rt.Threads_Num, None))
         if events:
             events[1].record(self.stream)                # events[0..1]: the render kernels alone
         npx = rt.width * rt.height
@@ -505,7 +505,8 @@ class Tiled_Ray_Tracer:
             else:
                 allb = self.gather.gather(self.local)
                 if self.rank == 0:
-                    _ck(self.L.gcore_resolve_gathered_device(C.c_void_p(allb.data_ptr()), rt.GetSPP(), hdr_p, C.c_void_p(self.d_ldr.data_ptr())))
+                    spp = 1 if rt.g_rend_type in (RT_DEBUG, RT_WHITTED) else rt.GetSPP()      # the palette is resolved without 1/spp
+                    _ck(self.L.gcore_resolve_gathered_device(C.c_void_p(allb.data_ptr()), spp, hdr_p, C.c_void_p(self.d_ldr.data_ptr())))
             if self.rank == 0 and host_ldr is not None:
                 host_ldr.copy_(self.d_ldr, non_blocking=True)
         if events:

@@ -47,6 +47,7 @@ struct State {
   // render state
   gcore_render_config cfg{GCORE_PT_MIS, 1, 8, 0x5EED0003u, {0.f, 0.f, 0.f}};
   int width = 0, height = 0, spp = 0;
+  bool palette_frame = false;                // the last pass was Debug_Ray_Tracing: resolve without 1/spp (ray_tracer.adb:245-257)
   int rank = 0, world = 1;
   float4* d_accum = nullptr; int nslots = 0;
   unsigned long long* d_rays = nullptr;      // 3 cumulative counters: rays, mesh-bbox queries, bounces
@@ -136,7 +137,7 @@ int alloc_accum() {
   CU(cudaMemsetAsync(s.d_accum, 0, sizeof(float4) * (size_t)s.nslots, s.stream), "memset accum");
   CU(cudaMemsetAsync(s.d_rays, 0, 6 * sizeof(unsigned long long), s.stream), "memset counters");
   s.last_counters[0] = s.last_counters[1] = s.last_counters[2] = s.last_counters[3] = 0;
-  s.spp = 0;
+  s.spp = 0; s.palette_frame = false;
   return 0;
 }
 
@@ -314,10 +315,11 @@ int render_units_locked(int units, gcore_render_stats* stats) {
   if (s.cfg.render_type == GCORE_RT_DEBUG || s.cfg.render_type == GCORE_RT_WHITTED) {
     CU(gcore_dev::launch_debug(s.hs.mesh_kind, a, s.stream), "debug_kernel");           // Debug_Ray_Tracing overwrites the buffer, spp stays
     launches = 1; samples = pixels;
-    if (s.spp == 0) s.spp = 1;
+    s.palette_frame = true;                                              // g_spp is not touched (ray_tracer.adb:245-260)
   } else if (units > 0) {
     const int per = s.cfg.anti_aliasing ? 4 : 1;
     // the colour buffer holds one float4 per (pass, pixel): long renders go in chunks of passes
+    s.palette_frame = false;
     size_t cap_bytes = GC_COLBUF_CAP_BYTES;
     if (const char* e = getenv("GCORE_COLBUF_CAP_KB")) { long v = atol(e); if (v > 0) cap_bytes = (size_t)v << 10; }   // tests: force the chunked path on small frames
     size_t chunk = cap_bytes / (sizeof(float4) * (size_t)s.nslots);
@@ -350,6 +352,12 @@ int render_units_locked(int units, gcore_render_stats* stats) {
   return 0;
 }
 
+// normC = 1 / g_spp for path-traced frames; the debug palette is resolved as it is (ray_tracer.adb:245-257 vs :281-291)
+int resolve_spp() {
+  State& s = S();
+  return (s.palette_frame || s.spp <= 0) ? 1 : s.spp;
+}
+
 int read_frame_locked(float* hdr4, uint32_t* ldr, int* launches) {
   State& s = S();
   if (!s.d_accum) return fail(GCORE_E_STATE, "no viewport");
@@ -357,7 +365,7 @@ int read_frame_locked(float* hdr4, uint32_t* ldr, int* launches) {
   if (!hdr4 && !ldr) return 0;
   if (int rc = ensure_out_buffers(hdr4 != nullptr, ldr != nullptr)) return rc;
   RenderArgs a = make_args();
-  CU(gcore_dev::launch_resolve(a, s.spp > 0 ? s.spp : 1, hdr4 ? s.d_hdr : nullptr, ldr ? s.d_ldr : nullptr, s.stream), "resolve_kernel");
+  CU(gcore_dev::launch_resolve(a, resolve_spp(), hdr4 ? s.d_hdr : nullptr, ldr ? s.d_ldr : nullptr, s.stream), "resolve_kernel");
   if (launches) *launches += 1;
   size_t px = (size_t)s.width * s.height;
   if (hdr4) CU(cudaMemcpyAsync(hdr4, s.d_hdr, sizeof(float4) * px, cudaMemcpyDeviceToHost, s.stream), "memcpy hdr");
@@ -854,7 +862,7 @@ int gcore_render(const gcore_render_config* cfg, int width, int height, int unit
     CU(cudaMemsetAsync(s.d_accum, 0, sizeof(float4) * (size_t)s.nslots, s.stream), "memset accum");
     CU(cudaMemsetAsync(s.d_rays, 0, 6 * sizeof(unsigned long long), s.stream), "memset counters");
     s.last_counters[0] = s.last_counters[1] = s.last_counters[2] = s.last_counters[3] = 0;
-    s.spp = 0;
+    s.spp = 0; s.palette_frame = false;
   }
   gcore_render_stats st; memset(&st, 0, sizeof(st));
   if ((rc = render_units_locked(units, &st))) return rc;
@@ -879,7 +887,7 @@ int gcore_load_frame(const float* hdr4, int spp) {
   RenderArgs a = make_args();
   CU(gcore_dev::launch_load_accum(a, s.d_hdr, s.stream), "load_accum_kernel");
   CU(cudaStreamSynchronize(s.stream), "load_frame sync");
-  s.spp = spp;
+  s.spp = spp; s.palette_frame = false;
   return 0;
 }
 
@@ -920,7 +928,7 @@ int gcore_resolve_device(void* d_hdr4, void* d_ldr) {
   if (!s.d_accum) return fail(GCORE_E_STATE, "no viewport");
   if (s.world != 1) return fail(GCORE_E_STATE, "gcore_resolve_device needs world == 1");
   RenderArgs a = make_args();
-  CU(gcore_dev::launch_resolve(a, s.spp > 0 ? s.spp : 1, (float4*)d_hdr4, (uint32_t*)d_ldr, s.stream), "resolve_kernel");
+  CU(gcore_dev::launch_resolve(a, resolve_spp(), (float4*)d_hdr4, (uint32_t*)d_ldr, s.stream), "resolve_kernel");
   return 0;
 }
 
