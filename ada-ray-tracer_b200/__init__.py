@@ -64,6 +64,8 @@ EXPORTS = [
     "gcore_resize_viewport", "gcore_render_units", "gcore_get_counters", "gcore_get_spp", "gcore_read_frame", "gcore_render",
     "gcore_primary_hits", "gcore_accum_device_ptr", "gcore_resolve_device", "gcore_resolve_gathered_device",
     "gcore_stream", "gcore_synchronize", "gcore_last_error", "gcore_bvh_info", "gcore_kernel_regs", "gcore_bvh_bench", "gcore_load_frame", "gcore_set_stats_level", "gcore_get_bvh_counters",
+    "gcore_set_gpu_count", "gcore_get_gpu_count", "gcore_device_kernel_ms", "gcore_set_seam_two_sided", "gcore_set_mesh_material",
+    "gcore_set_mesh_normals_3f", "gcore_use_committed_scene", "gcore_get_committed_scene", "gcore_bvh_occluded_batch",
 ]
 
 _lib = None
@@ -117,6 +119,14 @@ def lib():
     L.gcore_bvh_info.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(f32)]
     L.gcore_kernel_regs.argtypes = [i32]
     L.gcore_bvh_bench.argtypes = [i32, vp, f32, f32, i32, i32, C.POINTER(f32), vp]
+    L.gcore_set_gpu_count.argtypes = [i32]
+    L.gcore_device_kernel_ms.argtypes = [vp, i32]
+    L.gcore_set_seam_two_sided.argtypes = [i32]
+    L.gcore_set_mesh_material.argtypes = [i32, i32]
+    L.gcore_set_mesh_normals_3f.argtypes = [i32, vp, i32]
+    L.gcore_use_committed_scene.argtypes = [i32]
+    L.gcore_get_committed_scene.argtypes = [vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
+    L.gcore_bvh_occluded_batch.argtypes = [i32, vp, f32, f32, vp]
     _lib = L
     return L
 
@@ -255,6 +265,35 @@ class GeometryCore:
         found = np.zeros(len(rays), np.int32)
         _ck(self.L.gcore_bvh_closest_hit_batch(len(rays), _p(rays), t_near, t_far, _p(hits), _p(found)))
         return found, hits
+
+    def set_mesh_material(self, mesh_id, mat_id):
+        _ck(self.L.gcore_set_mesh_material(mesh_id, mat_id))
+
+    def set_mesh_normals_3f(self, mesh_id, normals):
+        n = np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+        _ck(self.L.gcore_set_mesh_normals_3f(mesh_id, _p(n), len(n)))
+
+    def use_committed_scene(self, enable=True):
+        """the integrators trace the committed scene (meshes + instances + per-mesh materials) instead of the Scene.set_mesh mesh"""
+        _ck(self.L.gcore_use_committed_scene(1 if enable else 0))
+
+    def set_two_sided(self, enable):
+        _ck(self.L.gcore_set_seam_two_sided(1 if enable else 0))
+
+    def committed_scene(self):
+        """-> (pos[nv,3], tris[nt,3], normals[nt,3,3], mats[nt]) of the flattened world-space scene the devices hold"""
+        nv, nt = C.c_int(), C.c_int()
+        _ck(self.L.gcore_get_committed_scene(None, None, None, None, C.byref(nv), C.byref(nt)))
+        pos = np.zeros((nv.value, 3), np.float32); tris = np.zeros((nt.value, 3), np.int32)
+        n9 = np.zeros((nt.value, 3, 3), np.float32); mats = np.zeros(nt.value, np.int32)
+        _ck(self.L.gcore_get_committed_scene(_p(pos), _p(tris), _p(n9), _p(mats), C.byref(nv), C.byref(nt)))
+        return pos, tris, n9, mats
+
+    def occluded_batch(self, rays, t_near=0.0, t_far=100000.0):
+        rays = np.ascontiguousarray(rays, ray_dt)
+        occ = np.zeros(len(rays), np.int32)
+        _ck(self.L.gcore_bvh_occluded_batch(len(rays), _p(rays), t_near, t_far, _p(occ)))
+        return occ
 
     def bvh_info(self):
         a, b, c, ms = C.c_int64(), C.c_int64(), C.c_int64(), C.c_float()
@@ -406,6 +445,22 @@ def set_device(device):
 
 def set_partition(rank, world):
     _ck(lib().gcore_set_partition(int(rank), int(world)))
+
+
+def set_gpu_count(n):
+    """multi-GPU inside this one process: devices [device, device + n) split the tiles, gcore_read_frame gathers with NCCL"""
+    _ck(lib().gcore_set_gpu_count(int(n)))
+
+
+def get_gpu_count():
+    return lib().gcore_get_gpu_count()
+
+
+def device_kernel_ms(n=None):
+    n = n or get_gpu_count()
+    out = np.zeros(n, np.float32)
+    _ck(lib().gcore_device_kernel_ms(_p(out), n))
+    return out
 
 
 def accum_device_ptr():

@@ -188,7 +188,8 @@ ART_D void find_closest_hit(f3 o, f3 d, bool want_record, DHit& h, unsigned int&
     h.prim_type = PRIM_QUAD; h.prim_index = 0; h.matId = 0; h.mat = 4;
     h.normal = mk3(0.0f, -1.0f, 0.0f);
   } else {
-    h.prim_type = PRIM_TRIANGLE; h.prim_index = tri_id; h.matId = 2; h.mat = -1;
+    h.prim_type = PRIM_TRIANGLE; h.prim_index = tri_id; h.mat = -1;
+    h.matId = (MESHK == MESHK_BVH && g_scn.bvh.tri_mat != nullptr) ? __ldg(g_scn.bvh.tri_mat + tri_id) : 2;   // geometry.adb:312 / gcore_set_mesh_material
     const float* n9 = (MESHK == MESHK_CONST) ? g_scn.triN[tri_id] : (g_scn.bvh.tri_normals + 9 * (size_t)tri_id);
     float w = 1.0f - tri_u - tri_v;                                            // geometry.adb:301
     h.normal = mk3(w * n9[0] + tri_v * n9[3] + tri_u * n9[6],

@@ -22,6 +22,7 @@ struct BvhView {                   // packed LBVH (see lbvh.cuh); all pointers a
   const float4* nodes;             // 4 x float4 per internal node
   const float4* tris;              // 3 x float4 per sorted triangle: (A, prim id), (e1, 0), (e2, 0)
   const float*  tri_normals;       // 9 floats per ORIGINAL triangle id: nA, nB, nC
+  const int*    tri_mat;           // material id per ORIGINAL triangle id, or null: matId 2 (IntersectMeshBF, geometry.adb:312)
   int           ntris;
   int           root;              // root node index, or ~0 for a single-triangle tree
 };

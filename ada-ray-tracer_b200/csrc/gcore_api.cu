@@ -1,14 +1,23 @@
 // gcore_api.cu -- the C ABI of libgcore_b200.so (include/gcore.h): process-wide render-core state, scene marshalling,
 // kernel launches.  Replaces cpp/embree_connect.cpp (legacy seam) and the state of ray_tracer.adb / scene.adb that the
 // hot path needs on the device.  No CPU compute path exists here: every query / render call launches CUDA kernels.
+//
+// One host process drives 1..8 GPUs (the reference host is ONE Ada process, ray_tracer.adb:264-277): the scene description
+// lives once on the host, every device holds its own copy (constant block + LBVHs, rebuilt deterministically per device),
+// renders the tiles t with t % G == d into its own slot-major accumulator, and the accumulators meet on device 0 through
+// one grouped ncclSend/ncclRecv per frame read.
 #include "gcore_internal.h"
 #include "art_types.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -18,45 +27,78 @@ using gcore_dev::WaveBuffers;
 
 namespace {
 
-struct LegacyMesh { std::vector<float> verts; std::vector<int> idx; };
+#define GC_MAX_GPUS 8
+
+struct LegacyMesh { std::vector<float> verts; std::vector<int> idx; std::vector<float> normals; int mat = 2; };
 struct LegacyInstance { int mesh; float m[12]; };
+
+// the committed legacy scene, flattened to world space on the host (every device builds its LBVH from this)
+struct FlatScene {
+  std::vector<float> verts; std::vector<int> tris;
+  std::vector<int> prim, inst, mat;          // flattened triangle -> triangle index inside its mesh / instance id / material id
+  std::vector<float> n9;                     // flattened triangle -> nA, nB, nC (vertex normals under the instance's 3x3, or the geometric normal)
+  float tight_min[3] = {0, 0, 0}, tight_max[3] = {0, 0, 0};
+  int version = 0;
+};
+
+// NCCL entry points, bound at run time: a host process that already carries an NCCL (PyTorch bundles its own libnccl.so.2)
+// must not get a second one through our link line
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+struct Device {
+  int  ordinal = 0;
+  bool ready = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  bool scene_dirty = true;
+  int  mesh_version = -1, legacy_version = -1;      // what mesh_bvh / legacy_bvh were built from
+  LbvhBuffers mesh_bvh, legacy_bvh;
+  float4* d_accum = nullptr;                        // device 0: the first nslots of d_gather
+  float4* d_gather = nullptr;                       // device 0 only: gpu_count accumulators back to back
+  int nslots = 0;
+  unsigned long long* d_rays = nullptr;             // 6 cumulative counters (RenderArgs::counters)
+  unsigned long long last_counters[6] = {0, 0, 0, 0, 0, 0};
+  float last_kernel_ms = 0.f;
+  float4* d_hdr = nullptr; uint32_t* d_ldr = nullptr; size_t out_pixels = 0;
+  gcore_ray* d_batch_rays = nullptr; gcore_HitCpp* d_batch_hits = nullptr; int* d_batch_found = nullptr; size_t batch_cap = 0;
+  WaveBuffers wave;
+  int sm_count = 0;
+};
 
 struct State {
   std::recursive_mutex mu;
-  int  device = 0;
-  bool dev_ready = false;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  int  base_device = 0, gpu_count = 1;
+  Device dev[GC_MAX_GPUS];
+  NcclApi nccl; ncclComm_t comms[GC_MAX_GPUS]; bool nccl_ready = false;
 
   // legacy seam
   bool legacy_alive = false;
   std::vector<LegacyMesh> meshes;
   std::vector<LegacyInstance> instances;
-  LbvhBuffers legacy_bvh;
-  int* d_legacy_prim = nullptr;          // flattened triangle -> triangle index inside its mesh
-  int* d_legacy_inst = nullptr;          // flattened triangle -> instance id
-  std::vector<int> h_legacy_prim, h_legacy_inst;
-  float* d_legacy_verts = nullptr; int* d_legacy_tris = nullptr;
+  FlatScene flat;
+  bool use_committed = false;                // render source: false = gcore_set_mesh mesh, true = the committed legacy scene
+  int  seam_two_sided = 0;
 
   // analytic scene (host mirror of the __constant__ block)
   art::DeviceScene hs;
-  bool scene_dirty = true;
   std::vector<float> mesh_pos, mesh_nrm; std::vector<int> mesh_tris; float mesh_bbox[6] = {0, 0, 0, 0, 0, 0};
-  LbvhBuffers mesh_bvh;
+  int mesh_version = 0;
 
   // render state
   gcore_render_config cfg{GCORE_PT_MIS, 1, 8, 0x5EED0003u, {0.f, 0.f, 0.f}};
   int width = 0, height = 0, spp = 0;
   bool palette_frame = false;                // the last pass was Debug_Ray_Tracing: resolve without 1/spp (ray_tracer.adb:245-257)
-  int rank = 0, world = 1;
-  float4* d_accum = nullptr; int nslots = 0;
-  unsigned long long* d_rays = nullptr;      // 3 cumulative counters: rays, mesh-bbox queries, bounces
-  unsigned long long last_counters[4] = {0, 0, 0, 0};
-  float4* d_hdr = nullptr; uint32_t* d_ldr = nullptr; size_t out_pixels = 0;
-  gcore_ray* d_batch_rays = nullptr; gcore_HitCpp* d_batch_hits = nullptr; int* d_batch_found = nullptr; size_t batch_cap = 0;
-  WaveBuffers wave;                          // work buffers of the wavefront render kernel
+  int rank = 0, world = 1;                   // multi-PROCESS partition (one device per process); exclusive with gpu_count > 1
   int stats_level = 1;
-  int sm_count = 0;
 
   int  err_code = 0;
   std::string err_text;
@@ -75,20 +117,37 @@ int fail_cuda(cudaError_t e, const char* where) {
 }
 #define CU(x, where) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail_cuda(e_, where); } while (0)
 
-int ensure_device() {
+// nothing throws across the ABI (include/gcore.h): every extern "C" body that can allocate runs inside one of these
+#define GC_TRY try {
+#define GC_CATCH_INT } catch (const std::bad_alloc&) { return fail(GCORE_E_LIMIT, "out of host memory"); } \
+                       catch (const std::exception& e_) { return fail(GCORE_E_STATE, std::string("internal error: ") + e_.what()); } \
+                       catch (...) { return fail(GCORE_E_STATE, "internal error"); }
+#define GC_CATCH_VOID } catch (const std::bad_alloc&) { fail(GCORE_E_LIMIT, "out of host memory"); } \
+                        catch (const std::exception& e_) { fail(GCORE_E_STATE, std::string("internal error: ") + e_.what()); } \
+                        catch (...) { fail(GCORE_E_STATE, "internal error"); }
+
+inline int world_eff() { State& s = S(); return s.world * s.gpu_count; }
+inline int rank_eff(int d) { State& s = S(); return s.rank * s.gpu_count + d; }
+
+int ensure_device(int d) {
   State& s = S();
-  if (s.dev_ready) return 0;
+  Device& dv = s.dev[d];
+  if (dv.ready) { CU(cudaSetDevice(dv.ordinal), "cudaSetDevice"); return 0; }
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(GCORE_E_CUDA, "no CUDA device available (libgcore_b200 has no CPU fallback)"); }
-  if (s.device >= n) return fail(GCORE_E_ARG, "device index out of range");
-  CU(cudaSetDevice(s.device), "cudaSetDevice");
-  CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
-  CU(cudaEventCreate(&s.ev0), "cudaEventCreate"); CU(cudaEventCreate(&s.ev1), "cudaEventCreate"); CU(cudaEventCreate(&s.ev2), "cudaEventCreate");
-  CU(cudaMalloc(&s.d_rays, 6 * sizeof(unsigned long long)), "cudaMalloc");
-  CU(cudaMemset(s.d_rays, 0, 6 * sizeof(unsigned long long)), "cudaMemset");
-  s.dev_ready = true;
-  s.scene_dirty = true;
+  dv.ordinal = s.base_device + d;
+  if (dv.ordinal >= n) return fail(GCORE_E_ARG, "device index out of range");
+  CU(cudaSetDevice(dv.ordinal), "cudaSetDevice");
+  CU(cudaStreamCreateWithFlags(&dv.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  CU(cudaEventCreate(&dv.ev0), "cudaEventCreate"); CU(cudaEventCreate(&dv.ev1), "cudaEventCreate"); CU(cudaEventCreate(&dv.ev2), "cudaEventCreate");
+  CU(cudaMalloc(&dv.d_rays, 6 * sizeof(unsigned long long)), "cudaMalloc");
+  CU(cudaMemset(dv.d_rays, 0, 6 * sizeof(unsigned long long)), "cudaMemset");
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dv.ordinal), "cudaGetDeviceProperties");
+  dv.sm_count = prop.multiProcessorCount;
+  dv.ready = true;
+  dv.scene_dirty = true;
   return 0;
 }
 
@@ -100,97 +159,187 @@ void init_host_scene(art::DeviceScene& hs) {
 
 struct Init { Init() { init_host_scene(S().hs); } } g_init;
 
-int sync_scene() {
-  State& s = S();
-  if (int rc = ensure_device()) return rc;
-  if (s.scene_dirty) {
-    s.hs.bvh.nodes = s.mesh_bvh.nodes; s.hs.bvh.tris = s.mesh_bvh.tris; s.hs.bvh.tri_normals = s.mesh_bvh.tri_normals;
-    s.hs.bvh.ntris = s.mesh_bvh.ntris; s.hs.bvh.root = s.mesh_bvh.root;
-    s.hs.bvh_legacy.nodes = s.legacy_bvh.nodes; s.hs.bvh_legacy.tris = s.legacy_bvh.tris; s.hs.bvh_legacy.tri_normals = nullptr;
-    s.hs.bvh_legacy.ntris = s.legacy_bvh.ntris; s.hs.bvh_legacy.root = s.legacy_bvh.root;
-    CU(gcore_dev::upload_scene(&s.hs, s.stream), "upload_scene");
-    CU(cudaStreamSynchronize(s.stream), "upload_scene sync");     // hs may change right after we return
-    s.scene_dirty = false;
+void mark_scene_dirty() { State& s = S(); for (int d = 0; d < GC_MAX_GPUS; d++) s.dev[d].scene_dirty = true; }
+
+// ---- per-device copies of the two triangle scenes: built from the host data, lazily where needed, so that a device that
+// joins later (gcore_set_gpu_count) or a scene that changes picks the right version up at its next use
+int build_mesh_bvh(int d) {
+  State& s = S(); Device& dv = s.dev[d];
+  gcore_dev::lbvh_free(&dv.mesh_bvh);
+  dv.mesh_version = s.mesh_version;
+  const int ntris = (int)s.mesh_tris.size() / 3, nverts = (int)s.mesh_pos.size() / 3;
+  if (ntris <= GC_MAX_BF_TRIS) return 0;                         // lives in the constant block
+  auto N = [&](int v, int k) { return s.mesh_nrm[3 * (size_t)v + k]; };
+  std::vector<float> n9(9 * (size_t)ntris);
+  for (int t = 0; t < ntris; t++)
+    for (int c = 0; c < 3; c++) for (int k = 0; k < 3; k++) n9[9 * (size_t)t + 3 * c + k] = N(s.mesh_tris[3 * (size_t)t + c], k);
+  float *d_v = nullptr, *d_n = nullptr; int* d_t = nullptr;
+  auto cleanup = [&]() { cudaFree(d_v); cudaFree(d_n); cudaFree(d_t); };
+  cudaError_t e;
+  if ((e = cudaMalloc(&d_v, s.mesh_pos.size() * 4)) != cudaSuccess || (e = cudaMalloc(&d_t, s.mesh_tris.size() * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&d_n, n9.size() * 4)) != cudaSuccess) { cleanup(); return fail_cuda(e, "cudaMalloc mesh"); }
+  cudaMemcpyAsync(d_v, s.mesh_pos.data(), s.mesh_pos.size() * 4, cudaMemcpyHostToDevice, dv.stream);
+  cudaMemcpyAsync(d_t, s.mesh_tris.data(), s.mesh_tris.size() * 4, cudaMemcpyHostToDevice, dv.stream);
+  cudaMemcpyAsync(d_n, n9.data(), n9.size() * 4, cudaMemcpyHostToDevice, dv.stream);
+  e = gcore_dev::lbvh_build(d_v, nverts, d_t, ntris, d_n, nullptr, &dv.mesh_bvh, dv.stream);
+  cudaStreamSynchronize(dv.stream);
+  cleanup();
+  if (e != cudaSuccess) { gcore_dev::lbvh_free(&dv.mesh_bvh); return fail_cuda(e, "lbvh_build"); }
+  return 0;
+}
+
+int build_legacy_bvh(int d) {
+  State& s = S(); Device& dv = s.dev[d];
+  gcore_dev::lbvh_free(&dv.legacy_bvh);
+  dv.legacy_version = s.flat.version;
+  const FlatScene& f = s.flat;
+  const int ntris = (int)f.tris.size() / 3;
+  if (ntris == 0) return 0;
+  float *d_v = nullptr, *d_n = nullptr; int *d_t = nullptr, *d_m = nullptr;
+  auto cleanup = [&]() { cudaFree(d_v); cudaFree(d_n); cudaFree(d_t); cudaFree(d_m); };
+  cudaError_t e;
+  if ((e = cudaMalloc(&d_v, f.verts.size() * 4)) != cudaSuccess || (e = cudaMalloc(&d_t, f.tris.size() * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&d_n, f.n9.size() * 4)) != cudaSuccess || (e = cudaMalloc(&d_m, f.mat.size() * 4)) != cudaSuccess) { cleanup(); return fail_cuda(e, "cudaMalloc legacy scene"); }
+  cudaMemcpyAsync(d_v, f.verts.data(), f.verts.size() * 4, cudaMemcpyHostToDevice, dv.stream);
+  cudaMemcpyAsync(d_t, f.tris.data(), f.tris.size() * 4, cudaMemcpyHostToDevice, dv.stream);
+  cudaMemcpyAsync(d_n, f.n9.data(), f.n9.size() * 4, cudaMemcpyHostToDevice, dv.stream);
+  cudaMemcpyAsync(d_m, f.mat.data(), f.mat.size() * 4, cudaMemcpyHostToDevice, dv.stream);
+  e = gcore_dev::lbvh_build(d_v, (int)f.verts.size() / 3, d_t, ntris, d_n, d_m, &dv.legacy_bvh, dv.stream);
+  cudaStreamSynchronize(dv.stream);
+  cleanup();
+  if (e != cudaSuccess) { gcore_dev::lbvh_free(&dv.legacy_bvh); return fail_cuda(e, "lbvh_build (legacy scene)"); }
+  return 0;
+}
+
+void fill_view(art::BvhView& v, const LbvhBuffers& b) {
+  v.nodes = b.nodes; v.tris = b.tris; v.tri_normals = b.tri_normals; v.tri_mat = b.tri_mat; v.ntris = b.ntris; v.root = b.root;
+}
+
+// make device d see the current scene: LBVHs of the right version + the constant block
+int sync_scene(int d) {
+  State& s = S(); Device& dv = s.dev[d];
+  if (int rc = ensure_device(d)) return rc;
+  if (dv.mesh_version != s.mesh_version) { if (int rc = build_mesh_bvh(d)) return rc; dv.scene_dirty = true; }
+  if (dv.legacy_version != s.flat.version) { if (int rc = build_legacy_bvh(d)) return rc; dv.scene_dirty = true; }
+  if (dv.scene_dirty) {
+    art::DeviceScene hs = s.hs;
+    fill_view(hs.bvh_legacy, dv.legacy_bvh);
+    if (s.use_committed) {                                       // the integrators trace the committed legacy scene
+      fill_view(hs.bvh, dv.legacy_bvh);
+      hs.ntris_bf = 0; hs.pair_group = 0; hs.mesh_mode = art::MESH_NEAREST;
+      hs.mesh_kind = dv.legacy_bvh.ntris > 0 ? 2 : 0;
+      for (int k = 0; k < 3; k++) { hs.mesh_tight_min[k] = s.flat.tight_min[k]; hs.mesh_tight_max[k] = s.flat.tight_max[k]; }
+    } else {
+      fill_view(hs.bvh, dv.mesh_bvh);
+    }
+    CU(gcore_dev::upload_scene(&hs, dv.stream), "upload_scene");
+    CU(cudaStreamSynchronize(dv.stream), "upload_scene sync");   // `hs` is a stack copy
+    dv.scene_dirty = false;
   }
   return 0;
 }
 
-void free_accum() {
+int active_mesh_kind() {                                         // which render kernel family: 0/1 constant-memory mesh, 2 LBVH
   State& s = S();
-  if (s.d_accum) { cudaFree(s.d_accum); s.d_accum = nullptr; }
-  s.nslots = 0;
+  if (s.use_committed) return s.flat.tris.empty() ? 0 : 2;
+  return s.hs.mesh_kind;
+}
+
+void free_accum(int d) {
+  Device& dv = S().dev[d];
+  if (dv.ready) {
+    cudaSetDevice(dv.ordinal);
+    if (dv.d_gather) cudaFree(dv.d_gather);
+    else if (dv.d_accum) cudaFree(dv.d_accum);
+  }
+  dv.d_accum = dv.d_gather = nullptr;
+  dv.nslots = 0;
 }
 
 int alloc_accum() {
   State& s = S();
-  if (int rc = ensure_device()) return rc;
-  if (s.width <= 0 || s.height <= 0) { free_accum(); return 0; }
-  int tiles_x = (s.width + GC_TILE - 1) / GC_TILE, tiles_y = (s.height + GC_TILE - 1) / GC_TILE;
-  int ntiles = tiles_x * tiles_y;
-  int local_tiles = (ntiles + s.world - 1) / s.world;           // equal share per rank (padded) so gathers are uniform
+  const int tiles_x = (s.width + GC_TILE - 1) / GC_TILE, tiles_y = (s.height + GC_TILE - 1) / GC_TILE;
+  const int ntiles = tiles_x * tiles_y;
+  const int we = world_eff();
+  const int local_tiles = (ntiles + we - 1) / we;              // equal share per rank (padded) so gathers are uniform
   const int nslots = local_tiles * GC_TILE * GC_TILE;
-  if (!s.d_accum || nslots != s.nslots) {                       // same size: keep the allocation, just clear it
-    free_accum();
-    CU(cudaMalloc(&s.d_accum, sizeof(float4) * (size_t)nslots), "cudaMalloc accum");
-    s.nslots = nslots;
+  for (int d = 0; d < s.gpu_count; d++) {
+    if (int rc = ensure_device(d)) return rc;
+    Device& dv = s.dev[d];
+    if (s.width <= 0 || s.height <= 0) { free_accum(d); continue; }
+    if (!dv.d_accum || nslots != dv.nslots) {                   // same size: keep the allocation, just clear it
+      free_accum(d);
+      if (d == 0) {                                             // device 0 receives the other devices' accumulators behind its own
+        CU(cudaMalloc(&dv.d_gather, sizeof(float4) * (size_t)nslots * s.gpu_count), "cudaMalloc accum");
+        dv.d_accum = dv.d_gather;
+      } else CU(cudaMalloc(&dv.d_accum, sizeof(float4) * (size_t)nslots), "cudaMalloc accum");
+      dv.nslots = nslots;
+    }
+    CU(cudaMemsetAsync(dv.d_accum, 0, sizeof(float4) * (size_t)dv.nslots, dv.stream), "memset accum");
+    CU(cudaMemsetAsync(dv.d_rays, 0, 6 * sizeof(unsigned long long), dv.stream), "memset counters");
+    memset(dv.last_counters, 0, sizeof(dv.last_counters));
   }
-  CU(cudaMemsetAsync(s.d_accum, 0, sizeof(float4) * (size_t)s.nslots, s.stream), "memset accum");
-  CU(cudaMemsetAsync(s.d_rays, 0, 6 * sizeof(unsigned long long), s.stream), "memset counters");
-  s.last_counters[0] = s.last_counters[1] = s.last_counters[2] = s.last_counters[3] = 0;
   s.spp = 0; s.palette_frame = false;
   return 0;
 }
 
-// work buffers of render_wave_kernel: per-slot recursion stacks (fixed size) and the (pass, pixel) colour buffer
-#define GC_COLBUF_CAP_BYTES ((size_t)2 << 30)
-int ensure_wave_buffers(size_t items) {
-  State& s = S();
-  if (!s.wave.sm_count) {
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, s.device), "cudaGetDeviceProperties");
-    s.sm_count = prop.multiProcessorCount;
-    s.wave.sm_count = s.sm_count;
-    const size_t total_slots = (size_t)gcore_dev::wave_total_slots(s.sm_count);
-    CU(cudaMalloc(&s.wave.stackA, sizeof(float4) * total_slots * gcore_dev::wave_max_depth()), "cudaMalloc stackA");
-    CU(cudaMalloc(&s.wave.stackB, sizeof(float2) * total_slots * gcore_dev::wave_max_depth()), "cudaMalloc stackB");
-    CU(cudaMalloc(&s.wave.next_item, sizeof(unsigned int)), "cudaMalloc next_item");
+// work buffers of render_wave_kernel: per-slot recursion stacks (fixed size) and the (pass, pixel) colour buffer.
+// The colour buffer is sized so that every BASELINE config is one launch (C4: 2048^2 x 64 units x 16 B = 4.3 GB of the
+// 180 GB of HBM3e); longer renders go in chunks of passes.
+#define GC_COLBUF_CAP_BYTES ((size_t)8 << 30)
+int ensure_wave_buffers(int d, size_t items, bool lbvh) {
+  Device& dv = S().dev[d];
+  if (!dv.wave.sm_count) {
+    const size_t total_slots = (size_t)gcore_dev::wave_total_slots(dv.sm_count);
+    float4* a = nullptr; float2* b = nullptr; unsigned int* c = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&a, sizeof(float4) * total_slots * gcore_dev::wave_max_depth())) != cudaSuccess ||
+        (e = cudaMalloc(&b, sizeof(float2) * total_slots * gcore_dev::wave_max_depth())) != cudaSuccess ||
+        (e = cudaMalloc(&c, sizeof(unsigned int))) != cudaSuccess) {
+      cudaFree(a); cudaFree(b); cudaFree(c);
+      return fail_cuda(e, "cudaMalloc wave stacks");
+    }
+    dv.wave.stackA = a; dv.wave.stackB = b; dv.wave.next_item = c;
+    dv.wave.sm_count = dv.sm_count;                             // only now: a failed allocation leaves the buffers unset
   }
-  if (items > s.wave.colbuf_items) {
-    if (s.wave.colbuf) { cudaFree(s.wave.colbuf); s.wave.colbuf = nullptr; s.wave.colbuf_items = 0; }
-    CU(cudaMalloc(&s.wave.colbuf, sizeof(float4) * items), "cudaMalloc colbuf");
-    s.wave.colbuf_items = items;
+  if (lbvh && !dv.wave.tstack_ovf)
+    CU(cudaMalloc(&dv.wave.tstack_ovf, sizeof(int) * (size_t)gcore_dev::wave_total_slots(dv.sm_count) * gcore_dev::wave_stack_overflow_entries()), "cudaMalloc traversal stacks");
+  if (items > dv.wave.colbuf_items) {
+    if (dv.wave.colbuf) { cudaFree(dv.wave.colbuf); dv.wave.colbuf = nullptr; dv.wave.colbuf_items = 0; }
+    CU(cudaMalloc(&dv.wave.colbuf, sizeof(float4) * items), "cudaMalloc colbuf");
+    dv.wave.colbuf_items = items;
   }
   return 0;
 }
 
-RenderArgs make_args() {
-  State& s = S();
+RenderArgs make_args(int d) {
+  State& s = S(); Device& dv = s.dev[d];
   RenderArgs a;
   memset(&a, 0, sizeof(a));
   a.width = s.width; a.height = s.height;
   a.tiles_x = (s.width + GC_TILE - 1) / GC_TILE;
   a.ntiles = a.tiles_x * ((s.height + GC_TILE - 1) / GC_TILE);
-  a.rank = s.rank; a.world = s.world; a.nslots = s.nslots;
+  a.rank = rank_eff(d); a.world = world_eff(); a.nslots = dv.nslots;
   a.anti_aliasing = s.cfg.anti_aliasing ? 1 : 0; a.max_depth = s.cfg.max_depth; a.passes = 0;
   a.seed = s.cfg.seed; a.first_sample = s.spp;
   a.bg[0] = s.cfg.background[0]; a.bg[1] = s.cfg.background[1]; a.bg[2] = s.cfg.background[2];
   const float fov = 1.57079632679489661923f;                      // Pi / 2.0            (ray_tracer.adb:63)
   a.zdir = -(float)s.width / tanf(fov / 2.0f);                     // safe_tan(fov / 2.0) (ray_tracer.adb:67, vector_math.adb:14-22)
   a.half_w = (float)s.width / 2.0f; a.half_h = (float)s.height / 2.0f;
-  a.accum = s.d_accum; a.counters = s.d_rays;
+  a.accum = dv.d_accum; a.counters = dv.d_rays;
   return a;
 }
 
-int ensure_out_buffers(bool hdr, bool ldr) {
-  State& s = S();
+int ensure_out_buffers(bool hdr, bool ldr) {                     // device 0
+  State& s = S(); Device& dv = s.dev[0];
   size_t px = (size_t)s.width * s.height;
-  if (px != s.out_pixels) {
-    if (s.d_hdr) { cudaFree(s.d_hdr); s.d_hdr = nullptr; }
-    if (s.d_ldr) { cudaFree(s.d_ldr); s.d_ldr = nullptr; }
-    s.out_pixels = px;
+  if (px != dv.out_pixels) {
+    if (dv.d_hdr) { cudaFree(dv.d_hdr); dv.d_hdr = nullptr; }
+    if (dv.d_ldr) { cudaFree(dv.d_ldr); dv.d_ldr = nullptr; }
+    dv.out_pixels = px;
   }
-  if (hdr && !s.d_hdr) CU(cudaMalloc(&s.d_hdr, sizeof(float4) * px), "cudaMalloc hdr");
-  if (ldr && !s.d_ldr) CU(cudaMalloc(&s.d_ldr, sizeof(uint32_t) * px), "cudaMalloc ldr");
+  if (hdr && !dv.d_hdr) CU(cudaMalloc(&dv.d_hdr, sizeof(float4) * px), "cudaMalloc hdr");
+  if (ldr && !dv.d_ldr) CU(cudaMalloc(&dv.d_ldr, sizeof(uint32_t) * px), "cudaMalloc ldr");
   return 0;
 }
 
@@ -202,6 +351,17 @@ void fold_bbox(const std::vector<float>& pos, float bbox[6]) {       // geometry
   for (size_t i = 0; i + 2 < pos.size(); i += 3) {
     bbox[0] = min2(bbox[0], pos[i]); bbox[1] = min2(bbox[1], pos[i + 1]); bbox[2] = min2(bbox[2], pos[i + 2]);
     bbox[3] = max2(bbox[3], pos[i]); bbox[4] = max2(bbox[4], pos[i + 1]); bbox[5] = max2(bbox[5], pos[i + 2]);
+  }
+}
+
+// padded tight bounds of a vertex set (culling only; 1e-4 relative + 1e-5 absolute >> rounding error of the triangle test)
+void tight_bounds(const std::vector<float>& pos, float mn_o[3], float mx_o[3]) {
+  float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (size_t i = 0; i + 2 < pos.size(); i += 3)
+    for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], pos[i + k]); mx[k] = fmaxf(mx[k], pos[i + k]); }
+  for (int k = 0; k < 3; k++) {
+    float pad = fmaxf(fabsf(mn[k]), fabsf(mx[k])) * 1.0e-4f + 1.0e-5f;
+    mn_o[k] = mn[k] - pad; mx_o[k] = mx[k] + pad;
   }
 }
 
@@ -230,26 +390,24 @@ M4 rotation(float angle, float vx, float vy, float vz) {             // vector_m
   return M;
 }
 
+// the shaded mesh of gcore_set_mesh / gcore_set_mesh_vsgf: constant-memory triangles up to 64, LBVH per device above
 int install_mesh(int mesh_mode) {
   State& s = S();
   const int ntris = (int)s.mesh_tris.size() / 3;
   const int nverts = (int)s.mesh_pos.size() / 3;
-  for (int v : s.mesh_tris) if (v < 0 || v >= nverts) return fail(GCORE_E_ARG, "gcore_set_mesh: triangle index out of range");
-  gcore_dev::lbvh_free(&s.mesh_bvh);
+  bool bad_index = false;
+  for (int v : s.mesh_tris) if (v < 0 || v >= nverts) bad_index = true;
+  const bool too_big = ntris > GC_MAX_BF_TRIS && mesh_mode == GCORE_MESH_REFERENCE_BF;
+  if (bad_index || too_big) { s.mesh_pos.clear(); s.mesh_nrm.clear(); s.mesh_tris.clear(); }   // leave a scene without a mesh, not half of one
+  s.mesh_version++;
   s.hs.mesh_mode = mesh_mode;
   s.hs.ntris_bf = 0; s.hs.mesh_kind = 0; s.hs.pair_group = 0;
   for (int k = 0; k < 3; k++) { s.hs.mesh_bmin[k] = s.mesh_bbox[k]; s.hs.mesh_bmax[k] = s.mesh_bbox[3 + k]; }
-  s.scene_dirty = true;
+  mark_scene_dirty();
+  if (bad_index) return fail(GCORE_E_ARG, "gcore_set_mesh: triangle index out of range");
+  if (too_big) return fail(GCORE_E_LIMIT, "GCORE_MESH_REFERENCE_BF (brute-force reference semantics) is limited to 64 triangles; use GCORE_MESH_NEAREST");
   if (ntris == 0) return 0;
-  {  // padded tight bounds of the vertices (culling only; 1e-4 relative + 1e-5 absolute >> rounding error of the triangle test)
-    float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    for (size_t i = 0; i + 2 < s.mesh_pos.size(); i += 3)
-      for (int k = 0; k < 3; k++) { mn[k] = fminf(mn[k], s.mesh_pos[i + k]); mx[k] = fmaxf(mx[k], s.mesh_pos[i + k]); }
-    for (int k = 0; k < 3; k++) {
-      float pad = fmaxf(fabsf(mn[k]), fabsf(mx[k])) * 1.0e-4f + 1.0e-5f;
-      s.hs.mesh_tight_min[k] = mn[k] - pad; s.hs.mesh_tight_max[k] = mx[k] + pad;
-    }
-  }
+  tight_bounds(s.mesh_pos, s.hs.mesh_tight_min, s.hs.mesh_tight_max);
   auto P = [&](int v, int k) { return s.mesh_pos[3 * (size_t)v + k]; };
   auto N = [&](int v, int k) { return s.mesh_nrm[3 * (size_t)v + k]; };
   if (ntris <= GC_MAX_BF_TRIS) {
@@ -267,88 +425,9 @@ int install_mesh(int mesh_mode) {
     if (ntris <= 8) s.hs.pair_group = ntris;            // WAVE_PAIR_TRIS of render_wave.cuh
     return 0;
   }
-  if (mesh_mode == GCORE_MESH_REFERENCE_BF)
-    return fail(GCORE_E_LIMIT, "GCORE_MESH_REFERENCE_BF (brute-force reference semantics) is limited to 64 triangles; use GCORE_MESH_NEAREST");
-  if (int rc = ensure_device()) return rc;
-  std::vector<float> n9(9 * (size_t)ntris);
-  for (int t = 0; t < ntris; t++)
-    for (int c = 0; c < 3; c++) for (int k = 0; k < 3; k++) n9[9 * (size_t)t + 3 * c + k] = N(s.mesh_tris[3 * (size_t)t + c], k);
-  float *d_v = nullptr, *d_n = nullptr; int* d_t = nullptr;
-  auto cleanup = [&]() { cudaFree(d_v); cudaFree(d_n); cudaFree(d_t); };
-  cudaError_t e;
-  if ((e = cudaMalloc(&d_v, s.mesh_pos.size() * 4)) != cudaSuccess || (e = cudaMalloc(&d_t, s.mesh_tris.size() * 4)) != cudaSuccess ||
-      (e = cudaMalloc(&d_n, n9.size() * 4)) != cudaSuccess) { cleanup(); return fail_cuda(e, "cudaMalloc mesh"); }
-  cudaMemcpyAsync(d_v, s.mesh_pos.data(), s.mesh_pos.size() * 4, cudaMemcpyHostToDevice, s.stream);
-  cudaMemcpyAsync(d_t, s.mesh_tris.data(), s.mesh_tris.size() * 4, cudaMemcpyHostToDevice, s.stream);
-  cudaMemcpyAsync(d_n, n9.data(), n9.size() * 4, cudaMemcpyHostToDevice, s.stream);
-  e = gcore_dev::lbvh_build(d_v, nverts, d_t, ntris, d_n, &s.mesh_bvh, s.stream);
-  cudaStreamSynchronize(s.stream);
-  cleanup();
-  if (e != cudaSuccess) return fail_cuda(e, "lbvh_build");
   s.hs.mesh_kind = 2;
-  return 0;
-}
-
-void free_legacy_device() {
-  State& s = S();
-  gcore_dev::lbvh_free(&s.legacy_bvh);
-  if (s.d_legacy_prim) { cudaFree(s.d_legacy_prim); s.d_legacy_prim = nullptr; }
-  if (s.d_legacy_inst) { cudaFree(s.d_legacy_inst); s.d_legacy_inst = nullptr; }
-  if (s.d_legacy_verts) { cudaFree(s.d_legacy_verts); s.d_legacy_verts = nullptr; }
-  if (s.d_legacy_tris) { cudaFree(s.d_legacy_tris); s.d_legacy_tris = nullptr; }
-  s.h_legacy_prim.clear(); s.h_legacy_inst.clear();
-  s.scene_dirty = true;
-}
-
-int render_units_locked(int units, gcore_render_stats* stats) {
-  State& s = S();
-  if (units < 0) return fail(GCORE_E_ARG, "units < 0");
-  if (!s.d_accum) return fail(GCORE_E_STATE, "gcore_resize_viewport has not been called");
-  if (s.cfg.max_depth < 1 || s.cfg.max_depth > 16) return fail(GCORE_E_ARG, "max_depth must be in 1..16");
-  if (int rc = sync_scene()) return rc;
-  RenderArgs a = make_args();
-  a.passes = units;
-  CU(cudaEventRecord(s.ev0, s.stream), "event");
-  int launches = 0;
-  uint64_t samples = 0;
-  const uint64_t pixels = (uint64_t)s.width * s.height;
-  if (s.cfg.render_type == GCORE_RT_DEBUG || s.cfg.render_type == GCORE_RT_WHITTED) {
-    CU(gcore_dev::launch_debug(s.hs.mesh_kind, a, s.stream), "debug_kernel");           // Debug_Ray_Tracing overwrites the buffer, spp stays
-    launches = 1; samples = pixels;
-    s.palette_frame = true;                                              // g_spp is not touched (ray_tracer.adb:245-260)
-  } else if (units > 0) {
-    const int per = s.cfg.anti_aliasing ? 4 : 1;
-    // the colour buffer holds one float4 per (pass, pixel): long renders go in chunks of passes
-    s.palette_frame = false;
-    size_t cap_bytes = GC_COLBUF_CAP_BYTES;
-    if (const char* e = getenv("GCORE_COLBUF_CAP_KB")) { long v = atol(e); if (v > 0) cap_bytes = (size_t)v << 10; }   // tests: force the chunked path on small frames
-    size_t chunk = cap_bytes / (sizeof(float4) * (size_t)s.nslots);
-    if (chunk < 1) chunk = 1;
-    if (chunk > (size_t)units) chunk = (size_t)units;
-    while ((chunk * (size_t)s.nslots) >> 31) chunk >>= 1;
-    if (chunk < 1) return fail(GCORE_E_LIMIT, "viewport too large for the work-item counter");
-    if (int rc = ensure_wave_buffers(chunk * (size_t)s.nslots)) return rc;
-    for (int done = 0; done < units; done += (int)chunk) {
-      const int n = (units - done < (int)chunk) ? (units - done) : (int)chunk;
-      a.passes = n; a.first_sample = s.spp;
-      CU(gcore_dev::launch_render_wave(s.cfg.render_type, s.hs.mesh_kind, a, s.wave, n, s.stats_level >= 2 ? 1 : 0, s.stream), "render_wave_kernel");
-      launches += 2;
-      s.spp += n * per;                                                  // ray_tracer.adb:168-176
-    }
-    samples = pixels * (uint64_t)(units * per);
-  }
-  CU(cudaEventRecord(s.ev1, s.stream), "event");
-  if (stats) {
-    unsigned long long c[4] = {0, 0, 0, 0};
-    CU(cudaMemcpyAsync(c, s.d_rays, sizeof(c), cudaMemcpyDeviceToHost, s.stream), "memcpy counters");
-    CU(cudaStreamSynchronize(s.stream), "render sync");
-    float ms = 0.f; cudaEventElapsedTime(&ms, s.ev0, s.ev1);
-    stats->rays = c[0] - s.last_counters[0]; stats->mesh_queries = c[1] - s.last_counters[1]; stats->bounces = c[2] - s.last_counters[2];
-    stats->reserved0 = 0;
-    s.last_counters[0] = c[0]; s.last_counters[1] = c[1]; s.last_counters[2] = c[2]; s.last_counters[3] = c[3];
-    stats->samples = samples; stats->kernel_ms = ms; stats->total_ms = ms; stats->spp = s.spp;
-    stats->kernel_launches = launches;
-  }
+  // build on the devices in use right away: an allocation / build failure belongs to this call
+  for (int d = 0; d < s.gpu_count; d++) { if (int rc = ensure_device(d)) return rc; if (int rc = build_mesh_bvh(d)) return rc; s.dev[d].scene_dirty = true; }
   return 0;
 }
 
@@ -358,19 +437,242 @@ int resolve_spp() {
   return (s.palette_frame || s.spp <= 0) ? 1 : s.spp;
 }
 
-int read_frame_locked(float* hdr4, uint32_t* ldr, int* launches) {
+int render_units_locked(int units, gcore_render_stats* stats) {
   State& s = S();
-  if (!s.d_accum) return fail(GCORE_E_STATE, "no viewport");
-  if (s.world != 1) return fail(GCORE_E_STATE, "gcore_read_frame needs world == 1; gather the accumulators and use gcore_resolve_gathered_device");
-  if (!hdr4 && !ldr) return 0;
-  if (int rc = ensure_out_buffers(hdr4 != nullptr, ldr != nullptr)) return rc;
-  RenderArgs a = make_args();
-  CU(gcore_dev::launch_resolve(a, resolve_spp(), hdr4 ? s.d_hdr : nullptr, ldr ? s.d_ldr : nullptr, s.stream), "resolve_kernel");
+  if (units < 0) return fail(GCORE_E_ARG, "units < 0");
+  if (!s.dev[0].d_accum) return fail(GCORE_E_STATE, "gcore_resize_viewport has not been called");
+  if (s.cfg.max_depth < 1 || s.cfg.max_depth > 16) return fail(GCORE_E_ARG, "max_depth must be in 1..16");
+  const int G = s.gpu_count;
+  for (int d = 0; d < G; d++) if (int rc = sync_scene(d)) return rc;
+  const int mesh_kind = active_mesh_kind();
+  int launches = 0;
+  uint64_t samples = 0;
+  const uint64_t pixels = (uint64_t)s.width * s.height;
+  const bool debug = (s.cfg.render_type == GCORE_RT_DEBUG || s.cfg.render_type == GCORE_RT_WHITTED);
+  const int per = s.cfg.anti_aliasing ? 4 : 1;
+  size_t chunk = 0;
+  if (!debug && units > 0) {
+    // the colour buffer holds one float4 per (pass, pixel): very long renders go in chunks of passes
+    size_t cap_bytes = GC_COLBUF_CAP_BYTES;
+    if (const char* e = getenv("GCORE_COLBUF_CAP_KB")) { long v = atol(e); if (v > 0) cap_bytes = (size_t)v << 10; }   // tests: force the chunked path on small frames
+    const size_t nslots = (size_t)s.dev[0].nslots;
+    chunk = cap_bytes / (sizeof(float4) * nslots);
+    if (chunk < 1) chunk = 1;
+    if (chunk > (size_t)units) chunk = (size_t)units;
+    while (chunk > 1 && ((chunk * nslots) >> 31)) chunk >>= 1;
+    if ((chunk * nslots) >> 31) return fail(GCORE_E_LIMIT, "viewport too large for the work-item counter");
+  }
+  // every device gets its whole share enqueued before the next one: launches are asynchronous, the devices run concurrently
+  for (int d = 0; d < G; d++) {
+    Device& dv = s.dev[d];
+    CU(cudaSetDevice(dv.ordinal), "cudaSetDevice");
+    RenderArgs a = make_args(d);
+    a.passes = units;
+    CU(cudaEventRecord(dv.ev0, dv.stream), "event");
+    if (debug) {
+      CU(gcore_dev::launch_debug(mesh_kind, a, dv.stream), "debug_kernel");                 // Debug_Ray_Tracing overwrites the buffer
+      launches += 1;
+    } else if (units > 0) {
+      if (int rc = ensure_wave_buffers(d, chunk * (size_t)dv.nslots, mesh_kind == 2)) return rc;
+      int spp = s.spp;
+      for (int done = 0; done < units; done += (int)chunk) {
+        const int n = (units - done < (int)chunk) ? (units - done) : (int)chunk;
+        a.passes = n; a.first_sample = spp;
+        CU(gcore_dev::launch_render_wave(s.cfg.render_type, mesh_kind, a, dv.wave, n, s.stats_level >= 2 ? 1 : 0, dv.stream), "render_wave_kernel");
+        launches += 2;
+        spp += n * per;
+      }
+    }
+    CU(cudaEventRecord(dv.ev1, dv.stream), "event");
+  }
+  if (debug) { samples = pixels; s.palette_frame = true; }                                    // g_spp is not touched (ray_tracer.adb:245-260)
+  else if (units > 0) { samples = pixels * (uint64_t)(units * per); s.spp += units * per; s.palette_frame = false; }   // ray_tracer.adb:168-176
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    float kernel_ms = 0.f;
+    for (int d = 0; d < G; d++) {
+      Device& dv = s.dev[d];
+      CU(cudaSetDevice(dv.ordinal), "cudaSetDevice");
+      unsigned long long c[6] = {0, 0, 0, 0, 0, 0};
+      CU(cudaMemcpyAsync(c, dv.d_rays, sizeof(c), cudaMemcpyDeviceToHost, dv.stream), "memcpy counters");
+      CU(cudaStreamSynchronize(dv.stream), "render sync");
+      float ms = 0.f; cudaEventElapsedTime(&ms, dv.ev0, dv.ev1);
+      dv.last_kernel_ms = ms;
+      if (ms > kernel_ms) kernel_ms = ms;
+      stats->rays += c[0] - dv.last_counters[0]; stats->mesh_queries += c[1] - dv.last_counters[1]; stats->bounces += c[2] - dv.last_counters[2];
+      for (int k = 0; k < 6; k++) dv.last_counters[k] = c[k];
+    }
+    stats->samples = samples; stats->kernel_ms = kernel_ms; stats->total_ms = kernel_ms; stats->spp = s.spp;
+    stats->kernel_launches = launches;
+  }
+  return 0;
+}
+
+// ---- the one exchange step of a multi-GPU frame: accumulators of devices 1..G-1 -> device 0, behind its own (NCCL)
+int ensure_nccl() {
+  State& s = S();
+  if (s.nccl_ready) return 0;
+  NcclApi& n = s.nccl;
+  if (!n.h) {
+    n.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!n.h) n.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!n.h) return fail(GCORE_E_STATE, std::string("multi-GPU rendering needs NCCL: ") + dlerror());
+    n.CommInitAll = (decltype(n.CommInitAll))dlsym(n.h, "ncclCommInitAll");
+    n.CommDestroy = (decltype(n.CommDestroy))dlsym(n.h, "ncclCommDestroy");
+    n.GroupStart = (decltype(n.GroupStart))dlsym(n.h, "ncclGroupStart");
+    n.GroupEnd = (decltype(n.GroupEnd))dlsym(n.h, "ncclGroupEnd");
+    n.Send = (decltype(n.Send))dlsym(n.h, "ncclSend");
+    n.Recv = (decltype(n.Recv))dlsym(n.h, "ncclRecv");
+    n.GetErrorString = (decltype(n.GetErrorString))dlsym(n.h, "ncclGetErrorString");
+    if (!n.CommInitAll || !n.CommDestroy || !n.GroupStart || !n.GroupEnd || !n.Send || !n.Recv || !n.GetErrorString)
+      return fail(GCORE_E_STATE, "libnccl lacks an entry point");
+  }
+  int devs[GC_MAX_GPUS];
+  for (int d = 0; d < s.gpu_count; d++) devs[d] = s.dev[d].ordinal;
+  ncclResult_t r = n.CommInitAll(s.comms, s.gpu_count, devs);
+  if (r != ncclSuccess) return fail(GCORE_E_CUDA, std::string("ncclCommInitAll: ") + n.GetErrorString(r));
+  s.nccl_ready = true;
+  return 0;
+}
+
+void destroy_nccl() {
+  State& s = S();
+  if (!s.nccl_ready) return;
+  for (int d = 0; d < s.gpu_count; d++) s.nccl.CommDestroy(s.comms[d]);
+  s.nccl_ready = false;
+}
+
+int gather_accumulators() {
+  State& s = S();
+  const int G = s.gpu_count;
+  if (G == 1) return 0;
+  if (int rc = ensure_nccl()) return rc;
+  NcclApi& n = s.nccl;
+  const size_t count = (size_t)s.dev[0].nslots * 4;
+  ncclResult_t r = n.GroupStart();
+  for (int d = 1; d < G && r == ncclSuccess; d++) {
+    r = n.Send(s.dev[d].d_accum, count, ncclFloat, 0, s.comms[d], s.dev[d].stream);
+    if (r == ncclSuccess) r = n.Recv(s.dev[0].d_gather + (size_t)d * s.dev[0].nslots, count, ncclFloat, d, s.comms[0], s.dev[0].stream);
+  }
+  ncclResult_t r2 = n.GroupEnd();
+  if (r == ncclSuccess) r = r2;
+  if (r != ncclSuccess) return fail(GCORE_E_CUDA, std::string("nccl gather: ") + n.GetErrorString(r));
+  return 0;
+}
+
+// resolve into device buffers of device 0 (gathering first when several devices rendered)
+int resolve_to(float4* d_hdr, uint32_t* d_ldr, int* launches) {
+  State& s = S(); Device& d0 = s.dev[0];
+  if (int rc = gather_accumulators()) return rc;
+  CU(cudaSetDevice(d0.ordinal), "cudaSetDevice");
+  RenderArgs a = make_args(0);
+  if (s.gpu_count == 1) CU(gcore_dev::launch_resolve(a, resolve_spp(), d_hdr, d_ldr, d0.stream), "resolve_kernel");
+  else CU(gcore_dev::launch_resolve_gathered(a, d0.d_gather, resolve_spp(), d_hdr, d_ldr, d0.stream), "resolve_kernel");
   if (launches) *launches += 1;
+  return 0;
+}
+
+int read_frame_locked(float* hdr4, uint32_t* ldr, int* launches) {
+  State& s = S(); Device& d0 = s.dev[0];
+  if (!d0.d_accum) return fail(GCORE_E_STATE, "no viewport");
+  if (s.world != 1) return fail(GCORE_E_STATE, "gcore_read_frame needs world == 1 (multi-process partition: gather the accumulators and use gcore_resolve_gathered_device; one process: gcore_set_gpu_count)");
+  if (!hdr4 && !ldr) return 0;
+  CU(cudaSetDevice(d0.ordinal), "cudaSetDevice");
+  if (int rc = ensure_out_buffers(hdr4 != nullptr, ldr != nullptr)) return rc;
+  if (int rc = resolve_to(hdr4 ? d0.d_hdr : nullptr, ldr ? d0.d_ldr : nullptr, launches)) return rc;
   size_t px = (size_t)s.width * s.height;
-  if (hdr4) CU(cudaMemcpyAsync(hdr4, s.d_hdr, sizeof(float4) * px, cudaMemcpyDeviceToHost, s.stream), "memcpy hdr");
-  if (ldr) CU(cudaMemcpyAsync(ldr, s.d_ldr, sizeof(uint32_t) * px, cudaMemcpyDeviceToHost, s.stream), "memcpy ldr");
-  CU(cudaStreamSynchronize(s.stream), "read_frame sync");
+  if (hdr4) CU(cudaMemcpyAsync(hdr4, d0.d_hdr, sizeof(float4) * px, cudaMemcpyDeviceToHost, d0.stream), "memcpy hdr");
+  if (ldr) CU(cudaMemcpyAsync(ldr, d0.d_ldr, sizeof(uint32_t) * px, cudaMemcpyDeviceToHost, d0.stream), "memcpy ldr");
+  CU(cudaStreamSynchronize(d0.stream), "read_frame sync");
+  return 0;
+}
+
+void release_device(int d) {
+  State& s = S(); Device& dv = s.dev[d];
+  if (!dv.ready) return;
+  cudaSetDevice(dv.ordinal);
+  cudaStreamSynchronize(dv.stream);
+  free_accum(d);
+  gcore_dev::lbvh_free(&dv.mesh_bvh); gcore_dev::lbvh_free(&dv.legacy_bvh);
+  dv.mesh_version = dv.legacy_version = -1;
+  cudaFree(dv.wave.colbuf); cudaFree(dv.wave.stackA); cudaFree(dv.wave.stackB); cudaFree(dv.wave.next_item); cudaFree(dv.wave.tstack_ovf);
+  dv.wave = WaveBuffers();
+  dv.scene_dirty = true;
+}
+
+// flatten the instances of the legacy scene into world space (what rtcCommitScene of the instanced scene makes traceable,
+// cpp/embree_connect.cpp:147-184, 241-244)
+void flatten_legacy() {
+  State& s = S();
+  FlatScene f;
+  f.version = s.flat.version + 1;
+  std::vector<LegacyInstance> inst = s.instances;
+  if (inst.empty()) {                                                  // no instance declared: every mesh once, identity
+    for (int m = 0; m < (int)s.meshes.size(); m++) { LegacyInstance in; in.mesh = m; memset(in.m, 0, sizeof(in.m)); in.m[0] = in.m[5] = in.m[10] = 1.0f; inst.push_back(in); }
+  }
+  for (int ii = 0; ii < (int)inst.size(); ii++) {
+    const LegacyMesh& m = s.meshes[inst[ii].mesh];
+    const float* M = inst[ii].m;
+    const int base = (int)f.verts.size() / 3;
+    for (size_t v = 0; v + 2 < m.verts.size(); v += 3) {
+      float x = m.verts[v], y = m.verts[v + 1], z = m.verts[v + 2];
+      f.verts.push_back(M[0] * x + M[1] * y + M[2] * z + M[3]);
+      f.verts.push_back(M[4] * x + M[5] * y + M[6] * z + M[7]);
+      f.verts.push_back(M[8] * x + M[9] * y + M[10] * z + M[11]);
+    }
+    const bool has_n = !m.normals.empty() && m.normals.size() == m.verts.size();
+    for (size_t t = 0; t + 2 < m.idx.size(); t += 3) {
+      const int i3[3] = {m.idx[t], m.idx[t + 1], m.idx[t + 2]};
+      for (int c = 0; c < 3; c++) f.tris.push_back(base + i3[c]);
+      f.prim.push_back((int)(t / 3)); f.inst.push_back(ii); f.mat.push_back(m.mat);
+      float n9[9];
+      if (has_n) {                                                     // vertex normals under the instance's 3x3, normalised
+        for (int c = 0; c < 3; c++) {
+          const float nx = m.normals[3 * (size_t)i3[c]], ny = m.normals[3 * (size_t)i3[c] + 1], nz = m.normals[3 * (size_t)i3[c] + 2];
+          const float wx = M[0] * nx + M[1] * ny + M[2] * nz, wy = M[4] * nx + M[5] * ny + M[6] * nz, wz = M[8] * nx + M[9] * ny + M[10] * nz;
+          const float l_inv = 1.0f / sqrtf(wx * wx + wy * wy + wz * wz);
+          n9[3 * c] = l_inv * wx; n9[3 * c + 1] = l_inv * wy; n9[3 * c + 2] = l_inv * wz;
+        }
+      } else {                                                         // geometric normal normalize(cross(B - A, C - A)) at all three corners
+        const float* A = &f.verts[3 * (size_t)(base + i3[0])]; const float* B = &f.verts[3 * (size_t)(base + i3[1])]; const float* C = &f.verts[3 * (size_t)(base + i3[2])];
+        const float e1[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, e2[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
+        const float cx = e1[1] * e2[2] - e2[1] * e1[2], cy = e1[2] * e2[0] - e2[2] * e1[0], cz = e1[0] * e2[1] - e2[0] * e1[1];
+        const float l_inv = 1.0f / sqrtf(cx * cx + cy * cy + cz * cz);
+        for (int c = 0; c < 3; c++) { n9[3 * c] = l_inv * cx; n9[3 * c + 1] = l_inv * cy; n9[3 * c + 2] = l_inv * cz; }
+      }
+      f.n9.insert(f.n9.end(), n9, n9 + 9);
+    }
+  }
+  if (!f.verts.empty()) tight_bounds(f.verts, f.tight_min, f.tight_max);
+  s.flat = std::move(f);
+  mark_scene_dirty();
+}
+
+// device staging of the batched seam queries: grown on demand and kept
+int ensure_batch_buffers(size_t n) {
+  Device& dv = S().dev[0];
+  if (n <= dv.batch_cap) return 0;
+  cudaFree(dv.d_batch_rays); cudaFree(dv.d_batch_hits); cudaFree(dv.d_batch_found);
+  dv.d_batch_rays = nullptr; dv.d_batch_hits = nullptr; dv.d_batch_found = nullptr; dv.batch_cap = 0;
+  size_t cap = n < 256 ? 256 : n;
+  CU(cudaMalloc(&dv.d_batch_rays, sizeof(gcore_ray) * cap), "cudaMalloc batch");
+  CU(cudaMalloc(&dv.d_batch_hits, sizeof(gcore_HitCpp) * cap), "cudaMalloc batch");
+  CU(cudaMalloc(&dv.d_batch_found, sizeof(int) * cap), "cudaMalloc batch");
+  dv.batch_cap = cap;
+  return 0;
+}
+
+int read_counters(unsigned long long out[6]) {
+  State& s = S();
+  for (int k = 0; k < 6; k++) out[k] = 0;
+  for (int d = 0; d < s.gpu_count; d++) {
+    if (int rc = ensure_device(d)) return rc;
+    Device& dv = s.dev[d];
+    unsigned long long c[6] = {0, 0, 0, 0, 0, 0};
+    CU(cudaMemcpyAsync(c, dv.d_rays, sizeof(c), cudaMemcpyDeviceToHost, dv.stream), "memcpy counters");
+    CU(cudaStreamSynchronize(dv.stream), "counters sync");
+    for (int k = 0; k < 6; k++) out[k] += c[k];
+  }
   return 0;
 }
 
@@ -390,15 +692,42 @@ int gcore_last_error(char* buf, int n) {
 int gcore_set_device(int device) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
-  if (s.dev_ready && device != s.device) return fail(GCORE_E_STATE, "gcore_set_device must be called before any other device work");
-  s.device = device;
-  return ensure_device();
+  if (device < 0) return fail(GCORE_E_ARG, "gcore_set_device: negative device");
+  if (s.dev[0].ready && device != s.base_device) return fail(GCORE_E_STATE, "gcore_set_device must be called before any other device work");
+  s.base_device = device;
+  return ensure_device(0);
+}
+
+int gcore_set_gpu_count(int n) {
+  State& s = S();
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
+  if (n < 1 || n > GC_MAX_GPUS) return fail(GCORE_E_ARG, "gcore_set_gpu_count: 1..8 devices");
+  if (n > 1 && s.world != 1) return fail(GCORE_E_STATE, "gcore_set_gpu_count: in-process multi-GPU and the multi-process partition (gcore_set_partition) exclude each other");
+  int have = 0;
+  if (cudaGetDeviceCount(&have) != cudaSuccess || have == 0) { cudaGetLastError(); return fail(GCORE_E_CUDA, "no CUDA device available (libgcore_b200 has no CPU fallback)"); }
+  if (s.base_device + n > have) return fail(GCORE_E_ARG, "gcore_set_gpu_count: more devices than the box has");
+  if (n == s.gpu_count) return 0;
+  destroy_nccl();
+  for (int d = 0; d < GC_MAX_GPUS; d++) { if (d >= n) release_device(d); else free_accum(d); }
+  s.gpu_count = n;
+  s.spp = 0; s.palette_frame = false;
+  if (s.width > 0) return alloc_accum();
+  return 0;
+  GC_CATCH_INT
+}
+
+int gcore_get_gpu_count(void) {
+  State& s = S();
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  return s.gpu_count;
 }
 
 int gcore_set_partition(int rank, int world) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
   if (world < 1 || rank < 0 || rank >= world) return fail(GCORE_E_ARG, "bad partition");
+  if (world > 1 && s.gpu_count != 1) return fail(GCORE_E_STATE, "gcore_set_partition: the multi-process partition and in-process multi-GPU (gcore_set_gpu_count) exclude each other");
   s.rank = rank; s.world = world;
   if (s.width > 0) return alloc_accum();
   return 0;
@@ -407,23 +736,25 @@ int gcore_set_partition(int rank, int world) {
 int gcore_stream(void** stream) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
-  if (int rc = ensure_device()) return rc;
-  if (stream) *stream = (void*)s.stream;
+  if (int rc = ensure_device(0)) return rc;
+  if (stream) *stream = (void*)s.dev[0].stream;
   return 0;
 }
 
 int gcore_synchronize(void) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
-  if (int rc = ensure_device()) return rc;
-  CU(cudaStreamSynchronize(s.stream), "synchronize");
+  for (int d = 0; d < s.gpu_count; d++) {
+    if (int rc = ensure_device(d)) return rc;
+    CU(cudaStreamSynchronize(s.dev[d].stream), "synchronize");
+  }
   return 0;
 }
 
 int gcore_bvh_info(int64_t* ntris, int64_t* nnodes, int64_t* bytes, float* build_ms) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
-  const LbvhBuffers& b = s.mesh_bvh.ntris ? s.mesh_bvh : s.legacy_bvh;
+  const LbvhBuffers& b = (!s.use_committed && s.dev[0].mesh_bvh.ntris) ? s.dev[0].mesh_bvh : s.dev[0].legacy_bvh;
   if (ntris) *ntris = b.ntris;
   if (nnodes) *nnodes = b.nnodes;
   if (bytes) *bytes = (int64_t)b.bytes;
@@ -434,17 +765,30 @@ int gcore_bvh_info(int64_t* ntris, int64_t* nnodes, int64_t* bytes, float* build
 int gcore_kernel_regs(int render_type) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
-  if (int rc = ensure_device()) return rc;
+  if (int rc = ensure_device(0)) return rc;
   return gcore_dev::render_kernel_regs(render_type);
+}
+
+int gcore_device_kernel_ms(float* out, int n) {
+  State& s = S();
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  if (!out || n < 0) return fail(GCORE_E_ARG, "gcore_device_kernel_ms: bad arguments");
+  for (int d = 0; d < n; d++) out[d] = d < s.gpu_count ? s.dev[d].last_kernel_ms : 0.f;
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------- legacy seam
 void gcore_destroy(void) {                                             // embree_connect.cpp:51-58
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
   s.meshes.clear(); s.instances.clear();
-  if (s.dev_ready) free_legacy_device();
+  const int v = s.flat.version + 1;
+  s.flat = FlatScene(); s.flat.version = v;
+  for (int d = 0; d < GC_MAX_GPUS; d++) if (s.dev[d].ready) { cudaSetDevice(s.dev[d].ordinal); gcore_dev::lbvh_free(&s.dev[d].legacy_bvh); s.dev[d].legacy_version = v; }
+  mark_scene_dirty();
   s.legacy_alive = false;
+  GC_CATCH_VOID
 }
 
 void gcore_init_and_clear(void) {                                      // embree_connect.cpp:60-67
@@ -457,28 +801,53 @@ void gcore_init_and_clear(void) {                                      // embree
 int gcore_add_mesh_3f(const float* a_vertices3f, int a_vertexNum, const int* a_indices, int a_indicesNum) {   // :69-144
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
-  if (!a_vertices3f || !a_indices || a_vertexNum <= 0 || a_indicesNum < 0) { fail(GCORE_E_ARG, "gcore_add_mesh_3f: bad arguments"); return -1; }
-  LegacyMesh m;
-  const int triNum = a_indicesNum / 3;
-  m.idx.resize(3 * (size_t)triNum);
-  int maxVertexId = 0;
-  for (int i = 0; i < triNum; i++) {
-    int A = a_indices[i * 3 + 0], B = a_indices[i * 3 + 1], C = a_indices[i * 3 + 2];
-    if (A >= a_vertexNum || B >= a_vertexNum || C >= a_vertexNum || A < 0 || B < 0 || C < 0) A = B = C = a_vertexNum - 1;   // :98-109
-    if (A > maxVertexId) maxVertexId = A;
-    if (B > maxVertexId) maxVertexId = B;
-    if (C > maxVertexId) maxVertexId = C;
-    m.idx[3 * (size_t)i] = A; m.idx[3 * (size_t)i + 1] = B; m.idx[3 * (size_t)i + 2] = C;
-  }
-  // the shim copies `maxVertexId` vertices (:122-134), one short of what the indices reference; copy maxVertexId + 1
-  m.verts.assign(a_vertices3f, a_vertices3f + 3 * (size_t)(maxVertexId + 1));
-  s.meshes.push_back(std::move(m));
-  return (int)s.meshes.size() - 1;
+  try {
+    if (!a_vertices3f || !a_indices || a_vertexNum <= 0 || a_indicesNum < 0) { fail(GCORE_E_ARG, "gcore_add_mesh_3f: bad arguments"); return -1; }
+    LegacyMesh m;
+    const int triNum = a_indicesNum / 3;
+    m.idx.resize(3 * (size_t)triNum);
+    int maxVertexId = 0;
+    for (int i = 0; i < triNum; i++) {
+      int A = a_indices[i * 3 + 0], B = a_indices[i * 3 + 1], C = a_indices[i * 3 + 2];
+      if (A >= a_vertexNum || B >= a_vertexNum || C >= a_vertexNum || A < 0 || B < 0 || C < 0) A = B = C = a_vertexNum - 1;   // :98-109
+      if (A > maxVertexId) maxVertexId = A;
+      if (B > maxVertexId) maxVertexId = B;
+      if (C > maxVertexId) maxVertexId = C;
+      m.idx[3 * (size_t)i] = A; m.idx[3 * (size_t)i + 1] = B; m.idx[3 * (size_t)i + 2] = C;
+    }
+    // the shim copies `maxVertexId` vertices (:122-134), one short of what the indices reference; copy maxVertexId + 1
+    m.verts.assign(a_vertices3f, a_vertices3f + 3 * (size_t)(maxVertexId + 1));
+    s.meshes.push_back(std::move(m));
+    return (int)s.meshes.size() - 1;
+  } catch (...) { fail(GCORE_E_LIMIT, "gcore_add_mesh_3f: out of host memory"); return -1; }
+}
+
+int gcore_set_mesh_material(int meshId, int matId) {
+  State& s = S();
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  if (meshId < 0 || meshId >= (int)s.meshes.size()) return fail(GCORE_E_ARG, "gcore_set_mesh_material: bad meshId");
+  if (matId < 0 || matId >= GC_MAX_MATERIALS) return fail(GCORE_E_ARG, "gcore_set_mesh_material: material id outside 0..31");
+  s.meshes[meshId].mat = matId;
+  return 0;
+}
+
+int gcore_set_mesh_normals_3f(int meshId, const float* a_normals3f, int a_vertexNum) {
+  State& s = S();
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
+  if (meshId < 0 || meshId >= (int)s.meshes.size()) return fail(GCORE_E_ARG, "gcore_set_mesh_normals_3f: bad meshId");
+  LegacyMesh& m = s.meshes[meshId];
+  if (!a_normals3f) { m.normals.clear(); return 0; }
+  if (a_vertexNum < 0 || (size_t)a_vertexNum * 3 < m.verts.size()) return fail(GCORE_E_ARG, "gcore_set_mesh_normals_3f: fewer normals than vertices in use");
+  m.normals.assign(a_normals3f, a_normals3f + m.verts.size());
+  return 0;
+  GC_CATCH_INT
 }
 
 void gcore_instance_meshes(int a_geomId, const float* a_matrices16f, int a_matrixNum) {   // :147-184
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
   s.err_code = 0; s.err_text.clear();
   if (a_geomId < 0 || a_geomId >= (int)s.meshes.size() || !a_matrices16f) { fail(GCORE_E_ARG, "gcore_instance_meshes: bad meshId"); return; }
   for (int k = 0; k < a_matrixNum; k++) {
@@ -486,114 +855,109 @@ void gcore_instance_meshes(int a_geomId, const float* a_matrices16f, int a_matri
     memcpy(in.m, a_matrices16f + 16 * (size_t)k, 12 * sizeof(float));   // RTC_FORMAT_FLOAT3X4_ROW_MAJOR (:169)
     s.instances.push_back(in);
   }
+  GC_CATCH_VOID
 }
 
 void gcore_commit_scene(void) {                                        // :241-244
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
   s.err_code = 0; s.err_text.clear();                                  // void signature: gcore_last_error() afterwards speaks for this call
-  if (ensure_device()) return;
-  free_legacy_device();
-  std::vector<LegacyInstance> inst = s.instances;
-  if (inst.empty()) {                                                  // no instance declared: every mesh once, identity
-    for (int m = 0; m < (int)s.meshes.size(); m++) { LegacyInstance in; in.mesh = m; memset(in.m, 0, sizeof(in.m)); in.m[0] = in.m[5] = in.m[10] = 1.0f; inst.push_back(in); }
-  }
-  std::vector<float> verts; std::vector<int> tris;
-  for (int ii = 0; ii < (int)inst.size(); ii++) {
-    const LegacyMesh& m = s.meshes[inst[ii].mesh];
-    const float* M = inst[ii].m;
-    int base = (int)verts.size() / 3;
-    for (size_t v = 0; v + 2 < m.verts.size(); v += 3) {
-      float x = m.verts[v], y = m.verts[v + 1], z = m.verts[v + 2];
-      verts.push_back(M[0] * x + M[1] * y + M[2] * z + M[3]);
-      verts.push_back(M[4] * x + M[5] * y + M[6] * z + M[7]);
-      verts.push_back(M[8] * x + M[9] * y + M[10] * z + M[11]);
-    }
-    for (size_t t = 0; t + 2 < m.idx.size(); t += 3) {
-      tris.push_back(base + m.idx[t]); tris.push_back(base + m.idx[t + 1]); tris.push_back(base + m.idx[t + 2]);
-      s.h_legacy_prim.push_back((int)(t / 3)); s.h_legacy_inst.push_back(ii);
-    }
-  }
-  const int ntris = (int)tris.size() / 3;
-  if (ntris == 0) return;
-  cudaError_t e;
-  if ((e = cudaMalloc(&s.d_legacy_verts, verts.size() * 4)) != cudaSuccess || (e = cudaMalloc(&s.d_legacy_tris, tris.size() * 4)) != cudaSuccess ||
-      (e = cudaMalloc(&s.d_legacy_prim, 4 * (size_t)ntris)) != cudaSuccess || (e = cudaMalloc(&s.d_legacy_inst, 4 * (size_t)ntris)) != cudaSuccess) {
-    fail_cuda(e, "cudaMalloc legacy scene"); free_legacy_device(); return;
-  }
-  cudaMemcpyAsync(s.d_legacy_verts, verts.data(), verts.size() * 4, cudaMemcpyHostToDevice, s.stream);
-  cudaMemcpyAsync(s.d_legacy_tris, tris.data(), tris.size() * 4, cudaMemcpyHostToDevice, s.stream);
-  cudaMemcpyAsync(s.d_legacy_prim, s.h_legacy_prim.data(), 4 * (size_t)ntris, cudaMemcpyHostToDevice, s.stream);
-  cudaMemcpyAsync(s.d_legacy_inst, s.h_legacy_inst.data(), 4 * (size_t)ntris, cudaMemcpyHostToDevice, s.stream);
-  e = gcore_dev::lbvh_build(s.d_legacy_verts, (int)verts.size() / 3, s.d_legacy_tris, ntris, nullptr, &s.legacy_bvh, s.stream);
-  if (e != cudaSuccess) { fail_cuda(e, "lbvh_build (legacy scene)"); free_legacy_device(); return; }
-  s.scene_dirty = true;
+  if (ensure_device(0)) return;
+  flatten_legacy();
+  for (int d = 0; d < s.gpu_count; d++) { if (ensure_device(d)) return; if (build_legacy_bvh(d)) return; s.dev[d].scene_dirty = true; }
+  GC_CATCH_VOID
 }
 
-// device staging of the batched seam queries: grown on demand and kept, so that the one-ray-per-call legacy entry point
-// (scene_hydra_embree.adb:426-446 calls it for every ray) costs a launch and two small copies, not six allocations
-static int ensure_batch_buffers(size_t n) {
+int gcore_use_committed_scene(int enable) {
   State& s = S();
-  if (n <= s.batch_cap) return 0;
-  cudaFree(s.d_batch_rays); cudaFree(s.d_batch_hits); cudaFree(s.d_batch_found);
-  s.d_batch_rays = nullptr; s.d_batch_hits = nullptr; s.d_batch_found = nullptr; s.batch_cap = 0;
-  size_t cap = n < 256 ? 256 : n;
-  CU(cudaMalloc(&s.d_batch_rays, sizeof(gcore_ray) * cap), "cudaMalloc batch");
-  CU(cudaMalloc(&s.d_batch_hits, sizeof(gcore_HitCpp) * cap), "cudaMalloc batch");
-  CU(cudaMalloc(&s.d_batch_found, sizeof(int) * cap), "cudaMalloc batch");
-  s.batch_cap = cap;
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  s.use_committed = enable != 0;
+  mark_scene_dirty();
+  return 0;
+}
+
+int gcore_set_seam_two_sided(int enable) {
+  State& s = S();
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  s.seam_two_sided = enable ? 1 : 0;
   return 0;
 }
 
 int gcore_bvh_closest_hit_batch(int n, const gcore_ray* rays, float t_near, float t_far, gcore_HitCpp* hits, int32_t* found) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
   if (n < 0 || (n > 0 && (!rays || !hits || !found))) return fail(GCORE_E_ARG, "gcore_bvh_closest_hit_batch: bad arguments");
   if (n == 0) return 0;
-  if (int rc = sync_scene()) return rc;
+  if (int rc = sync_scene(0)) return rc;
   if (int rc = ensure_batch_buffers((size_t)n)) return rc;
-  gcore_ray* d_r = s.d_batch_rays; gcore_HitCpp* d_h = s.d_batch_hits; int* d_f = s.d_batch_found;
-  cudaError_t e = cudaMemcpyAsync(d_r, rays, sizeof(gcore_ray) * (size_t)n, cudaMemcpyHostToDevice, s.stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_h, hits, sizeof(gcore_HitCpp) * (size_t)n, cudaMemcpyHostToDevice, s.stream);   // records are only written on a hit
-  if (e == cudaSuccess) e = gcore_dev::launch_bvh_batch(n, d_r, t_near, t_far, d_h, d_f, s.stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_h, sizeof(gcore_HitCpp) * (size_t)n, cudaMemcpyDeviceToHost, s.stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(found, d_f, 4 * (size_t)n, cudaMemcpyDeviceToHost, s.stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+  Device& dv = s.dev[0];
+  gcore_ray* d_r = dv.d_batch_rays; gcore_HitCpp* d_h = dv.d_batch_hits; int* d_f = dv.d_batch_found;
+  cudaError_t e = cudaMemcpyAsync(d_r, rays, sizeof(gcore_ray) * (size_t)n, cudaMemcpyHostToDevice, dv.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_h, hits, sizeof(gcore_HitCpp) * (size_t)n, cudaMemcpyHostToDevice, dv.stream);   // records are only written on a hit
+  if (e == cudaSuccess) e = gcore_dev::launch_bvh_batch(n, d_r, t_near, t_far, d_h, d_f, s.seam_two_sided, dv.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_h, sizeof(gcore_HitCpp) * (size_t)n, cudaMemcpyDeviceToHost, dv.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(found, d_f, 4 * (size_t)n, cudaMemcpyDeviceToHost, dv.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(dv.stream);
   if (e != cudaSuccess) return fail_cuda(e, "bvh batch");
   // flattened triangle id -> (primIndex inside its mesh, instIndex); Ng from the flattened world-space triangle
   for (int i = 0; i < n; i++) if (found[i]) {
     int flat = hits[i].primIndex;
-    if (flat >= 0 && flat < (int)s.h_legacy_prim.size()) { hits[i].primIndex = s.h_legacy_prim[flat]; hits[i].instIndex = s.h_legacy_inst[flat]; hits[i].geomIndex = 0; }
+    if (flat >= 0 && flat < (int)s.flat.prim.size()) { hits[i].primIndex = s.flat.prim[flat]; hits[i].instIndex = s.flat.inst[flat]; hits[i].geomIndex = 0; }
   }
   return 0;
+  GC_CATCH_INT
+}
+
+int gcore_bvh_occluded_batch(int n, const gcore_ray* rays, float t_near, float t_far, int32_t* occluded) {   // rtcOccluded1 counterpart
+  State& s = S();
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
+  if (n < 0 || (n > 0 && (!rays || !occluded))) return fail(GCORE_E_ARG, "gcore_bvh_occluded_batch: bad arguments");
+  if (n == 0) return 0;
+  if (int rc = sync_scene(0)) return rc;
+  if (int rc = ensure_batch_buffers((size_t)n)) return rc;
+  Device& dv = s.dev[0];
+  cudaError_t e = cudaMemcpyAsync(dv.d_batch_rays, rays, sizeof(gcore_ray) * (size_t)n, cudaMemcpyHostToDevice, dv.stream);
+  if (e == cudaSuccess) e = gcore_dev::launch_bvh_occluded(n, dv.d_batch_rays, t_near, t_far, dv.d_batch_found, s.seam_two_sided, dv.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(occluded, dv.d_batch_found, 4 * (size_t)n, cudaMemcpyDeviceToHost, dv.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(dv.stream);
+  if (e != cudaSuccess) return fail_cuda(e, "bvh occluded");
+  return 0;
+  GC_CATCH_INT
 }
 
 int gcore_bvh_bench(int n, const gcore_ray* rays, float t_near, float t_far, int which, int repeat, float* ms_per_launch, uint64_t* stats3) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
   if (n <= 0 || !rays || repeat < 1 || which < 0 || which > 1) return fail(GCORE_E_ARG, "gcore_bvh_bench: bad arguments");
-  if (int rc = sync_scene()) return rc;
-  if ((which ? s.mesh_bvh.ntris : s.legacy_bvh.ntris) <= 0) return fail(GCORE_E_STATE, "gcore_bvh_bench: no LBVH of that kind is built");
+  if (int rc = sync_scene(0)) return rc;
+  Device& dv = s.dev[0];
+  const LbvhBuffers& tree = which ? (s.use_committed ? dv.legacy_bvh : dv.mesh_bvh) : dv.legacy_bvh;
+  if (tree.ntris <= 0 || (tree.ntris > 1 && !tree.nodes)) return fail(GCORE_E_STATE, "gcore_bvh_bench: no LBVH of that kind is built");
   gcore_ray* d_r = nullptr; gcore_HitCpp* d_h = nullptr; int* d_f = nullptr; unsigned long long* d_c = nullptr;
   auto cleanup = [&]() { cudaFree(d_r); cudaFree(d_h); cudaFree(d_f); cudaFree(d_c); };
   cudaError_t e;
   if ((e = cudaMalloc(&d_r, sizeof(gcore_ray) * (size_t)n)) != cudaSuccess || (e = cudaMalloc(&d_h, sizeof(gcore_HitCpp) * (size_t)n)) != cudaSuccess ||
       (e = cudaMalloc(&d_f, 4 * (size_t)n)) != cudaSuccess || (e = cudaMalloc(&d_c, 24)) != cudaSuccess) { cleanup(); return fail_cuda(e, "cudaMalloc bvh bench"); }
-  cudaMemcpyAsync(d_r, rays, sizeof(gcore_ray) * (size_t)n, cudaMemcpyHostToDevice, s.stream);
-  cudaMemsetAsync(d_c, 0, 24, s.stream);
-  e = gcore_dev::launch_bvh_batch_which(n, d_r, t_near, t_far, d_h, d_f, which, d_c, s.stream);          // counting pass (also the warm-up)
+  cudaMemcpyAsync(d_r, rays, sizeof(gcore_ray) * (size_t)n, cudaMemcpyHostToDevice, dv.stream);
+  cudaMemsetAsync(d_c, 0, 24, dv.stream);
+  e = gcore_dev::launch_bvh_batch_which(n, d_r, t_near, t_far, d_h, d_f, which, d_c, dv.stream);          // counting pass (also the warm-up)
   unsigned long long c[3] = {0, 0, 0};
-  if (e == cudaSuccess) e = cudaMemcpyAsync(c, d_c, 24, cudaMemcpyDeviceToHost, s.stream);
-  if (e == cudaSuccess) e = cudaEventRecord(s.ev0, s.stream);
-  for (int k = 0; k < repeat && e == cudaSuccess; k++) e = gcore_dev::launch_bvh_batch_which(n, d_r, t_near, t_far, d_h, d_f, which, nullptr, s.stream);
-  if (e == cudaSuccess) e = cudaEventRecord(s.ev1, s.stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c, d_c, 24, cudaMemcpyDeviceToHost, dv.stream);
+  if (e == cudaSuccess) e = cudaEventRecord(dv.ev0, dv.stream);
+  for (int k = 0; k < repeat && e == cudaSuccess; k++) e = gcore_dev::launch_bvh_batch_which(n, d_r, t_near, t_far, d_h, d_f, which, nullptr, dv.stream);
+  if (e == cudaSuccess) e = cudaEventRecord(dv.ev1, dv.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(dv.stream);
   cleanup();
   if (e != cudaSuccess) return fail_cuda(e, "bvh bench");
-  float ms = 0.f; cudaEventElapsedTime(&ms, s.ev0, s.ev1);
+  float ms = 0.f; cudaEventElapsedTime(&ms, dv.ev0, dv.ev1);
   if (ms_per_launch) *ms_per_launch = ms / (float)repeat;
   if (stats3) { stats3[0] = c[0]; stats3[1] = c[1]; stats3[2] = c[2]; }
   return 0;
+  GC_CATCH_INT
 }
 
 bool gcore_closest_hit(const float a_rayPos[3], const float a_rayDir[3], float t_near, float t_far, gcore_HitCpp* pHit) {   // :196-238
@@ -610,6 +974,11 @@ int gcore_set_analytic_scene(const gcore_sphere* spheres, int nspheres, const gc
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
   if (nspheres < 0 || nspheres > GC_MAX_SPHERES || (nspheres > 0 && !spheres)) return fail(GCORE_E_LIMIT, "gcore_set_analytic_scene: 0..96 spheres");
+  // material ids index g_scn.mats[] unchecked in the kernels (the reference would raise Constraint_Error): refuse bad ones here
+  for (int i = 0; i < nspheres; i++)
+    if (spheres[i].mat < -1 || spheres[i].mat >= GC_MAX_MATERIALS) return fail(GCORE_E_ARG, "gcore_set_analytic_scene: sphere material id outside -1..31");
+  if (box) for (int k = 0; k < 6; k++)
+    if (box->mat_indices[k] < 0 || box->mat_indices[k] >= GC_MAX_MATERIALS) return fail(GCORE_E_ARG, "gcore_set_analytic_scene: box material id outside 0..31");
   s.hs.nspheres = nspheres;
   for (int i = 0; i < nspheres; i++) {
     s.hs.sph[i][0] = spheres[i].pos[0]; s.hs.sph[i][1] = spheres[i].pos[1]; s.hs.sph[i][2] = spheres[i].pos[2]; s.hs.sph[i][3] = spheres[i].r;
@@ -620,7 +989,7 @@ int gcore_set_analytic_scene(const gcore_sphere* spheres, int nspheres, const gc
     memcpy(s.hs.box_mat, box->mat_indices, 24); memcpy(s.hs.box_nrm, box->normals, 72);
   }
   if (fl) { memcpy(s.hs.fl_min, fl->boxMin, 12); memcpy(s.hs.fl_max, fl->boxMax, 12); }
-  s.scene_dirty = true;
+  mark_scene_dirty();
   return 0;
 }
 
@@ -628,6 +997,8 @@ int gcore_set_materials(const gcore_material* materials, int n) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
   if (n < 0 || n > GC_MAX_MATERIALS - 1 || (n > 0 && !materials)) return fail(GCORE_E_LIMIT, "gcore_set_materials: 0..31 materials");
+  for (int i = 0; i < n; i++)
+    if (materials[i].type < GCORE_MAT_NULL || materials[i].type > GCORE_MAT_PHONG) return fail(GCORE_E_ARG, "gcore_set_materials: unknown material type");
   memset(s.hs.mats, 0, sizeof(s.hs.mats));
   for (int i = 0; i < n; i++) {
     art::DMaterial& d = s.hs.mats[i];
@@ -635,7 +1006,7 @@ int gcore_set_materials(const gcore_material* materials, int n) {
     d.param = materials[i].param; d.light = materials[i].light;
   }
   s.hs.nmaterials = n;
-  s.scene_dirty = true;
+  mark_scene_dirty();
   return 0;
 }
 
@@ -643,11 +1014,12 @@ int gcore_set_light(const gcore_light* l) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
   if (!l) return fail(GCORE_E_ARG, "gcore_set_light: null");
+  if (l->shape != GCORE_LIGHT_RECT && l->shape != GCORE_LIGHT_SPHERE) return fail(GCORE_E_ARG, "gcore_set_light: unknown shape");
   s.hs.light_shape = l->shape;
   memcpy(s.hs.l_boxMin, l->boxMin, 12); memcpy(s.hs.l_boxMax, l->boxMax, 12); memcpy(s.hs.l_normal, l->normal, 12);
   memcpy(s.hs.l_center, l->center, 12); s.hs.l_radius = l->radius; memcpy(s.hs.l_intensity, l->intensity, 12);
   s.hs.l_area = l->surfaceArea;
-  s.scene_dirty = true;
+  mark_scene_dirty();
   return 0;
 }
 
@@ -657,13 +1029,14 @@ int gcore_set_camera(const gcore_camera* c) {
   if (!c) return fail(GCORE_E_ARG, "gcore_set_camera: null");
   memcpy(s.hs.cam_pos, c->pos, 12);
   memcpy(s.hs.cam_m, c->matrix, 48);                                   // rows 0..2 of the row-major 4x4
-  s.scene_dirty = true;
+  mark_scene_dirty();
   return 0;
 }
 
 int gcore_set_mesh(const float* pos3, const float* nrm3, int nverts, const int32_t* tris3, int ntris, const float* bbox6, int mesh_mode) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
   if (nverts < 0 || ntris < 0 || (ntris > 0 && (!pos3 || !nrm3 || !tris3))) return fail(GCORE_E_ARG, "gcore_set_mesh: bad arguments");
   if (mesh_mode != GCORE_MESH_REFERENCE_BF && mesh_mode != GCORE_MESH_NEAREST) return fail(GCORE_E_ARG, "gcore_set_mesh: bad mesh_mode");
   s.mesh_pos.assign(pos3, pos3 + 3 * (size_t)nverts);
@@ -672,17 +1045,26 @@ int gcore_set_mesh(const float* pos3, const float* nrm3, int nverts, const int32
   if (bbox6) memcpy(s.mesh_bbox, bbox6, 24);
   else { memset(s.mesh_bbox, 0, 24); fold_bbox(s.mesh_pos, s.mesh_bbox); }
   return install_mesh(mesh_mode);
+  GC_CATCH_INT
 }
 
 int gcore_set_mesh_vsgf(const char* path, const float* matrix16, int mesh_mode) {      // geometry.adb:499-609
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
   if (!path || !matrix16) return fail(GCORE_E_ARG, "gcore_set_mesh_vsgf: null argument");
+  if (mesh_mode != GCORE_MESH_REFERENCE_BF && mesh_mode != GCORE_MESH_NEAREST) return fail(GCORE_E_ARG, "gcore_set_mesh_vsgf: bad mesh_mode");
   FILE* f = fopen(path, "rb");
   if (!f) return fail(GCORE_E_IO, std::string("cannot open ") + path);
   struct { int64_t fileSizeInBytes; int32_t verticesNum, indicesNum, materialsNum, flags; } hd;   // :499-507
   if (fread(&hd, 24, 1, f) != 1 || hd.verticesNum <= 0 || hd.indicesNum < 0) { fclose(f); return fail(GCORE_E_IO, "bad .vsgf header"); }
+  // the counts come from an untrusted file: they must fit the bytes that are really there before anything is allocated
+  fseek(f, 0, SEEK_END);
+  const long long real_size = ftell(f);
+  fseek(f, 24, SEEK_SET);
   const int vn = hd.verticesNum, tn = hd.indicesNum / 3;
+  const long long need = 24 + (long long)vn * (16 + 16 + 8 + (hd.flags != 0 ? 16 : 0)) + (long long)tn * (12 + 4);
+  if (real_size < need) { fclose(f); return fail(GCORE_E_IO, "truncated .vsgf file (header counts exceed the file size)"); }
   std::vector<float> p4(4 * (size_t)vn), n4(4 * (size_t)vn), skip(4 * (size_t)vn);
   std::vector<int> idx(3 * (size_t)tn), mids(tn);
   bool ok = fread(p4.data(), 16, vn, f) == (size_t)vn && fread(n4.data(), 16, vn, f) == (size_t)vn &&
@@ -704,11 +1086,13 @@ int gcore_set_mesh_vsgf(const char* path, const float* matrix16, int mesh_mode) 
   memset(s.mesh_bbox, 0, 24);
   fold_bbox(s.mesh_pos, s.mesh_bbox);
   return install_mesh(mesh_mode);
+  GC_CATCH_INT
 }
 
 int gcore_scene_init_cornell(const char* vsgf_path) {                                     // scene.adb:89-217
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
   const float M_PI_F = 3.14159265358979323846f;
   gcore_light l; memset(&l, 0, sizeof(l));
   l.shape = GCORE_LIGHT_SPHERE;                                                          // g_lightRef := sphLight (:128)
@@ -742,12 +1126,14 @@ int gcore_scene_init_cornell(const char* vsgf_path) {                           
   if ((rc = gcore_set_analytic_scene(sph, 3, &box, nullptr))) return rc;
   if ((rc = gcore_set_materials(mats, 11))) return rc;
   if ((rc = gcore_set_camera(&cam))) return rc;
+  s.use_committed = false;                                                               // the default build traces its own mesh
   M4 mrot = rotation(-M_PI_F / 6.0f, 0.0f, 1.0f, 0.0f);                                  // :194-206
   M4 mscale = ident(), mtans = ident();
   mtans.m[0][3] = -0.75f; mtans.m[1][3] = 0.1f; mtans.m[2][3] = 3.1f; mtans.m[3][3] = 1.0f;
   mscale.m[0][0] = 2.0f; mscale.m[1][1] = 2.0f; mscale.m[2][2] = 2.0f;
   M4 M = mul(mul(mtans, mrot), mscale);
   return gcore_set_mesh_vsgf(vsgf_path, &M.m[0][0], GCORE_MESH_REFERENCE_BF);
+  GC_CATCH_INT
 }
 
 int gcore_get_mesh(float* pos3, float* nrm3, int32_t* tris3, float* bbox6, int* nverts, int* ntris) {
@@ -762,25 +1148,41 @@ int gcore_get_mesh(float* pos3, float* nrm3, int32_t* tris3, float* bbox6, int* 
   return 0;
 }
 
+int gcore_get_committed_scene(float* pos3, int32_t* tris3, float* normals9, int32_t* mats, int* nverts, int* ntris) {
+  State& s = S();
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  const FlatScene& f = s.flat;
+  if (pos3 && !f.verts.empty()) memcpy(pos3, f.verts.data(), f.verts.size() * 4);
+  if (tris3 && !f.tris.empty()) memcpy(tris3, f.tris.data(), f.tris.size() * 4);
+  if (normals9 && !f.n9.empty()) memcpy(normals9, f.n9.data(), f.n9.size() * 4);
+  if (mats && !f.mat.empty()) memcpy(mats, f.mat.data(), f.mat.size() * 4);
+  if (nverts) *nverts = (int)f.verts.size() / 3;
+  if (ntris) *ntris = (int)f.tris.size() / 3;
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- batched scene queries
 int gcore_closest_hit_batch(int n, const gcore_ray* rays, gcore_hit* hits) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
   if (n < 0 || (n > 0 && (!rays || !hits))) return fail(GCORE_E_ARG, "gcore_closest_hit_batch: bad arguments");
   if (n == 0) return 0;
-  if (int rc = sync_scene()) return rc;
+  if (int rc = sync_scene(0)) return rc;
+  Device& dv = s.dev[0];
   gcore_ray* d_r = nullptr; gcore_hit* d_h = nullptr;
   cudaError_t e;
   if ((e = cudaMalloc(&d_r, sizeof(gcore_ray) * (size_t)n)) != cudaSuccess || (e = cudaMalloc(&d_h, sizeof(gcore_hit) * (size_t)n)) != cudaSuccess) {
     cudaFree(d_r); cudaFree(d_h); return fail_cuda(e, "cudaMalloc batch");
   }
-  cudaMemcpyAsync(d_r, rays, sizeof(gcore_ray) * (size_t)n, cudaMemcpyHostToDevice, s.stream);
-  e = gcore_dev::launch_closest_batch(s.hs.mesh_kind, n, d_r, d_h, s.stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_h, sizeof(gcore_hit) * (size_t)n, cudaMemcpyDeviceToHost, s.stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+  cudaMemcpyAsync(d_r, rays, sizeof(gcore_ray) * (size_t)n, cudaMemcpyHostToDevice, dv.stream);
+  e = gcore_dev::launch_closest_batch(active_mesh_kind(), n, d_r, d_h, dv.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_h, sizeof(gcore_hit) * (size_t)n, cudaMemcpyDeviceToHost, dv.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(dv.stream);
   cudaFree(d_r); cudaFree(d_h);
   if (e != cudaSuccess) return fail_cuda(e, "closest batch");
   return 0;
+  GC_CATCH_INT
 }
 
 // ---------------------------------------------------------------------------------------------- rendering
@@ -805,18 +1207,18 @@ int gcore_resize_viewport(int width, int height) {
 int gcore_render_units(int units, gcore_render_stats* stats) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
   return render_units_locked(units, stats);
+  GC_CATCH_INT
 }
 
-int gcore_get_counters(uint64_t* out3) {
+int gcore_get_counters(uint64_t* out4) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
-  if (!out3) return fail(GCORE_E_ARG, "gcore_get_counters: null");
-  if (int rc = ensure_device()) return rc;
-  unsigned long long c[4] = {0, 0, 0, 0};
-  CU(cudaMemcpyAsync(c, s.d_rays, sizeof(c), cudaMemcpyDeviceToHost, s.stream), "memcpy counters");
-  CU(cudaStreamSynchronize(s.stream), "counters sync");
-  out3[0] = c[0]; out3[1] = c[1]; out3[2] = c[2]; out3[3] = c[3];
+  if (!out4) return fail(GCORE_E_ARG, "gcore_get_counters: null");
+  unsigned long long c[6];
+  if (int rc = read_counters(c)) return rc;
+  out4[0] = c[0]; out4[1] = c[1]; out4[2] = c[2]; out4[3] = c[3];
   return 0;
 }
 
@@ -832,10 +1234,8 @@ int gcore_get_bvh_counters(uint64_t* out3) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
   if (!out3) return fail(GCORE_E_ARG, "gcore_get_bvh_counters: null");
-  if (int rc = ensure_device()) return rc;
-  unsigned long long c[6] = {0, 0, 0, 0, 0, 0};
-  CU(cudaMemcpyAsync(c, s.d_rays, sizeof(c), cudaMemcpyDeviceToHost, s.stream), "memcpy counters");
-  CU(cudaStreamSynchronize(s.stream), "counters sync");
+  unsigned long long c[6];
+  if (int rc = read_counters(c)) return rc;
   out3[0] = c[3]; out3[1] = c[4]; out3[2] = c[5];
   return 0;
 }
@@ -849,96 +1249,107 @@ int gcore_get_spp(void) {
 int gcore_read_frame(float* hdr4, uint32_t* ldr) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
   return read_frame_locked(hdr4, ldr, nullptr);
+  GC_CATCH_INT
 }
 
 int gcore_render(const gcore_render_config* cfg, int width, int height, int units, float* hdr4, uint32_t* ldr, gcore_render_stats* stats) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
   int rc;
   if ((rc = gcore_init_render(cfg))) return rc;
-  if (width != s.width || height != s.height || !s.d_accum) { if ((rc = gcore_resize_viewport(width, height))) return rc; }
-  else {                                                               // same viewport: clear like Resize_Viewport does
-    CU(cudaMemsetAsync(s.d_accum, 0, sizeof(float4) * (size_t)s.nslots, s.stream), "memset accum");
-    CU(cudaMemsetAsync(s.d_rays, 0, 6 * sizeof(unsigned long long), s.stream), "memset counters");
-    s.last_counters[0] = s.last_counters[1] = s.last_counters[2] = s.last_counters[3] = 0;
-    s.spp = 0; s.palette_frame = false;
-  }
+  if (width != s.width || height != s.height || !s.dev[0].d_accum) { if ((rc = gcore_resize_viewport(width, height))) return rc; }
+  else if ((rc = alloc_accum())) return rc;                            // same viewport: clear like Resize_Viewport does (allocations are kept)
   gcore_render_stats st; memset(&st, 0, sizeof(st));
   if ((rc = render_units_locked(units, &st))) return rc;
   int launches = st.kernel_launches;
   if ((rc = read_frame_locked(hdr4, ldr, &launches))) return rc;
-  CU(cudaEventRecord(s.ev2, s.stream), "event");
-  CU(cudaEventSynchronize(s.ev2), "event sync");
-  float ms = 0.f; cudaEventElapsedTime(&ms, s.ev0, s.ev2);
+  Device& d0 = s.dev[0];
+  CU(cudaSetDevice(d0.ordinal), "cudaSetDevice");
+  CU(cudaEventRecord(d0.ev2, d0.stream), "event");
+  CU(cudaEventSynchronize(d0.ev2), "event sync");
+  float ms = 0.f; cudaEventElapsedTime(&ms, d0.ev0, d0.ev2);
   st.total_ms = ms; st.kernel_launches = launches;
   if (stats) *stats = st;
   return 0;
+  GC_CATCH_INT
 }
 
 int gcore_load_frame(const float* hdr4, int spp) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
   if (!hdr4 || spp < 0) return fail(GCORE_E_ARG, "gcore_load_frame: bad arguments");
-  if (!s.d_accum) return fail(GCORE_E_STATE, "gcore_load_frame: no viewport");
-  if (int rc = ensure_out_buffers(true, false)) return rc;
-  size_t px = (size_t)s.width * s.height;
-  CU(cudaMemcpyAsync(s.d_hdr, hdr4, sizeof(float4) * px, cudaMemcpyHostToDevice, s.stream), "memcpy hdr");
-  RenderArgs a = make_args();
-  CU(gcore_dev::launch_load_accum(a, s.d_hdr, s.stream), "load_accum_kernel");
-  CU(cudaStreamSynchronize(s.stream), "load_frame sync");
+  if (!s.dev[0].d_accum) return fail(GCORE_E_STATE, "gcore_load_frame: no viewport");
+  const size_t px = (size_t)s.width * s.height;
+  for (int d = 0; d < s.gpu_count; d++) {                              // every device picks its own tiles out of the full frame
+    Device& dv = s.dev[d];
+    if (int rc = ensure_device(d)) return rc;
+    float4* tmp = nullptr;
+    CU(cudaMalloc(&tmp, sizeof(float4) * px), "cudaMalloc frame");
+    cudaError_t e = cudaMemcpyAsync(tmp, hdr4, sizeof(float4) * px, cudaMemcpyHostToDevice, dv.stream);
+    RenderArgs a = make_args(d);
+    if (e == cudaSuccess) e = gcore_dev::launch_load_accum(a, tmp, dv.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dv.stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail_cuda(e, "load_frame");
+  }
   s.spp = spp; s.palette_frame = false;
   return 0;
+  GC_CATCH_INT
 }
 
 int gcore_primary_hits(int width, int height, gcore_hit* hits) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
+  GC_TRY
   if (width <= 0 || height <= 0 || !hits) return fail(GCORE_E_ARG, "gcore_primary_hits: bad arguments");
-  if (int rc = sync_scene()) return rc;
-  const int sw = s.width, sh = s.height, srank = s.rank, sworld = s.world, sslots = s.nslots;
-  s.width = width; s.height = height; s.rank = 0; s.world = 1;
-  RenderArgs a = make_args();
-  s.width = sw; s.height = sh; s.rank = srank; s.world = sworld;
+  if (int rc = sync_scene(0)) return rc;
+  Device& dv = s.dev[0];
+  const int sw = s.width, sh = s.height, srank = s.rank, sworld = s.world, sg = s.gpu_count;
+  s.width = width; s.height = height; s.rank = 0; s.world = 1; s.gpu_count = 1;
+  RenderArgs a = make_args(0);
+  s.width = sw; s.height = sh; s.rank = srank; s.world = sworld; s.gpu_count = sg;
   a.nslots = a.ntiles * GC_TILE * GC_TILE; a.accum = nullptr;
-  (void)sslots;
   gcore_hit* d_h = nullptr;
   size_t px = (size_t)width * height;
   CU(cudaMalloc(&d_h, sizeof(gcore_hit) * px), "cudaMalloc hits");
-  cudaError_t e = gcore_dev::launch_primary_hits(s.hs.mesh_kind, a, d_h, s.stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_h, sizeof(gcore_hit) * px, cudaMemcpyDeviceToHost, s.stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+  cudaError_t e = gcore_dev::launch_primary_hits(active_mesh_kind(), a, d_h, dv.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_h, sizeof(gcore_hit) * px, cudaMemcpyDeviceToHost, dv.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(dv.stream);
   cudaFree(d_h);
   if (e != cudaSuccess) return fail_cuda(e, "primary hits");
   return 0;
+  GC_CATCH_INT
 }
 
 int gcore_accum_device_ptr(void** d_accum, int64_t* nslots) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
-  if (!s.d_accum) return fail(GCORE_E_STATE, "no viewport");
-  if (d_accum) *d_accum = s.d_accum;
-  if (nslots) *nslots = s.nslots;
+  if (!s.dev[0].d_accum) return fail(GCORE_E_STATE, "no viewport");
+  if (d_accum) *d_accum = s.dev[0].d_accum;
+  if (nslots) *nslots = s.dev[0].nslots;
   return 0;
 }
 
 int gcore_resolve_device(void* d_hdr4, void* d_ldr) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
-  if (!s.d_accum) return fail(GCORE_E_STATE, "no viewport");
+  if (!s.dev[0].d_accum) return fail(GCORE_E_STATE, "no viewport");
   if (s.world != 1) return fail(GCORE_E_STATE, "gcore_resolve_device needs world == 1");
-  RenderArgs a = make_args();
-  CU(gcore_dev::launch_resolve(a, resolve_spp(), (float4*)d_hdr4, (uint32_t*)d_ldr, s.stream), "resolve_kernel");
-  return 0;
+  return resolve_to((float4*)d_hdr4, (uint32_t*)d_ldr, nullptr);
 }
 
 int gcore_resolve_gathered_device(const void* d_all_accum, int spp, void* d_hdr4, void* d_ldr) {
   State& s = S();
   std::lock_guard<std::recursive_mutex> lk(s.mu);
   if (!d_all_accum || s.width <= 0) return fail(GCORE_E_ARG, "gcore_resolve_gathered_device: bad arguments");
-  if (int rc = ensure_device()) return rc;
-  RenderArgs a = make_args();
-  CU(gcore_dev::launch_resolve_gathered(a, (const float4*)d_all_accum, spp > 0 ? spp : 1, (float4*)d_hdr4, (uint32_t*)d_ldr, s.stream), "resolve_kernel");
+  if (s.gpu_count != 1) return fail(GCORE_E_STATE, "gcore_resolve_gathered_device is the multi-process path (gpu_count == 1)");
+  if (int rc = ensure_device(0)) return rc;
+  RenderArgs a = make_args(0);
+  CU(gcore_dev::launch_resolve_gathered(a, (const float4*)d_all_accum, spp > 0 ? spp : 1, (float4*)d_hdr4, (uint32_t*)d_ldr, s.dev[0].stream), "resolve_kernel");
   return 0;
 }
 

@@ -44,7 +44,10 @@ cudaError_t launch_debug(int mesh_kind, const RenderArgs& a, cudaStream_t s);
 cudaError_t launch_primary_hits(int mesh_kind, const RenderArgs& a, gcore_hit* d_hits, cudaStream_t s);
 cudaError_t launch_closest_batch(int mesh_kind, int n, const gcore_ray* d_rays, gcore_hit* d_hits, cudaStream_t s);
 // pure triangle query on the committed LBVH (legacy gcore_closest_hit semantics)
-cudaError_t launch_bvh_batch(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, cudaStream_t s);
+// two_sided: Embree's rtcIntersect1 semantics (both faces) instead of the reference's one-sided triangle test
+cudaError_t launch_bvh_batch(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, int two_sided, cudaStream_t s);
+// occlusion query on the committed legacy scene (rtcOccluded1 semantics: any hit inside (t_near, t_far)); d_occluded[i] = 0 / 1
+cudaError_t launch_bvh_occluded(int n, const gcore_ray* d_rays, float t_near, float t_far, int* d_occluded, int two_sided, cudaStream_t s);
 // the same kernel on either LBVH (which: 0 legacy scene, 1 shaded mesh); d_counters != null: also count nodes visited,
 // triangle slots tested and hits into d_counters[0..2]
 cudaError_t launch_bvh_batch_which(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, int which,
@@ -65,23 +68,26 @@ struct WaveBuffers {
   float4* stackA = nullptr;              // [max_depth][wave_total_slots] per-bounce (explicit.xyz, weight.x)
   float2* stackB = nullptr;              //                                                (weight.y, weight.z)
   unsigned int* next_item = nullptr;     // global work counter
+  int*    tstack_ovf = nullptr;          // LBVH scenes: per-slot overflow of the shared short traversal stack
   int     sm_count = 0;
 };
 int wave_total_slots(int sm_count);      // path slots resident on the device (grid * slots per block)
 int wave_max_depth();
+int wave_stack_overflow_entries();       // ints per path slot in WaveBuffers::tstack_ovf
 // `units` DoPass units over this rank's slots (units * nslots < 2^31): wavefront kernel + fold into a.accum
 // count_mesh: statistics level 2 (counters[1] = rays entering the reference's mesh bbox; otherwise = rays that ran the mesh stage)
 cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, int count_mesh, cudaStream_t s);
 
 // ---- lbvh_build.cu ----
 struct LbvhBuffers {                     // device allocations owned by the builder
-  float4* nodes = nullptr; float4* tris = nullptr; float* tri_normals = nullptr;
+  float4* nodes = nullptr; float4* tris = nullptr; float* tri_normals = nullptr; int* tri_mat = nullptr;
   int ntris = 0, nnodes = 0, root = -1;
   size_t bytes = 0;
   float build_ms = 0.0f;
 };
-// verts: device float3 array (world space), tris: device int3 array, normals9: optional device per-triangle nA,nB,nC
-cudaError_t lbvh_build(const float* d_verts, int nverts, const int* d_tris, int ntris, const float* d_normals9,
+// verts: device float3 array (world space), tris: device int3 array, normals9: optional device per-triangle nA,nB,nC,
+// tri_mat: optional device per-triangle material id.  On failure `out` is left empty (nothing half-built).
+cudaError_t lbvh_build(const float* d_verts, int nverts, const int* d_tris, int ntris, const float* d_normals9, const int* d_tri_mat,
                        LbvhBuffers* out, cudaStream_t s);
 void lbvh_free(LbvhBuffers* b);
 

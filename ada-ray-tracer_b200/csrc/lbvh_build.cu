@@ -183,7 +183,7 @@ __global__ void pack_tris_kernel(int n, const int* __restrict__ vals, const floa
   out[3 * (size_t)slot + 2] = make_float4(cx - ax, cy - ay, cz - az, 0.0f);      // edge2 := C - A
 }
 
-#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); return e_; } } while (0)
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); gcore_dev::lbvh_free(out); return e_; } } while (0)
 
 }  // namespace
 
@@ -194,10 +194,11 @@ void lbvh_free(LbvhBuffers* b) {
   if (b->nodes) cudaFree(b->nodes);
   if (b->tris) cudaFree(b->tris);
   if (b->tri_normals) cudaFree(b->tri_normals);
+  if (b->tri_mat) cudaFree(b->tri_mat);
   *b = LbvhBuffers();
 }
 
-cudaError_t lbvh_build(const float* d_verts, int nverts, const int* d_tris, int ntris, const float* d_normals9,
+cudaError_t lbvh_build(const float* d_verts, int nverts, const int* d_tris, int ntris, const float* d_normals9, const int* d_tri_mat,
                        LbvhBuffers* out, cudaStream_t s) {
   (void)nverts;
   lbvh_free(out);
@@ -227,6 +228,11 @@ cudaError_t lbvh_build(const float* d_verts, int nverts, const int* d_tris, int 
     CK(cudaMalloc(&out->tri_normals, 36 * (size_t)n));
     CK(cudaMemcpyAsync(out->tri_normals, d_normals9, 36 * (size_t)n, cudaMemcpyDeviceToDevice, s));
     out->bytes += 36 * (size_t)n;
+  }
+  if (d_tri_mat) {
+    CK(cudaMalloc(&out->tri_mat, 4 * (size_t)n));
+    CK(cudaMemcpyAsync(out->tri_mat, d_tri_mat, 4 * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    out->bytes += 4 * (size_t)n;
   }
   const int B = 256, G = (n + B - 1) / B;
   CK(cudaEventRecord(ev0, s));

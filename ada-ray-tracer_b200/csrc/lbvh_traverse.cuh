@@ -1,6 +1,6 @@
 // lbvh_traverse.cuh -- closest-hit / any-hit traversal of the packed LBVH (replaces Embree's
-// BVHNIntersector1 reached through rtcIntersect1, cpp/embree_connect.cpp:218, and scales
-// geometry.adb:266-323 IntersectMeshBF beyond a handful of triangles).
+// BVHNIntersector1 reached through rtcIntersect1 / rtcOccluded1, cpp/embree_connect.cpp:218,
+// cpp/embree3/rtcore_scene.h:128, and scales geometry.adb:266-323 IntersectMeshBF beyond a handful of triangles).
 //
 // Node (64 B = 4 x float4, one 16-byte vector load each):
 //   n0 = (c0.min.x, c0.min.y, c0.min.z, c0.max.x)
@@ -13,7 +13,8 @@
 // Semantics: nearest hit of the reference's one-sided Moeller-Trumbore test (geometry.adb:231-263) inside the
 // open window (t_min, t_max); exact ties go to the lowest ORIGINAL triangle index.  Box tests only cull: boxes
 // are padded at build time and the slab test is evaluated conservatively, so the result equals testing every
-// triangle.
+// triangle.  TWO_SIDED (legacy seam only, selectable): both faces are hit, like Embree's rtcIntersect1.
+// ANY_HIT (gcore_bvh_occluded_batch): the walk ends at the first accepted hit, like rtcOccluded1.
 #pragma once
 
 namespace art {
@@ -36,6 +37,24 @@ ART_D bool slab_hit(float bminx, float bminy, float bminz, float bmaxx, float bm
 
 struct BvhStats { unsigned int nodes, tris; };     // nodes visited (64 B each), triangle slots tested (48 B each)
 
+// Moeller-Trumbore without the max(det, 1e-25) back-face rejection: det of either sign (Embree semantics)
+ART_D bool intersect_triangle_two_sided(f3 o, f3 d, f3 A, f3 edge1, f3 edge2, float t_min, float t_max, float& t_o, float& u_o, float& v_o) {
+  f3 pvec = cross(d, edge2);
+  f3 tvec = o - A;
+  float det = dot(edge1, pvec);
+  if (det == 0.0f) return false;
+  float invDet = 1.0f / det;
+  float v = dot(tvec, pvec) * invDet;
+  if (!(v > 0.0f)) return false;
+  f3 qvec = cross(tvec, edge1);
+  float u = dot(qvec, d) * invDet;
+  if (!(u > 0.0f && u + v < 1.0f)) return false;
+  float t = dot(edge2, qvec) * invDet;
+  if (t > t_min && t < t_max) { t_o = t; u_o = u; v_o = v; return true; }
+  return false;
+}
+
+template <bool TWO_SIDED>
 ART_D void bvh_leaf_test(const BvhView& bv, int first, int count, f3 o, f3 d, float t_min,
                          float& best_t, int& best_prim, float& best_u, float& best_v, int& best_slot) {
 #pragma unroll 1
@@ -45,8 +64,10 @@ ART_D void bvh_leaf_test(const BvhView& bv, int first, int count, f3 o, f3 d, fl
     float4 e2 = __ldg(&bv.tris[3 * s + 2]);
     int prim = __float_as_int(a.w);
     float t, u, v;
-    // closed upper bound so that equal-t candidates reach the tie rule: test against nextafter(best_t)
-    if (intersect_triangle(o, d, mk3(a.x, a.y, a.z), mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z), t_min, ART_FLT_LAST, t, u, v)) {
+    // closed upper bound so that equal-t candidates reach the tie rule
+    const bool hit = TWO_SIDED ? intersect_triangle_two_sided(o, d, mk3(a.x, a.y, a.z), mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z), t_min, ART_FLT_LAST, t, u, v)
+                               : intersect_triangle(o, d, mk3(a.x, a.y, a.z), mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z), t_min, ART_FLT_LAST, t, u, v);
+    if (hit) {
       if (t < best_t || (t == best_t && best_prim >= 0 && prim < best_prim)) { best_t = t; best_prim = prim; best_u = u; best_v = v; best_slot = s; }
     }
   }
@@ -54,13 +75,13 @@ ART_D void bvh_leaf_test(const BvhView& bv, int first, int count, f3 o, f3 d, fl
 
 // closest hit; prim = -1 when nothing is hit inside (t_min, t_max); slot = position of the winner in the Morton-ordered
 // triangle array (for callers that want its edges)
-template <bool STATS>
+template <bool STATS, bool TWO_SIDED = false, bool ANY_HIT = false>
 ART_D void bvh_closest_slot_t(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, float t_max, int& prim_o, float& t_o, float& u_o, float& v_o, int& slot_o,
                               BvhStats& st) {
   float best_t = t_max; int best_prim = -1; float best_u = 0.0f, best_v = 0.0f; int best_slot = -1;
   if (bv.ntris > 0) {
     if (bv.root < 0) {
-      bvh_leaf_test(bv, 0, bv.ntris, o, d, t_min, best_t, best_prim, best_u, best_v, best_slot);
+      bvh_leaf_test<TWO_SIDED>(bv, 0, bv.ntris, o, d, t_min, best_t, best_prim, best_u, best_v, best_slot);
     } else {
       int stack[LBVH_STACK];
       int sp = 0;
@@ -76,8 +97,9 @@ ART_D void bvh_closest_slot_t(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min
         bool h0 = slab_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, best_t, e0);
         bool h1 = slab_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, best_t, e1);
         if (STATS) { if (h0 && c0 < 0) st.tris += __float_as_int(n3.z); if (h1 && c1 < 0) st.tris += __float_as_int(n3.w); }
-        if (h0 && c0 < 0) { bvh_leaf_test(bv, ~c0, __float_as_int(n3.z), o, d, t_min, best_t, best_prim, best_u, best_v, best_slot); h0 = false; }
-        if (h1 && c1 < 0) { bvh_leaf_test(bv, ~c1, __float_as_int(n3.w), o, d, t_min, best_t, best_prim, best_u, best_v, best_slot); h1 = false; }
+        if (h0 && c0 < 0) { bvh_leaf_test<TWO_SIDED>(bv, ~c0, __float_as_int(n3.z), o, d, t_min, best_t, best_prim, best_u, best_v, best_slot); h0 = false; }
+        if (h1 && c1 < 0) { bvh_leaf_test<TWO_SIDED>(bv, ~c1, __float_as_int(n3.w), o, d, t_min, best_t, best_prim, best_u, best_v, best_slot); h1 = false; }
+        if (ANY_HIT && best_prim >= 0) break;                           // occlusion query: any hit inside the window will do
         if (h0 && h1) {
           // near child first, far child on the stack
           if (e1 < e0) { int t = c0; c0 = c1; c1 = t; }
@@ -89,8 +111,7 @@ ART_D void bvh_closest_slot_t(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min
       }
     }
   }
-  prim_o = (best_t < t_max || best_prim >= 0) ? best_prim : -1;
-  if (best_prim < 0) prim_o = -1;
+  prim_o = best_prim;
   t_o = best_t; u_o = best_u; v_o = best_v; slot_o = best_slot;
 }
 
@@ -104,23 +125,32 @@ ART_D void bvh_closest(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, float
   bvh_closest_slot(bv, o, d, inv, t_min, t_max, prim_o, t_o, u_o, v_o, slot);
 }
 
-// ---- resumable closest-hit traversal: the same walk in slices of at most `max_steps` nodes.  The render kernel advances
-// every pending ray by one slice per stage, so that no stage waits for the longest ray of the block.
-struct BvhCursor {
-  int   node;                       // next node to visit; -1: traversal finished
+// ---- resumable closest-hit traversal for the render kernel: the same walk in slices of at most `max_steps` nodes, so
+// that no stage waits for the longest ray of the block.  The traversal state is small and lives OUTSIDE the thread: the
+// cursor (next node, stack depth) and the running best hit are per path slot in shared memory, the first LBVH_SHORT_STACK
+// stack entries in shared memory too (a short stack covers almost every ray: the far children pending on a near-first
+// walk), deeper entries in a per-slot global overflow area.  Any thread can therefore continue any ray -- each slice is
+// run by the threads of a dense queue of pending rays, not by the slots' owners (render_wave.cuh).
+#define LBVH_SHORT_STACK 8
+#define LBVH_OVERFLOW (LBVH_STACK - LBVH_SHORT_STACK)
+
+struct BvhRayState {
+  int   node;                       // next node to visit; -1: finished; -2: single-leaf tree, not started
   int   sp;
   float best_t; int best_prim; float best_u, best_v;
 };
 
-ART_D void bvh_cursor_begin(const BvhView& bv, float t_max, BvhCursor& c) {
-  c.node = (bv.ntris > 0 && bv.root >= 0) ? bv.root : ((bv.ntris > 0) ? -2 : -1);   // -2: single-leaf tree
+ART_D void bvh_state_begin(const BvhView& bv, float t_max, BvhRayState& c) {
+  c.node = (bv.ntris > 0 && bv.root >= 0) ? bv.root : ((bv.ntris > 0) ? -2 : -1);
   c.sp = 0; c.best_t = t_max; c.best_prim = -1; c.best_u = 0.0f; c.best_v = 0.0f;
 }
 
+// smem_stack: this ray's column of the shared short stack (entry k at smem_stack[k * stride]); ovf: this ray's overflow area
 // returns true when the traversal is complete (c.best_* hold the answer; best_prim < 0: nothing hit)
-ART_D bool bvh_cursor_advance(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, int max_steps, BvhCursor& c, int* stack, BvhStats& st) {
+ART_D bool bvh_state_advance(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, int max_steps, BvhRayState& c,
+                             int* smem_stack, int stride, int* ovf, BvhStats& st) {
   int dummy_slot;
-  if (c.node == -2) { bvh_leaf_test(bv, 0, bv.ntris, o, d, t_min, c.best_t, c.best_prim, c.best_u, c.best_v, dummy_slot); c.node = -1; }
+  if (c.node == -2) { bvh_leaf_test<false>(bv, 0, bv.ntris, o, d, t_min, c.best_t, c.best_prim, c.best_u, c.best_v, dummy_slot); c.node = -1; }
   if (c.node < 0) return true;
   int node = c.node, sp = c.sp;
   float best_t = c.best_t, best_u = c.best_u, best_v = c.best_v; int best_prim = c.best_prim;
@@ -136,15 +166,20 @@ ART_D bool bvh_cursor_advance(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min
     float e0, e1;
     bool h0 = slab_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, best_t, e0);
     bool h1 = slab_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, best_t, e1);
-    if (h0 && c0 < 0) { st.tris += __float_as_int(n3.z); bvh_leaf_test(bv, ~c0, __float_as_int(n3.z), o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h0 = false; }
-    if (h1 && c1 < 0) { st.tris += __float_as_int(n3.w); bvh_leaf_test(bv, ~c1, __float_as_int(n3.w), o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h1 = false; }
+    if (h0 && c0 < 0) { st.tris += __float_as_int(n3.z); bvh_leaf_test<false>(bv, ~c0, __float_as_int(n3.z), o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h0 = false; }
+    if (h1 && c1 < 0) { st.tris += __float_as_int(n3.w); bvh_leaf_test<false>(bv, ~c1, __float_as_int(n3.w), o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h1 = false; }
     if (h0 && h1) {
       if (e1 < e0) { int t = c0; c0 = c1; c1 = t; }                    // near child first, far child on the stack
-      if (sp < LBVH_STACK) stack[sp++] = c1;
+      if (sp < LBVH_SHORT_STACK) { smem_stack[sp * stride] = c1; sp++; }
+      else if (sp < LBVH_STACK) { ovf[sp - LBVH_SHORT_STACK] = c1; sp++; }
       node = c0;
     } else if (h0) node = c0;
     else if (h1) node = c1;
-    else { if (sp == 0) { done = true; break; } node = stack[--sp]; }
+    else {
+      if (sp == 0) { done = true; break; }
+      sp--;
+      node = (sp < LBVH_SHORT_STACK) ? smem_stack[sp * stride] : ovf[sp - LBVH_SHORT_STACK];
+    }
   }
   c.node = done ? -1 : node; c.sp = sp;
   c.best_t = best_t; c.best_prim = best_prim; c.best_u = best_u; c.best_v = best_v;

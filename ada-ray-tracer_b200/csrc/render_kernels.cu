@@ -123,8 +123,9 @@ __global__ void __launch_bounds__(RENDER_BLOCK) closest_kernel(int n, const gcor
 }
 
 // STATS: also count the nodes visited / triangle slots tested (counters[0], [1]) and the hits ([2]); which: 0 = the scene
-// committed through the legacy seam, 1 = the shaded mesh of the renderer
-template <bool STATS>
+// committed through the legacy seam, 1 = the shaded mesh of the renderer.  TWO_SIDED: Embree's two-sided triangle test instead of
+// the reference's one-sided one.  ANY_HIT: occlusion query (found[] only, hits may be null).
+template <bool STATS, bool TWO_SIDED, bool ANY_HIT>
 __global__ void __launch_bounds__(RENDER_BLOCK) bvh_batch_kernel(int n, const gcore_ray* __restrict__ rays, float t_near, float t_far,
                                                                  gcore_HitCpp* __restrict__ hits, int* __restrict__ found, int which,
                                                                  unsigned long long* __restrict__ counters) {
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(RENDER_BLOCK) bvh_batch_kernel(int n, const gc
   f3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f);
   if (i < n) {
     o = ld3(rays[i].origin); d = ld3(rays[i].direction);
-    bvh_closest_slot_t<STATS>(bv, o, d, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), t_near, t_far, prim, t, u, v, slot, st);
+    bvh_closest_slot_t<STATS, TWO_SIDED, ANY_HIT>(bv, o, d, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), t_near, t_far, prim, t, u, v, slot, st);
   }
   if (STATS) {
     unsigned int a = __reduce_add_sync(0xffffffffu, st.nodes), b = __reduce_add_sync(0xffffffffu, st.tris);
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(RENDER_BLOCK) bvh_batch_kernel(int n, const gc
   }
   if (i >= n) return;
   found[i] = (prim >= 0) ? 1 : 0;
-  if (prim >= 0) {
+  if (!ANY_HIT && prim >= 0) {
     gcore_HitCpp hc;
     hc.primIndex = prim; hc.geomIndex = 0; hc.instIndex = 0; hc.t = t;
     const float4 e1 = __ldg(&bv.tris[3 * slot + 1]), e2 = __ldg(&bv.tris[3 * slot + 2]);
@@ -230,17 +231,25 @@ cudaError_t launch_closest_batch(int mesh_kind, int n, const gcore_ray* d_rays, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_bvh_batch(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, cudaStream_t s) {
+cudaError_t launch_bvh_batch(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, int two_sided, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  bvh_batch_kernel<false><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, d_hits, d_found, 0, nullptr);
+  if (two_sided) bvh_batch_kernel<false, true, false><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, d_hits, d_found, 0, nullptr);
+  else bvh_batch_kernel<false, false, false><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, d_hits, d_found, 0, nullptr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bvh_occluded(int n, const gcore_ray* d_rays, float t_near, float t_far, int* d_occluded, int two_sided, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  if (two_sided) bvh_batch_kernel<false, true, true><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, nullptr, d_occluded, 0, nullptr);
+  else bvh_batch_kernel<false, false, true><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, nullptr, d_occluded, 0, nullptr);
   return cudaGetLastError();
 }
 
 cudaError_t launch_bvh_batch_which(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, int which,
                                    unsigned long long* d_counters, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  if (d_counters) bvh_batch_kernel<true><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, d_hits, d_found, which, d_counters);
-  else bvh_batch_kernel<false><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, d_hits, d_found, which, nullptr);
+  if (d_counters) bvh_batch_kernel<true, false, false><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, d_hits, d_found, which, d_counters);
+  else bvh_batch_kernel<false, false, false><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, d_hits, d_found, which, nullptr);
   return cudaGetLastError();
 }
 
@@ -259,14 +268,12 @@ cudaError_t launch_resolve_gathered(const RenderArgs& a, const float4* d_all, in
 // ---- block-synchronous wavefront render (render_wave.cuh) ----
 template <int RT, int MESHK, int NT>
 static cudaError_t launch_wave_t(const art::WaveArgs& wa, int sm_count, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(art::render_wave_kernel<RT, MESHK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(art::WaveSmem<NT>));
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  typedef art::WaveSmem<NT, MESHK == MESHK_BVH> Smem;
+  // a per-device attribute (one host process may drive several GPUs): set it with every launch, it costs a microsecond
+  cudaError_t e = cudaFuncSetAttribute(art::render_wave_kernel<RT, MESHK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  if (e != cudaSuccess) return e;
   const int grid = sm_count * (WAVE_TOTAL_THREADS / NT);                     // persistent: one wave of resident blocks
-  art::render_wave_kernel<RT, MESHK, NT><<<grid, NT, sizeof(art::WaveSmem<NT>), s>>>(wa);
+  art::render_wave_kernel<RT, MESHK, NT><<<grid, NT, sizeof(Smem), s>>>(wa);
   return cudaGetLastError();
 }
 
@@ -289,11 +296,12 @@ static cudaError_t launch_wave_m(int render_type, const art::WaveArgs& wa, int s
 
 int wave_total_slots(int sm_count) { return sm_count * WAVE_TOTAL_THREADS; }   // upper bound for every block shape
 int wave_max_depth() { return WAVE_MAX_DEPTH; }
+int wave_stack_overflow_entries() { return LBVH_OVERFLOW; }
 
 cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, int count_mesh, cudaStream_t s) {
   if (a.nslots <= 0 || units <= 0) return cudaSuccess;
   art::WaveArgs wa;
-  wa.r = a; wa.colbuf = wb.colbuf; wa.stackA = wb.stackA; wa.stackB = wb.stackB; wa.next_item = wb.next_item; wa.units = units; wa.count_mesh = count_mesh;
+  wa.r = a; wa.colbuf = wb.colbuf; wa.stackA = wb.stackA; wa.stackB = wb.stackB; wa.next_item = wb.next_item; wa.tstack_ovf = wb.tstack_ovf; wa.units = units; wa.count_mesh = count_mesh;
   cudaError_t e = cudaMemsetAsync(wb.next_item, 0, sizeof(unsigned int), s);
   if (e != cudaSuccess) return e;
   e = (mesh_kind == 2) ? launch_wave_m<MESHK_BVH, WAVE_NT_BVH>(render_type, wa, wb.sm_count, s)

@@ -62,8 +62,28 @@ enum { ST_DEPTH_MASK = 31, ST_SUB_SHIFT = 5, ST_SPEC = 1 << 7, ST_HASRAY = 1 << 
 #define WAVE_BVH_SLICE 16                 // LBVH scenes: nodes a pending ray advances per mesh stage
 #endif
 
-template <int NT>
-struct WaveSmem {
+// mesh-kind specific part of a block's shared memory
+template <int NT, bool BVH> struct WaveMeshSmem;
+template <int NT> struct WaveMeshSmem<NT, false> {      // constant-memory meshes
+  float mesh_res[WAVE_PAIR_TRIS * NT];  // mesh stage results per candidate (see wave_mesh_stage)
+  short cand[NT];                    // candidate index of the slot's pending ray in the mesh stage, -1: none
+  short mrank[NT];                   // position of a surface slot inside its material bucket (counting sort X -> M1 -> Y)
+  short q_cs[NT], q_cp[NT], q_s[NT];
+  int   cnt_cs, cnt_cp, cnt_m[5];
+};
+template <int NT> struct WaveMeshSmem<NT, true> {       // LBVH meshes: the traversal state of the slot's pending ray lives here, not in a thread
+  float mesh_res[4 * NT];            // running best, then the result: t, u, v, bits(triangle id or -1)
+  int   tnode[NT];                   // cursor: next node to visit
+  short tsp[NT];                     //         stack depth
+  short pend[NT];                    // traversal in flight for the slot's 1 = path ray, 2 = shadow ray (+4: not started yet)
+  int   tstack[LBVH_SHORT_STACK * NT];   // short stack, entry k of slot s at [k * NT + s]; deeper entries: WaveArgs::tstack_ovf
+  short q_t[2][NT];                  // pending traversals: [0] advanced by M1, [1] by M2 (each stage hands its unfinished rays to the other queue)
+  short q_sb[5][NT];                 // surface slots whose shadow query is resolved, per material bucket (consumed by Y)
+  int   cnt_t[2], cnt_m[2][5];       // cnt_m[parity]: bucket sizes for this round's / the next round's Y
+};
+
+template <int NT, bool BVH>
+struct WaveSmem : WaveMeshSmem<NT, BVH> {
   // path ray
   float ox[NT], oy[NT], oz[NT], dx[NT], dy[NT], dz[NT];
   // surface hit + light sample of the current bounce (X -> Y)
@@ -77,14 +97,9 @@ struct WaveSmem {
   int   item[NT];                    // unit * nslots + q, or -1: no item
   unsigned int pixel[NT], sample[NT];   // Philox key word 1 / counter word 0 of the current path
   int   state[NT];                   // depth | sub << 5 | flags
-  // mesh stage results per candidate (see wave_mesh_stage)
-  float mesh_res[WAVE_PAIR_TRIS * NT];
-  short cand[NT];                    // candidate index of the slot's pending ray in the mesh stage, -1: none
   short hmat[NT];
-  short pend[NT];                    // LBVH scenes: traversal in flight for the slot's 1 = path ray, 2 = shadow ray (+4: not started yet)
-  short mrank[NT];                   // position of a surface slot inside its material bucket (counting sort X -> M1 -> Y)
-  short q_r[2][NT], q_cs[NT], q_cp[NT], q_s[NT];
-  int   cnt_r[2], cnt_cs, cnt_cp, cnt_m[5];
+  short q_r[2][NT];
+  int   cnt_r[2];
   int   pool_next, pool_end, exhausted, retired;
 };
 
@@ -108,6 +123,7 @@ struct WaveArgs {
   float4* stackA;                         // [WAVE_MAX_DEPTH][total_slots]  (E.xyz, W.x)
   float2* stackB;                         // [WAVE_MAX_DEPTH][total_slots]  (W.y, W.z)
   unsigned int* next_item;                // global work counter
+  int*    tstack_ovf;                     // LBVH scenes: [total_slots][LBVH_OVERFLOW] traversal stack entries beyond the shared short stack
   int     units;
   int     count_mesh;                     // statistics level 2: count reference-bbox entries (see mesh_candidate)
 };
@@ -226,7 +242,8 @@ ART_D void closest_with_mesh(f3 o, f3 d, f3 inv, int tri_id, float tri_t, float 
     h.prim_type = PRIM_QUAD; h.prim_index = 0; h.matId = 0; h.mat = 4;
     h.normal = mk3(0.0f, -1.0f, 0.0f);
   } else {
-    h.prim_type = PRIM_TRIANGLE; h.prim_index = tri_id; h.matId = 2; h.mat = -1;
+    h.prim_type = PRIM_TRIANGLE; h.prim_index = tri_id; h.mat = -1;
+    h.matId = (MESHK == MESHK_BVH && g_scn.bvh.tri_mat != nullptr) ? __ldg(g_scn.bvh.tri_mat + tri_id) : 2;   // geometry.adb:312 / gcore_set_mesh_material
     const float* n9 = (MESHK == MESHK_CONST) ? g_scn.triN[tri_id] : (g_scn.bvh.tri_normals + 9 * (size_t)tri_id);
     float w = 1.0f - tri_u - tri_v;                                            // geometry.adb:301
     h.normal = mk3(w * n9[0] + tri_v * n9[3] + tri_u * n9[6],
@@ -280,14 +297,14 @@ ART_D void triangle_tuv(f3 o, f3 d, f3 A, f3 edge1, f3 edge2, float& t, float& u
   t = dot(edge2, qvec) * invDet;
 }
 
-// mesh stage (M1 / M2) for the rays queued in q_c.  SHADOW: the ray is the shadow ray of the slot's hit.  Constant-memory
-// meshes of up to WAVE_PAIR_TRIS triangles are tested as (ray, triangle) pairs, one triangle test per thread, so the
+// mesh stage (M1 / M2) of constant-memory meshes for the rays queued in q_c.  SHADOW: the ray is the shadow ray of the slot's
+// hit.  Meshes of up to WAVE_PAIR_TRIS triangles are tested as (ray, triangle) pairs, one triangle test per thread, so the
 // stage is as short as one triangle test (nothing else runs on the SM meanwhile): mesh_res[c * ntris + i] = t of
 // triangle i if its (u, v) test passes, NaN otherwise.  Bigger meshes: one ray per thread, mesh_res[4c..] = t, u, v, id.
 template <int MESHK, bool SHADOW, int NT>
-ART_D void wave_mesh_stage(WaveSmem<NT>& S, const short* q_c, int n_c, int tid) {
+ART_D void wave_mesh_stage(WaveSmem<NT, false>& S, const short* q_c, int n_c, int tid) {
   const int ntris = g_scn.ntris_bf;
-  const bool pair_mode = (MESHK == MESHK_CONST) && (g_scn.pair_group != 0);
+  const bool pair_mode = (g_scn.pair_group != 0);
   const int work = pair_mode ? n_c * ntris : n_c;
   for (int j = tid; j < work; j += NT) {
     const int c = pair_mode ? j / ntris : j;
@@ -316,9 +333,9 @@ ART_D void wave_mesh_stage(WaveSmem<NT>& S, const short* q_c, int n_c, int tid) 
 
 // the mesh candidate of a ray out of mesh_res: the window walk of IntersectMeshBF (geometry.adb:276-296) over the pair
 // results in triangle order (u, v of the selected triangle are re-derived when the caller needs them), or the stored
-// per-ray result
+// per-ray result (LBVH scenes: c = the slot)
 template <int MESHK, int NT>
-ART_D void wave_mesh_result(const WaveSmem<NT>& S, int c, f3 o, f3 d, bool want_uv, int& id, float& t, float& u, float& v) {
+ART_D void wave_mesh_result(const WaveSmem<NT, MESHK == MESHK_BVH>& S, int c, f3 o, f3 d, bool want_uv, int& id, float& t, float& u, float& v) {
   id = -1; t = 0.0f; u = 0.0f; v = 0.0f;
   if (c < 0) return;
   const bool pair_mode = (MESHK == MESHK_CONST) && (g_scn.pair_group != 0);
@@ -343,11 +360,26 @@ ART_D void wave_mesh_result(const WaveSmem<NT>& S, int c, f3 o, f3 d, bool want_
   }
 }
 
+// rank `slot` inside the material bucket of its warp peers and file it in that bucket's queue (LBVH scenes: the counting sort
+// of the surface slots happens at the moment a slot's shadow query is resolved).  All 32 lanes call; pred selects.
+ART_D void bucket_push(bool pred, int bucket, int slot, int* cnt5, short* q, int stride) {
+  const int lane = threadIdx.x & 31;
+  const unsigned m = __match_any_sync(0xffffffffu, pred ? bucket : (-1 - lane));
+  if (pred) {
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&cnt5[bucket], __popc(m));
+    base = __shfl_sync(m, base, leader);
+    q[bucket * stride + base + __popc(m & ((1u << lane) - 1u))] = (short)slot;
+  }
+}
+
 template <int RT, int MESHK, int NT>
 __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kernel(const __grid_constant__ WaveArgs wa) {
   constexpr int NS = WAVE_SLOTS(NT);        // path slots of this block
+  constexpr bool BVH = (MESHK == MESHK_BVH);
   extern __shared__ __align__(16) unsigned char wave_smem_raw[];
-  WaveSmem<NT>& S = *reinterpret_cast<WaveSmem<NT>*>(wave_smem_raw);
+  WaveSmem<NT, BVH>& S = *reinterpret_cast<WaveSmem<NT, BVH>*>(wave_smem_raw);
   const gcore_dev::RenderArgs& a = wa.r;
   const int tid = threadIdx.x;
   const int gslot0 = blockIdx.x * NT;
@@ -369,40 +401,73 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
   unsigned int nrays = 0, nmesh = 0, nbounce = 0;
   const bool cnt = wa.count_mesh != 0;
 
-  // LBVH scenes: thread t owns the traversal of slot t's pending ray; cursor and stack survive from stage to stage
-  constexpr bool BVH = (MESHK == MESHK_BVH);
+  // LBVH scenes: the traversal state of a slot's pending ray lives in shared memory (cursor, running best hit, short stack), so
+  // every mesh stage advances a DENSE queue of pending rays by one slice -- full warps on the traversal code -- and hands the
+  // unfinished ones to the other stage's queue.  A slot whose ray is still in flight sits the next X / Y out.
   static_assert(!BVH || NS == NT, "LBVH scenes: one slot per thread");
   BvhStats tstat; tstat.nodes = 0; tstat.tris = 0; unsigned int ntrav = 0;      // LBVH nodes visited / triangle slots tested / traversals
-  BvhCursor cur; cur.node = -1; cur.sp = 0; cur.best_t = 0.f; cur.best_prim = -1; cur.best_u = 0.f; cur.best_v = 0.f;
-  int tv_stack[BVH ? LBVH_STACK : 1];
-  // one slice of the owner's pending traversal (M1 and M2 of LBVH scenes); rb = ray buffer of the path ray
-  auto bvh_slice = [&](int s) {
-    const int p = S.pend[s];
-    if (p == 0) return;
-    f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
-    if ((p & 3) == 2) {                                                       // shadow ray of Compute_Shadow, ray_tracer.adb:109-113
-      const float ht = S.ht[s];
-      const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
-      d = mk3(S.sx[s], S.sy[s], S.sz[s]);
-      float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
-      epsilon = max2(epsilon, 1.0e-30f);
-      o = hpos + d * epsilon;
-    }
-    if (p & 4) { bvh_cursor_begin(g_scn.bvh, 1000000.0f, cur); ntrav++; }
-    const bool done = bvh_cursor_advance(g_scn.bvh, o, d, mk3(S.ix[s], S.iy[s], S.iz[s]), 0.0f, WAVE_BVH_SLICE, cur, tv_stack, tstat);
-    if (done) {
-      S.mesh_res[4 * s + 0] = cur.best_t; S.mesh_res[4 * s + 1] = cur.best_u; S.mesh_res[4 * s + 2] = cur.best_v;
-      S.mesh_res[4 * s + 3] = __int_as_float(cur.best_prim);
-      S.pend[s] = 0;
-    } else S.pend[s] = (short)(p & 3);
+  int bpar = 0;                                                                 // LBVH scenes: which cnt_m set this round's Y reads
+  // one slice of slot s's pending traversal; returns true when the ray is resolved (result in mesh_res[4s..])
+  auto bvh_slice = [&](int s, int p) -> bool {
+    if constexpr (BVH) {
+      f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
+      float t_clip = 1000000.0f;
+      if ((p & 3) == 2) {                                                     // shadow ray of Compute_Shadow, ray_tracer.adb:109-113
+        const float ht = S.ht[s];
+        const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
+        d = mk3(S.sx[s], S.sy[s], S.sz[s]);
+        float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
+        epsilon = max2(epsilon, 1.0e-30f);
+        o = hpos + d * epsilon;
+        // only a hit with t < maxDist - epsilon2 can change in_shadow (ray_tracer.adb:119-128): a mesh hit beyond it either is not
+        // the closest hit or fails that test itself, so the walk is clipped there (the nearest hit below it is still exact)
+        t_clip = S.sh_thi[s];
+      }
+      BvhRayState c;
+      if (p & 4) { bvh_state_begin(g_scn.bvh, t_clip, c); ntrav++; }
+      else {
+        c.node = S.tnode[s]; c.sp = S.tsp[s];
+        c.best_t = S.mesh_res[4 * s + 0]; c.best_u = S.mesh_res[4 * s + 1]; c.best_v = S.mesh_res[4 * s + 2]; c.best_prim = __float_as_int(S.mesh_res[4 * s + 3]);
+      }
+      const bool done = bvh_state_advance(g_scn.bvh, o, d, mk3(S.ix[s], S.iy[s], S.iz[s]), 0.0f, WAVE_BVH_SLICE, c, &S.tstack[s], NT,
+                                          wa.tstack_ovf + (size_t)(gslot0 + s) * LBVH_OVERFLOW, tstat);
+      S.mesh_res[4 * s + 0] = c.best_t; S.mesh_res[4 * s + 1] = c.best_u; S.mesh_res[4 * s + 2] = c.best_v;
+      S.mesh_res[4 * s + 3] = __int_as_float(c.best_prim);
+      if (done) S.pend[s] = 0;
+      else { S.pend[s] = (short)(p & 3); S.tnode[s] = c.node; S.tsp[s] = (short)c.sp; }
+      return done;
+    } else { (void)s; (void)p; return true; }
+  };
+  // LBVH mesh stage: advance the rays of queue `qi` by one slice; unfinished -> the other queue, resolved shadow rays make their
+  // slot ready for the Y that reads cnt_m[ypar]
+  auto bvh_stage = [&](int qi, int ypar) {
+    if constexpr (BVH) {
+      const int n = S.cnt_t[qi];
+      for (int j0 = 0; j0 < n; j0 += NT) {
+        const int j = j0 + tid;
+        bool more = false, ready = false; int s = 0, bucket = 0;
+        if (j < n) {
+          s = S.q_t[qi][j];
+          const int p = S.pend[s];
+          const bool done = bvh_slice(s, p);
+          more = !done;
+          ready = done && ((p & 3) == 2);
+          bucket = (S.state[s] >> ST_BUCKET_SHIFT) & 7;
+        }
+        queue_push(more, S.q_t[qi ^ 1], &S.cnt_t[qi ^ 1], s);
+        bucket_push(ready, bucket, s, S.cnt_m[ypar], &S.q_sb[0][0], NT);
+      }
+    } else { (void)qi; (void)ypar; }
   };
 
   for (int s = tid; s < NS; s += NT) {
-    S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s; S.cand[s] = -1; S.pend[s] = 0;
+    S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s;
+    if constexpr (BVH) S.pend[s] = 0; else S.cand[s] = -1;
   }
   if (tid == 0) {
-    S.cnt_r[0] = NS; S.cnt_r[1] = 0; S.cnt_cs = 0; S.cnt_cp = 0; S.retired = 0; S.exhausted = 0;
-    for (int b = 0; b < 5; b++) S.cnt_m[b] = 0;
+    S.cnt_r[0] = NS; S.cnt_r[1] = 0; S.retired = 0; S.exhausted = 0;
+    if constexpr (BVH) { S.cnt_t[0] = 0; S.cnt_t[1] = 0; for (int b = 0; b < 5; b++) { S.cnt_m[0][b] = 0; S.cnt_m[1][b] = 0; } }
+    else { S.cnt_cs = 0; S.cnt_cp = 0; for (int b = 0; b < 5; b++) S.cnt_m[b] = 0; }
     unsigned int base, count;
     fetch_batch(base, count);
     if (base >= total_items) { S.exhausted = 1; S.pool_next = 0; S.pool_end = 0; }
@@ -414,7 +479,8 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
   for (;;) {
     // ================================================================= X: closest hit, path end or light sample
     if (tid == 0) {
-      S.cnt_cp = 0;                                                           // consumed by M2 of the previous round
+      if constexpr (BVH) S.cnt_t[1] = 0;                                      // consumed by M2 of the previous round
+      else S.cnt_cp = 0;
       if (!S.exhausted && S.pool_next >= S.pool_end) {                        // refill the item pool (fetched from in Y only)
         unsigned int base, count;
         fetch_batch(base, count);
@@ -425,14 +491,18 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
     for (int s = tid; s < NS; s += NT) {
       int st = S.state[s];
       // LBVH scenes: a slot whose path ray is still being traversed, or that waits for Y (shadow ray in flight), sits this X out
-      const bool on = BVH ? ((st & (ST_HASRAY | ST_SURF)) == ST_HASRAY && S.pend[s] == 0) : ((st & ST_HASRAY) != 0);
-      bool ended = false, push_cs = false;
+      bool on;
+      if constexpr (BVH) on = ((st & (ST_HASRAY | ST_SURF)) == ST_HASRAY) && S.pend[s] == 0;
+      else on = (st & ST_HASRAY) != 0;
+      bool ended = false, push_cs = false, surf = false;
       int bucket = -1 - (tid & 31);                                           // distinct per lane: no peers in the match below
       if (on) {
         const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
         const f3 inv = mk3(S.ix[s], S.iy[s], S.iz[s]);                        // 1.0/direction (geometry.adb:154-156), computed when the ray was made
         int tri_id; float tri_t, tri_u, tri_v;
-        wave_mesh_result<MESHK, NT>(S, BVH ? s : (int)S.cand[s], o, d, true, tri_id, tri_t, tri_u, tri_v);
+        int cidx;
+        if constexpr (BVH) cidx = s; else cidx = (int)S.cand[s];
+        wave_mesh_result<MESHK, NT>(S, cidx, o, d, true, tri_id, tri_t, tri_u, tri_v);
         DHit h;
         closest_with_mesh<MESHK>(o, d, inv, tri_id, tri_t, tri_u, tri_v, true, h);
         nrays++;
@@ -455,6 +525,7 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
         } else {
           // ---- surface: Philox draws, light sample + shadow ray (Compute_Shadow, ray_tracer.adb:100-116)
           nbounce++;
+          surf = true;
           st |= ST_SURF;
           const BounceRand br = bounce_rand(a.seed, S.pixel[s], S.sample[s], (uint32_t)(st & ST_DEPTH_MASK));
           S.r1[s] = br.u2; S.r2[s] = br.u3;
@@ -484,15 +555,17 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
         S.state[s] = st;
       }
       queue_push(ended, S.q_r[par], &S.cnt_r[par], s);
-      if (RT != GCORE_PT_STUPID) {
-        if (BVH) {
-          if (on && (st & ST_SURF)) { if (push_cs) S.pend[s] = 2 | 4; else S.mesh_res[4 * s + 3] = __int_as_float(-1); }
-        } else {
+      if constexpr (BVH) {
+        // a surface slot either starts its shadow traversal (queue of M1) or -- no mesh candidate, or no shadow ray at all -- is ready for Y
+        if (surf) { if (push_cs) S.pend[s] = 2 | 4; else S.mesh_res[4 * s + 3] = __int_as_float(-1); }
+        queue_push(surf && push_cs, S.q_t[0], &S.cnt_t[0], s);
+        bucket_push(surf && !push_cs, bucket, s, S.cnt_m[bpar], &S.q_sb[0][0], NT);
+      } else {
+        if (RT != GCORE_PT_STUPID) {
           const int c = queue_push(push_cs, S.q_cs, &S.cnt_cs, s);
           if (on) S.cand[s] = (short)c;                                       // -1 when the shadow ray skips the mesh
         }
-      }
-      if (!BVH) {                                                             // counting sort by material type: rank inside the bucket
+        // counting sort by material type: rank inside the bucket
         const unsigned m = __match_any_sync(0xffffffffu, bucket);
         if (bucket >= 0) {
           const int lane = tid & 31, leader = __ffs(m) - 1;
@@ -505,46 +578,32 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
     }
     __syncthreads();
 
-    // ================================================================= M1: scatter of the material sort + mesh stage of the shadow rays
-    if (BVH) {
-      // LBVH scenes: advance the pending traversals by one slice, then rank the surface slots whose shadow ray is resolved
-      for (int s = tid; s < NS; s += NT) {
-        bvh_slice(s);
-        int st = S.state[s];
-        const bool ready = ((st & (ST_SURF | ST_HASRAY)) == (ST_SURF | ST_HASRAY)) && S.pend[s] == 0;
-        const int bucket = ready ? ((st >> ST_BUCKET_SHIFT) & 7) : (-1 - (tid & 31));
-        const unsigned m = __match_any_sync(0xffffffffu, bucket);
-        if (ready) {
-          const int lane = tid & 31, leader = __ffs(m) - 1;
-          int base = 0;
-          if (lane == leader) base = atomicAdd(&S.cnt_m[bucket], __popc(m));
-          base = __shfl_sync(m, base, leader);
-          S.mrank[s] = (short)(base + __popc(m & ((1u << lane) - 1u)));
-          S.state[s] = st | ST_READY;
-        }
-      }
-      __syncthreads();
-    }
-    {
+    // ================================================================= M1: mesh stage of the shadow rays
+    if constexpr (BVH) {
+      bvh_stage(0, bpar);
+    } else {
+      // scatter of the material sort + (ray, triangle) pairs
       const int c0 = S.cnt_m[0], c1 = S.cnt_m[1], c2 = S.cnt_m[2], c3 = S.cnt_m[3];
       for (int s = tid; s < NS; s += NT) {
         const int st = S.state[s];
-        if (BVH ? ((st & ST_READY) != 0) : ((st & (ST_SURF | ST_HASRAY)) == (ST_SURF | ST_HASRAY))) {
+        if ((st & (ST_SURF | ST_HASRAY)) == (ST_SURF | ST_HASRAY)) {
           const int b = (st >> ST_BUCKET_SHIFT) & 7;
           const int off_b = (b == 0) ? 0 : (b == 1) ? c0 : (b == 2) ? c0 + c1 : (b == 3) ? c0 + c1 + c2 : c0 + c1 + c2 + c3;
           S.q_s[off_b + S.mrank[s]] = (short)s;
         }
       }
-      if (!BVH && RT != GCORE_PT_STUPID) wave_mesh_stage<MESHK, true, NT>(S, S.q_cs, S.cnt_cs, tid);
+      if (RT != GCORE_PT_STUPID) wave_mesh_stage<MESHK, true, NT>(S, S.q_cs, S.cnt_cs, tid);
     }
     __syncthreads();
 
     // ================================================================= Y: shade (slots sorted by material) + regenerate (queue R)
     {
-      if (tid == 0) S.cnt_cs = 0;
+      int c0, c1, c2, c3, c4;
+      if constexpr (BVH) { c0 = S.cnt_m[bpar][0]; c1 = S.cnt_m[bpar][1]; c2 = S.cnt_m[bpar][2]; c3 = S.cnt_m[bpar][3]; c4 = S.cnt_m[bpar][4]; if (tid == 0) S.cnt_t[0] = 0; }
+      else { c0 = S.cnt_m[0]; c1 = S.cnt_m[1]; c2 = S.cnt_m[2]; c3 = S.cnt_m[3]; c4 = S.cnt_m[4]; if (tid == 0) S.cnt_cs = 0; }
       // surface slots sorted by material type (buckets back to back: only the warps on a bucket boundary see two types),
       // one padding gap, then queue R
-      const int n_surf = S.cnt_m[0] + S.cnt_m[1] + S.cnt_m[2] + S.cnt_m[3] + S.cnt_m[4];
+      const int n_surf = c0 + c1 + c2 + c3 + c4;
       const int n_m = (n_surf + 31) & ~31;
       const int n_r = S.cnt_r[par];
       const int n_all = n_m + ((n_r + 31) & ~31);
@@ -555,7 +614,11 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
           // ------------------------------------------------------------- shade
           const bool on = i < n_surf;
           if (on) {
-            s = S.q_s[i];
+            if constexpr (BVH) {
+              int b = 0, off = 0;
+              if (i >= c0) { b = 1; off = c0; if (i >= c0 + c1) { b = 2; off = c0 + c1; if (i >= c0 + c1 + c2) { b = 3; off = c0 + c1 + c2; if (i >= c0 + c1 + c2 + c3) { b = 4; off = c0 + c1 + c2 + c3; } } } }
+              s = S.q_sb[b][i - off];
+            } else s = S.q_s[i];
             int st = S.state[s];
             const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
             const float ht = S.ht[s];
@@ -571,7 +634,9 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
               epsilon = max2(epsilon, 1.0e-30f);
               const f3 so = hpos + sdir * epsilon;
               int tri_id; float tri_t, tri_u, tri_v;
-              wave_mesh_result<MESHK, NT>(S, BVH ? s : (int)S.cand[s], so, sdir, false, tri_id, tri_t, tri_u, tri_v);
+              int cidx;
+              if constexpr (BVH) cidx = s; else cidx = (int)S.cand[s];
+              wave_mesh_result<MESHK, NT>(S, cidx, so, sdir, false, tri_id, tri_t, tri_u, tri_v);
               DHit hs;                                                        // closest hit; only is_hit / t are read (ray_tracer.adb:117-122)
               closest_with_mesh<MESHK>(so, sdir, mk3(S.ix[s], S.iy[s], S.iz[s]), tri_id, tri_t, 0.0f, 0.0f, false, hs);
               nrays++;
@@ -708,8 +773,9 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
             S.state[s] = st;
           }
         }
-        if (BVH) {
+        if constexpr (BVH) {
           if (newray) { if (push_cp) S.pend[s] = 1 | 4; else S.mesh_res[4 * s + 3] = __int_as_float(-1); }
+          queue_push(newray && push_cp, S.q_t[1], &S.cnt_t[1], s);            // the new path ray starts in M2
         } else {
           const int c = queue_push(push_cp, S.q_cp, &S.cnt_cp, s);
           if (newray) S.cand[s] = (short)c;
@@ -725,9 +791,14 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
 
     // ================================================================= M2: mesh stage of the new path rays
     if (tid == 0) S.cnt_r[par] = 0;
-    if (tid < 5) S.cnt_m[tid] = 0;
-    if (BVH) { for (int s = tid; s < NS; s += NT) bvh_slice(s); }
-    else wave_mesh_stage<MESHK, false, NT>(S, S.q_cp, S.cnt_cp, tid);
+    if constexpr (BVH) {
+      if (tid < 5) S.cnt_m[bpar][tid] = 0;                                    // consumed by Y; shadow rays resolved from here on count for the next Y
+      bvh_stage(1, bpar ^ 1);
+      bpar ^= 1;
+    } else {
+      if (tid < 5) S.cnt_m[tid] = 0;
+      wave_mesh_stage<MESHK, false, NT>(S, S.q_cp, S.cnt_cp, tid);
+    }
     par ^= 1;
     __syncthreads();
   }

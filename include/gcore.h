@@ -49,10 +49,32 @@ GCORE_API int  gcore_add_mesh_3f(const float* a_vertices3f, int a_vertexNum, con
 GCORE_API void gcore_instance_meshes(int a_geomId, const float* a_matrices16f, int a_matrixNum);
 /* replaces embree_connect.cpp:241-244 : flattens the instances and builds the LBVH on the GPU */
 GCORE_API void gcore_commit_scene(void);
-/* replaces embree_connect.cpp:196-238 : nearest hit with t in (t_near, t_far); re-entrant.  One ray per call
- * costs a kernel launch; use gcore_bvh_closest_hit_batch for throughput. */
+/* replaces embree_connect.cpp:196-238 : nearest hit with t in (t_near, t_far); re-entrant (callable from any number
+ * of host threads, scene_hydra_embree.adb:426-446 does so from every Ada task).  One ray per call costs a kernel
+ * launch; use gcore_bvh_closest_hit_batch for throughput.
+ * Semantics of the triangle test: by default the REFERENCE's one-sided Moeller-Trumbore test (geometry.adb:231-263, back
+ * faces are not hit) so that the seam agrees with the analytic build; gcore_set_seam_two_sided(1) selects Embree's
+ * two-sided rtcIntersect1 behaviour.  With no gcore_instance_meshes call before the commit every mesh is instanced once
+ * with the identity (Embree would trace an empty top-level scene, cpp/embree_connect.cpp:147-184). */
 GCORE_API bool gcore_closest_hit(const float a_rayPos[3], const float a_rayDir[3], float t_near, float t_far,
                                  gcore_HitCpp* pHit);
+
+/* ---- extension of the seam ---- */
+/* one-sided (0, default: reference semantics) or two-sided (1: Embree semantics) triangle test of the seam queries */
+GCORE_API int gcore_set_seam_two_sided(int enable);
+/* material id (index into the gcore_set_materials table, default 2 like IntersectMeshBF geometry.adb:312) and optional
+ * per-vertex normals of a mesh added with gcore_add_mesh_3f; call before gcore_commit_scene.  The reference reads the
+ * materials library but returns null for every material (scene_hydra_embree.adb:192-202) and hands the meshes over
+ * without normals (:253-268); without normals the normalised geometric normal cross(B-A, C-A) is shaded. */
+GCORE_API int gcore_set_mesh_material(int meshId, int matId);
+GCORE_API int gcore_set_mesh_normals_3f(int meshId, const float* a_normals3f, int a_vertexNum);
+/* 1: gcore_render* / gcore_closest_hit_batch / gcore_primary_hits trace the COMMITTED scene (all meshes and instances, per-mesh
+ * materials, nearest-hit semantics) together with the analytic primitives of section 2; 0 (default): the gcore_set_mesh mesh.
+ * prim_index of a triangle hit is then the index into the flattened scene (gcore_get_committed_scene). */
+GCORE_API int gcore_use_committed_scene(int enable);
+/* the committed scene as the devices see it: world-space vertices, int3 triangles, 9 normal floats and one material id per
+ * flattened triangle (instances in declaration order, each mesh's triangles in order).  Any pointer may be NULL. */
+GCORE_API int gcore_get_committed_scene(float* pos3, int32_t* tris3, float* normals9, int32_t* mats, int* nverts, int* ntris);
 
 /* ------------------------------------------------------------------------------------------------
  * 2. Scene description of the analytic build (replaces the state held by scene.ads:61-80 Render_Scene)
@@ -129,6 +151,9 @@ GCORE_API int gcore_closest_hit_batch(int n, const gcore_ray* rays, gcore_hit* h
 /* triangle-only query on the committed legacy scene (section 1) for n host rays; found[i] != 0 on a hit */
 GCORE_API int gcore_bvh_closest_hit_batch(int n, const gcore_ray* rays, float t_near, float t_far,
                                           gcore_HitCpp* hits, int32_t* found);
+/* occlusion query on the committed scene for n host rays (the rtcOccluded1 counterpart, cpp/embree3/rtcore_scene.h:128, which the
+ * reference's shim never exposed): occluded[i] = 1 if ANY triangle is hit with t in (t_near, t_far) */
+GCORE_API int gcore_bvh_occluded_batch(int n, const gcore_ray* rays, float t_near, float t_far, int32_t* occluded);
 
 /* ------------------------------------------------------------------------------------------------
  * 4. Rendering (replaces Ray_Tracer: ray_tracer.ads:20-48, ray_tracer.adb:240-320,
@@ -157,10 +182,19 @@ typedef struct gcore_render_stats {
   int32_t  kernel_launches; /* kernels launched by the last call                                       */
 } gcore_render_stats;
 
-/* select the CUDA device for this process (default 0) and the tile partition for multi-process rendering:
+/* select the (first) CUDA device for this process (default 0) and the tile partition for multi-PROCESS rendering:
  * this process renders the 32x32 tiles t with t % world == rank.  Resets the accumulator. */
 GCORE_API int gcore_set_device(int device);
 GCORE_API int gcore_set_partition(int rank, int world);
+/* multi-GPU inside ONE host process (the reference host is a single Ada process, ray_tracer.adb:264-277): devices
+ * [device, device + n) each hold the whole scene and render the tiles t with t % n == d; every call of this header works
+ * unchanged -- gcore_render_units launches on all devices, gcore_read_frame / gcore_render gather the slot-major
+ * accumulators on the first device with one grouped ncclSend/ncclRecv and resolve there.  Results are bit-identical for
+ * every n.  Resets the accumulator.  Exclusive with gcore_set_partition(world > 1). */
+GCORE_API int gcore_set_gpu_count(int n);
+GCORE_API int gcore_get_gpu_count(void);
+/* device time of the render kernels of the last gcore_render_units(.., stats != NULL) per device: out[0..n) milliseconds */
+GCORE_API int gcore_device_kernel_ms(float* out, int n);
 /* Init_Render (ray_tracer.adb:197-200) + the config variables */
 GCORE_API int gcore_init_render(const gcore_render_config* cfg);
 /* Resize_Viewport (ray_tracer.adb:297-320): allocate + zero the accumulator, spp := 0 */
@@ -181,7 +215,8 @@ GCORE_API int gcore_set_stats_level(int level);
 /* GetSPP */
 GCORE_API int gcore_get_spp(void);
 /* resolve the accumulator (ray_tracer.adb:281-291) and copy to HOST buffers, row-major [y*W+x];
- * hdr4 = float4 (r,g,b,spp) per pixel, ldr = R | G<<8 | B<<16.  Either may be NULL.  Only valid with world == 1. */
+ * hdr4 = float4 (r,g,b,spp) per pixel, ldr = R | G<<8 | B<<16.  Either may be NULL.  Gathers first when gcore_set_gpu_count > 1;
+ * not valid under a multi-process partition (world > 1: gather yourself, then gcore_resolve_gathered_device). */
 GCORE_API int gcore_read_frame(float* hdr4, uint32_t* ldr);
 /* checkpoint / resume (the reference only keeps the accumulator in memory and rewrites the BMP every pass, test.adb:63-69):
  * load a frame saved with gcore_read_frame (row-major float4, HOST) into the accumulator of the current viewport and

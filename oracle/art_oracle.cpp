@@ -336,6 +336,7 @@ struct Mesh {                                                                   
   std::vector<float>  tex_x, tex_y;
   std::vector<int>    tri;            // 3 per triangle
   std::vector<int>    material_ids;
+  bool custom_material_ids = false;   // ao_set_mesh_tri_materials: per-triangle ids of a scene committed through the legacy seam
   AABB bbox;                          // zero-initialised: LoadMeshFromVSGF never resets it (geometry.adb:593-603)
 };
 
@@ -470,7 +471,7 @@ Hit mesh_hit_record(const Mesh& m, const LiteGeomHit& nearestHit, int nearestTri
   float ity = w * m.tex_y[ia] + nearestHit.v * m.tex_y[ib] + nearestHit.u * m.tex_y[ic];
   Hit h;
   h.prim_type = AO_PRIM_TRIANGLE; h.prim_index = nearestTriId; h.is_hit = nearestHit.is_hit; h.t = nearestHit.tmin;
-  h.mat = -1; h.matId = 2; h.normal = inorm; h.tx = itx; h.ty = ity;
+  h.mat = -1; h.matId = m.custom_material_ids ? m.material_ids[nearestTriId] : 2; h.normal = inorm; h.tx = itx; h.ty = ity;
   return h;
 }
 
@@ -522,36 +523,78 @@ void tri_bounds(const float* pos, const int32_t* tr, float mn[3], float mx[3]) {
   }
 }
 
-int bvh_build_rec(ao_bvh& b, std::vector<float>& cent, int first, int count) {
-  int id = (int)b.nodes.size();
-  b.nodes.push_back(ao_bvh::Node());
+// Binned-SAH build (16 bins per axis, leaves of at most 4 triangles, median split where the bins cannot separate), single-ray
+// traversal below: the "CPU BVH restatement, not Embree" of SURVEY 8d.  The tree only culls -- results are those of the triangle
+// test and the tie rule -- so the split heuristic changes the speed of the CPU leg, never an answer.
+inline float half_area(const float mn[3], const float mx[3]) {
+  float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+  return dx * dy + dy * dz + dz * dx;
+}
+
+void bvh_build_rec(ao_bvh& b, const std::vector<float>& tb, std::atomic<int>& next_node, int id, int first, int count, int depth) {
+  // tb: per-triangle bounds, 6 floats (min.xyz, max.xyz); the centroid of a triangle is the middle of its box
+  auto cen = [&](int t, int k) { return 0.5f * (tb[6 * (size_t)t + k] + tb[6 * (size_t)t + 3 + k]); };
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   float cmn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int i = first; i < first + count; i++) {
-    int t = b.order[i];
-    float a[3], c[3];
-    tri_bounds(b.pos, b.tris + 3 * t, a, c);
+    const int t = b.order[i];
     for (int k = 0; k < 3; k++) {
-      mn[k] = std::min(mn[k], a[k]); mx[k] = std::max(mx[k], c[k]);
-      cmn[k] = std::min(cmn[k], cent[3 * t + k]); cmx[k] = std::max(cmx[k], cent[3 * t + k]);
+      mn[k] = std::min(mn[k], tb[6 * (size_t)t + k]); mx[k] = std::max(mx[k], tb[6 * (size_t)t + 3 + k]);
+      const float c = cen(t, k);
+      cmn[k] = std::min(cmn[k], c); cmx[k] = std::max(cmx[k], c);
     }
   }
   for (int k = 0; k < 3; k++) { b.nodes[id].bmin[k] = mn[k]; b.nodes[id].bmax[k] = mx[k]; }
   b.nodes[id].first = first; b.nodes[id].count = count; b.nodes[id].left = b.nodes[id].right = -1;
-  if (count <= 4) return id;
-  int axis = 0;
-  float ext = cmx[0] - cmn[0];
-  if (cmx[1] - cmn[1] > ext) { axis = 1; ext = cmx[1] - cmn[1]; }
-  if (cmx[2] - cmn[2] > ext) { axis = 2; ext = cmx[2] - cmn[2]; }
-  if (!(ext > 0.0f)) return id;
-  int mid = first + count / 2;
-  std::nth_element(b.order.begin() + first, b.order.begin() + mid, b.order.begin() + first + count,
-                   [&](int x, int y) { float cx = cent[3 * x + axis], cy = cent[3 * y + axis]; return cx < cy || (cx == cy && x < y); });
+  if (count <= 4) return;
+  const int NB = 16;
+  int cntb[3][NB]; float bmn[3][NB][3], bmx[3][NB][3]; float scale[3];
+  for (int ax = 0; ax < 3; ax++) {
+    const float ext = cmx[ax] - cmn[ax];
+    scale[ax] = (ext > 0.0f) ? (float)NB / ext : 0.0f;
+    for (int q = 0; q < NB; q++) { cntb[ax][q] = 0; for (int k = 0; k < 3; k++) { bmn[ax][q][k] = FLT_MAX; bmx[ax][q][k] = -FLT_MAX; } }
+  }
+  auto bin_of = [&](int t, int ax) { int q = (int)((cen(t, ax) - cmn[ax]) * scale[ax]); if (q >= NB) q = NB - 1; if (q < 0) q = 0; return q; };
+  for (int i = first; i < first + count; i++) {
+    const int t = b.order[i];
+    for (int ax = 0; ax < 3; ax++) {
+      if (scale[ax] == 0.0f) continue;
+      const int q = bin_of(t, ax);
+      cntb[ax][q]++;
+      for (int k = 0; k < 3; k++) { bmn[ax][q][k] = std::min(bmn[ax][q][k], tb[6 * (size_t)t + k]); bmx[ax][q][k] = std::max(bmx[ax][q][k], tb[6 * (size_t)t + 3 + k]); }
+    }
+  }
+  int best_axis = -1, best_split = 0; float best_cost = FLT_MAX;
+  for (int ax = 0; ax < 3; ax++) {
+    if (scale[ax] == 0.0f) continue;
+    float la[NB], ra[NB]; int ln[NB], rn[NB];
+    float amn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, amx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}; int n = 0;
+    for (int q = 0; q < NB; q++) { for (int k = 0; k < 3; k++) { amn[k] = std::min(amn[k], bmn[ax][q][k]); amx[k] = std::max(amx[k], bmx[ax][q][k]); } n += cntb[ax][q]; ln[q] = n; la[q] = n ? half_area(amn, amx) : 0.0f; }
+    for (int k = 0; k < 3; k++) { amn[k] = FLT_MAX; amx[k] = -FLT_MAX; } n = 0;
+    for (int q = NB - 1; q >= 0; q--) { for (int k = 0; k < 3; k++) { amn[k] = std::min(amn[k], bmn[ax][q][k]); amx[k] = std::max(amx[k], bmx[ax][q][k]); } n += cntb[ax][q]; rn[q] = n; ra[q] = n ? half_area(amn, amx) : 0.0f; }
+    for (int q = 0; q + 1 < NB; q++) {
+      if (ln[q] == 0 || rn[q + 1] == 0) continue;
+      const float cost = la[q] * (float)ln[q] + ra[q + 1] * (float)rn[q + 1];
+      if (cost < best_cost) { best_cost = cost; best_axis = ax; best_split = q; }
+    }
+  }
+  int mid = first + count / 2;                               // no axis separates the centroids: split the list in half (keeps the leaves small)
+  if (best_axis >= 0) {
+    auto it = std::partition(b.order.begin() + first, b.order.begin() + first + count, [&](int t) { return bin_of(t, best_axis) <= best_split; });
+    mid = (int)(it - b.order.begin());
+    if (mid == first || mid == first + count) mid = first + count / 2;
+  }
   b.nodes[id].count = 0;
-  int l = bvh_build_rec(b, cent, first, mid - first);
-  int r = bvh_build_rec(b, cent, mid, first + count - mid);
+  const int l = next_node.fetch_add(2), r = l + 1;
   b.nodes[id].left = l; b.nodes[id].right = r;
-  return id;
+  if (depth < 5 && count > 50000) {                          // the top of a big tree: the two halves are independent
+    std::thread th([&]() { bvh_build_rec(b, tb, next_node, l, first, mid - first, depth + 1); });
+    bvh_build_rec(b, tb, next_node, r, mid, first + count - mid, depth + 1);
+    th.join();
+  } else {
+    bvh_build_rec(b, tb, next_node, l, first, mid - first, depth + 1);
+    bvh_build_rec(b, tb, next_node, r, mid, first + count - mid, depth + 1);
+  }
 }
 
 // conservative slab test (double precision, padded) -- only a culling device; exactness of the
@@ -587,7 +630,14 @@ void bvh_closest_one(const ao_bvh& b, const Ray& r, float tmin, float tmax, int*
           LiteGeomHit h = IntersectTriangle(r, f3(b.pos + 3 * tr[0]), f3(b.pos + 3 * tr[1]), f3(b.pos + 3 * tr[2]), tmin, tmax);
           if (h.is_hit && (h.tmin < best_t || (h.tmin == best_t && best >= 0 && t < best))) { best = t; best_t = h.tmin; bu = h.u; bv = h.v; }
         }
-      } else { if (sp < 126) { stack[sp++] = n.left; stack[sp++] = n.right; } }
+      } else if (sp < 126) {
+        // nearer child (along the ray's dominant axis) on top of the stack
+        const ao_bvh::Node& L = b.nodes[n.left]; const ao_bvh::Node& R = b.nodes[n.right];
+        int ax = 0; double am = fabs(inv[0]) < 1e300 ? fabs(1.0 / inv[0]) : 0.0;
+        for (int k = 1; k < 3; k++) { double v = fabs(inv[k]) < 1e300 ? fabs(1.0 / inv[k]) : 0.0; if (v > am) { am = v; ax = k; } }
+        const bool left_first = (inv[ax] >= 0.0) ? (L.bmin[ax] <= R.bmin[ax]) : (L.bmax[ax] >= R.bmax[ax]);
+        if (left_first) { stack[sp++] = n.right; stack[sp++] = n.left; } else { stack[sp++] = n.left; stack[sp++] = n.right; }
+      }
     }
   }
   *prim = best; if (t_out) *t_out = best_t; if (u_out) *u_out = bu; if (v_out) *v_out = bv;
@@ -1139,6 +1189,13 @@ void ao_set_mesh(ao_scene* s, const float* pos3, const float* nrm3, int nverts, 
   fold_bbox(m);
 }
 
+void ao_set_mesh_tri_materials(ao_scene* s, const int32_t* mats, int ntris) {
+  Mesh& m = s->mymesh;
+  if ((size_t)ntris * 3 != m.tri.size()) return;
+  m.material_ids.assign(mats, mats + ntris);
+  m.custom_material_ids = true;
+}
+
 int ao_load_vsgf(ao_scene* s, const char* path, const float* matrix16) {                               // geometry.adb:499-609
   FILE* f = fopen(path, "rb");
   if (!f) return -1;
@@ -1384,14 +1441,17 @@ ao_bvh* ao_bvh_build(const float* pos3, int nverts, const int32_t* tris3, int nt
   b->tris_own.assign(tris3, tris3 + 3 * (size_t)ntris);
   b->pos = b->pos_own.data(); b->tris = b->tris_own.data(); b->ntris = ntris;
   b->order.resize(ntris);
-  std::vector<float> cent(3 * (size_t)ntris);
+  std::vector<float> tb(6 * (size_t)ntris);
   for (int t = 0; t < ntris; t++) {
     b->order[t] = t;
-    float mn[3], mx[3]; tri_bounds(b->pos, b->tris + 3 * t, mn, mx);
-    for (int k = 0; k < 3; k++) cent[3 * (size_t)t + k] = 0.5f * (mn[k] + mx[k]);
+    tri_bounds(b->pos, b->tris + 3 * t, &tb[6 * (size_t)t], &tb[6 * (size_t)t + 3]);
   }
-  b->nodes.reserve(ntris);
-  if (ntris > 0) bvh_build_rec(*b, cent, 0, ntris);
+  if (ntris > 0) {
+    b->nodes.resize(2 * (size_t)ntris);
+    std::atomic<int> next_node(1);
+    bvh_build_rec(*b, tb, next_node, 0, 0, ntris, 0);
+    b->nodes.resize(next_node.load());
+  }
   return b;
 }
 
@@ -1423,6 +1483,31 @@ void ao_bruteforce_closest(const float* pos3, const int32_t* tris3, int ntris, i
     int prim; float t, u, v;
     bruteforce_closest_one(pos3, tris3, ntris, r, tmin, tmax, &prim, &t, &u, &v);
     out_prim[i] = prim; if (out_t) out_t[i] = t; if (out_u) out_u[i] = u; if (out_v) out_v[i] = v;
+  }
+}
+
+// the same query with Embree's two-sided triangle test (det of either sign): the selectable behaviour of the legacy seam
+void ao_bruteforce_closest_two_sided(const float* pos3, const int32_t* tris3, int ntris, int n, const ao_ray* rays, float tmin, float tmax,
+                                     int32_t* out_prim, float* out_t, float* out_u, float* out_v) {
+  for (int i = 0; i < n; i++) {
+    Ray r; r.origin = f3(rays[i].origin); r.direction = f3(rays[i].direction);
+    int best = -1; float best_t = tmax, bu = 0, bv = 0;
+    for (int t = 0; t < ntris; t++) {
+      const int32_t* tr = tris3 + 3 * t;
+      float3 A = f3(pos3 + 3 * tr[0]), B = f3(pos3 + 3 * tr[1]), C = f3(pos3 + 3 * tr[2]);
+      float3 edge1 = B - A, edge2 = C - A;
+      float3 pvec = cross(r.direction, edge2);
+      float3 tvec = r.origin - A;
+      float det = dot(edge1, pvec);
+      if (det == 0.0f) continue;
+      float invDet = 1.0f / det;
+      float v = dot(tvec, pvec) * invDet;
+      float3 qvec = cross(tvec, edge1);
+      float u = dot(qvec, r.direction) * invDet;
+      float tt = dot(edge2, qvec) * invDet;
+      if (v > 0.0f && u > 0.0f && u + v < 1.0f && tt > tmin && tt < best_t) { best = t; best_t = tt; bu = u; bv = v; }
+    }
+    out_prim[i] = best; if (out_t) out_t[i] = best_t; if (out_u) out_u[i] = bu; if (out_v) out_v[i] = bv;
   }
 }
 

@@ -105,6 +105,9 @@ void ao_set_camera   (ao_scene*, const ao_camera*);
 /* mesh given in world space; bbox folded like geometry.adb:593-607 (starting from zero) */
 void ao_set_mesh     (ao_scene*, const float* pos3, const float* nrm3, int nverts,
                       const int32_t* tris3, int ntris);
+/* per-triangle material ids of the mesh set with ao_set_mesh (a scene committed through the legacy seam carries one material per
+ * mesh, scene_hydra_embree.adb:192-202); without it every triangle has matId 2 (geometry.adb:312) */
+void ao_set_mesh_tri_materials(ao_scene*, const int32_t* mats, int ntris);
 /* geometry.adb:499-609; matrix16 row-major; returns 0 on success */
 int  ao_load_vsgf    (ao_scene*, const char* path, const float* matrix16);
 
@@ -143,7 +146,7 @@ float ao_pow(float x, float y);
 void  ao_use_libm(int on);   /* 1: sinf/cosf/powf from libm instead of the deterministic kernels */
 
 /* nearest-hit triangle query on an arbitrary mesh through the oracle's own CPU BVH
- * (semantics of SURVEY C5: nearest front-facing hit, lowest index on exact ties) */
+ * (semantics of SURVEY C5: nearest front-facing hit, lowest index on exact ties); binned-SAH build, single-ray traversal */
 typedef struct ao_bvh ao_bvh;
 ao_bvh* ao_bvh_build(const float* pos3, int nverts, const int32_t* tris3, int ntris);
 void    ao_bvh_free(ao_bvh*);
@@ -151,6 +154,11 @@ void    ao_bvh_free(ao_bvh*);
 void    ao_bvh_closest(const ao_bvh*, int n, const ao_ray* rays, float tmin, float tmax,
                        int32_t* out_prim, float* out_t, float* out_u, float* out_v, int threads);
 void    ao_bruteforce_closest(const float* pos3, const int32_t* tris3, int ntris, int n,
+                       const ao_ray* rays, float tmin, float tmax,
+                       int32_t* out_prim, float* out_t, float* out_u, float* out_v);
+
+/* the same brute-force query with Embree's two-sided triangle test (rtcIntersect1 semantics) */
+void    ao_bruteforce_closest_two_sided(const float* pos3, const int32_t* tris3, int ntris, int n,
                        const ao_ray* rays, float tmin, float tmax,
                        int32_t* out_prim, float* out_t, float* out_u, float* out_v);
 

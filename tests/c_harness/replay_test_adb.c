@@ -9,7 +9,8 @@
  *   loop: Ray_Tracer.Render_Pass    -> gcore_render_units(Threads_Num) + gcore_read_frame   (test.adb:50)
  *         Bitmap.SaveBMP            -> 24-bit BMP, bottom-up, B G R, no padding             (test.adb:63-69, bitmap.adb:31-85)
  *
- * usage: replay_test_adb <libgcore_b200.so> <pyramid2.vsgf> <out.bmp> [width height threads_num passes]
+ * usage: replay_test_adb <libgcore_b200.so> <pyramid2.vsgf> <out.bmp> [width height threads_num passes [gpu_count]]
+ * gpu_count > 1: the same single host process drives that many devices (gcore_set_gpu_count) -- the BMP must not change.
  * prints one line: spp rays kernel_ms; exit code 0 on success.
  */
 #include <dlfcn.h>
@@ -44,13 +45,14 @@ static int save_bmp(const char* path, const uint32_t* data, int w, int h) {     
 int main(int argc, char** argv) {
   if (argc < 4) { fprintf(stderr, "usage: %s lib vsgf out.bmp [w h threads passes]\n", argv[0]); return 2; }
   int w = argc > 4 ? atoi(argv[4]) : 1024, hgt = argc > 5 ? atoi(argv[5]) : 768;
-  int threads_num = argc > 6 ? atoi(argv[6]) : 28, passes = argc > 7 ? atoi(argv[7]) : 1;
+  int threads_num = argc > 6 ? atoi(argv[6]) : 28, passes = argc > 7 ? atoi(argv[7]) : 1, gpus = argc > 8 ? atoi(argv[8]) : 1;
   void* h = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
   if (!h) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 2; }
   LOAD(gcore_scene_init_cornell) LOAD(gcore_init_render) LOAD(gcore_resize_viewport) LOAD(gcore_render_units)
-  LOAD(gcore_read_frame) LOAD(gcore_get_spp) LOAD(gcore_last_error)
+  LOAD(gcore_read_frame) LOAD(gcore_get_spp) LOAD(gcore_last_error) LOAD(gcore_set_gpu_count)
   char err[256];
   #define CK(x) do { int rc_ = (x); if (rc_ != 0) { p_gcore_last_error(err, 256); fprintf(stderr, "%s -> %d: %s\n", #x, rc_, err); return 1; } } while (0)
+  if (gpus > 1) CK(p_gcore_set_gpu_count(gpus));
   CK(p_gcore_scene_init_cornell(argv[2]));
   gcore_render_config cfg = {GCORE_PT_MIS, 1, 8, 0x5EED0003u, {0.f, 0.f, 0.f}};      /* ray_tracer.ads:20-32 defaults */
   CK(p_gcore_init_render(&cfg));

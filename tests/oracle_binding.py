@@ -69,6 +69,8 @@ def lib():
         L.ao_set_camera.argtypes = [vp, vp]
         L.ao_set_mesh.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int]
         L.ao_load_vsgf.argtypes = [vp, C.c_char_p, vp]
+        L.ao_set_mesh_tri_materials.argtypes = [vp, vp, C.c_int]
+        L.ao_bruteforce_closest_two_sided.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_float, C.c_float, vp, vp, vp, vp]
         L.ao_get_counts.argtypes = [vp] + [C.POINTER(C.c_int)] * 4
         for n in ("spheres", "cornell", "materials", "light", "camera"):
             getattr(L, "ao_get_" + n).argtypes = [vp, vp]
@@ -153,6 +155,10 @@ class OracleScene:
         pos = np.ascontiguousarray(pos, np.float32); nrm = np.ascontiguousarray(nrm, np.float32)
         tris = np.ascontiguousarray(tris, np.int32)
         self.L.ao_set_mesh(self.h, _p(pos), _p(nrm), len(pos), _p(tris), len(tris))
+
+    def set_mesh_tri_materials(self, mats):
+        mats = np.ascontiguousarray(mats, np.int32)
+        self.L.ao_set_mesh_tri_materials(self.h, _p(mats), len(mats))
 
     # --- queries ---------------------------------------------------------------------------------
     def closest_hit_batch(self, rays, mesh_mode=MESH_REFERENCE_BF):
