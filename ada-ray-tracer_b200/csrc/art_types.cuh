@@ -19,7 +19,7 @@ enum { MESH_REFERENCE_BF = 0, MESH_NEAREST = 1 };
 struct DMaterial { int type; float color[3]; float color2[3]; float param; int light; };
 
 struct BvhView {                   // packed LBVH (see lbvh.cuh); all pointers are device memory
-  const float4* nodes;             // 4 x float4 per internal node
+  const float4* nodes;             // 2 x float4 per internal node (32-byte quantised node, lbvh_traverse.cuh)
   const float4* tris;              // 3 x float4 per sorted triangle: (A, prim id), (e1, 0), (e2, 0)
   const float*  tri_normals;       // 9 floats per ORIGINAL triangle id: nA, nB, nC
   const int*    tri_mat;           // material id per ORIGINAL triangle id, or null: matId 2 (IntersectMeshBF, geometry.adb:312)

@@ -287,7 +287,7 @@ int alloc_accum() {
 // The colour buffer is sized so that every BASELINE config is one launch (C4: 2048^2 x 64 units x 16 B = 4.3 GB of the
 // 180 GB of HBM3e); longer renders go in chunks of passes.
 #define GC_COLBUF_CAP_BYTES ((size_t)8 << 30)
-int ensure_wave_buffers(int d, size_t items, bool lbvh) {
+int ensure_wave_buffers(int d, size_t items) {
   Device& dv = S().dev[d];
   if (!dv.wave.sm_count) {
     const size_t total_slots = (size_t)gcore_dev::wave_total_slots(dv.sm_count);
@@ -302,8 +302,6 @@ int ensure_wave_buffers(int d, size_t items, bool lbvh) {
     dv.wave.stackA = a; dv.wave.stackB = b; dv.wave.next_item = c;
     dv.wave.sm_count = dv.sm_count;                             // only now: a failed allocation leaves the buffers unset
   }
-  if (lbvh && !dv.wave.tstack_ovf)
-    CU(cudaMalloc(&dv.wave.tstack_ovf, sizeof(int) * (size_t)gcore_dev::wave_total_slots(dv.sm_count) * gcore_dev::wave_stack_overflow_entries()), "cudaMalloc traversal stacks");
   if (items > dv.wave.colbuf_items) {
     if (dv.wave.colbuf) { cudaFree(dv.wave.colbuf); dv.wave.colbuf = nullptr; dv.wave.colbuf_items = 0; }
     CU(cudaMalloc(&dv.wave.colbuf, sizeof(float4) * items), "cudaMalloc colbuf");
@@ -473,7 +471,7 @@ int render_units_locked(int units, gcore_render_stats* stats) {
       CU(gcore_dev::launch_debug(mesh_kind, a, dv.stream), "debug_kernel");                 // Debug_Ray_Tracing overwrites the buffer
       launches += 1;
     } else if (units > 0) {
-      if (int rc = ensure_wave_buffers(d, chunk * (size_t)dv.nslots, mesh_kind == 2)) return rc;
+      if (int rc = ensure_wave_buffers(d, chunk * (size_t)dv.nslots)) return rc;
       int spp = s.spp;
       for (int done = 0; done < units; done += (int)chunk) {
         const int n = (units - done < (int)chunk) ? (units - done) : (int)chunk;
@@ -595,7 +593,7 @@ void release_device(int d) {
   free_accum(d);
   gcore_dev::lbvh_free(&dv.mesh_bvh); gcore_dev::lbvh_free(&dv.legacy_bvh);
   dv.mesh_version = dv.legacy_version = -1;
-  cudaFree(dv.wave.colbuf); cudaFree(dv.wave.stackA); cudaFree(dv.wave.stackB); cudaFree(dv.wave.next_item); cudaFree(dv.wave.tstack_ovf);
+  cudaFree(dv.wave.colbuf); cudaFree(dv.wave.stackA); cudaFree(dv.wave.stackB); cudaFree(dv.wave.next_item);
   dv.wave = WaveBuffers();
   dv.scene_dirty = true;
 }

@@ -61,24 +61,23 @@ int render_kernel_regs(int render_type);
 // row-major HDR frame (device) -> this rank's slot-major accumulator (checkpoint / resume)
 cudaError_t launch_load_accum(const RenderArgs& a, const float4* d_hdr4, cudaStream_t s);
 
-// ---- block-synchronous wavefront render (render_wave.cuh): persistent grid of `grid` blocks ----
+// ---- wavefront render (render_wave.cuh): persistent grid, one wave of resident blocks ----
 struct WaveBuffers {
   float4* colbuf = nullptr;              // [units][nslots] colour of every (pass, pixel) work item
   size_t  colbuf_items = 0;
   float4* stackA = nullptr;              // [max_depth][wave_total_slots] per-bounce (explicit.xyz, weight.x)
   float2* stackB = nullptr;              //                                                (weight.y, weight.z)
   unsigned int* next_item = nullptr;     // global work counter
-  int*    tstack_ovf = nullptr;          // LBVH scenes: per-slot overflow of the shared short traversal stack
   int     sm_count = 0;
 };
 int wave_total_slots(int sm_count);      // path slots resident on the device (grid * slots per block)
 int wave_max_depth();
-int wave_stack_overflow_entries();       // ints per path slot in WaveBuffers::tstack_ovf
 // `units` DoPass units over this rank's slots (units * nslots < 2^31): wavefront kernel + fold into a.accum
 // count_mesh: statistics level 2 (counters[1] = rays entering the reference's mesh bbox; otherwise = rays that ran the mesh stage)
 cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, int count_mesh, cudaStream_t s);
 
 // ---- lbvh_build.cu ----
+#define LBVH_NODE_BYTES 32                // packed node: see lbvh_traverse.cuh
 struct LbvhBuffers {                     // device allocations owned by the builder
   float4* nodes = nullptr; float4* tris = nullptr; float* tri_normals = nullptr; int* tri_mat = nullptr;
   int ntris = 0, nnodes = 0, root = -1;

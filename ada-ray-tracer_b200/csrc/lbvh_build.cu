@@ -6,7 +6,7 @@
 //   3. cub::DeviceRadixSort (key = Morton code, value = triangle id)
 //   4. karras_kernel        binary radix tree (Karras 2012), ties broken by the sorted position
 //   5. refit_kernel         bottom-up AABB union with one atomic flag per internal node
-//   6. pack_kernel          64-byte nodes (both child boxes + child links), 48-byte triangle slots (A|id, e1, e2)
+//   6. pack_kernel          32-byte nodes (both child boxes quantised to 8 bits inside the node's box + child link), 48-byte triangle slots (A|id, e1, e2)
 //
 // Bit-exactness note: e1 = B - A and e2 = C - A are the same binary32 subtractions the reference performs per ray
 // (geometry.adb:238-239); they are done once here.  Boxes are only a culling device and are padded outward.
@@ -156,17 +156,57 @@ __global__ void refit_kernel(int n, const int* __restrict__ vals, const Aabb* __
   }
 }
 
+// biased exponent eb such that 255 * 2^(eb - 127) >= extent (with room for the rounding of the decode)
+__device__ __forceinline__ unsigned int quant_exponent(float extent) {
+  if (!(extent > 0.0f)) return 1u;
+  int e;
+  frexpf(extent * (1.0f / 255.0f) * 1.0001f, &e);                 // extent/255 = m * 2^e with m in [0.5, 1)  ->  2^e >= extent/255
+  int eb = e + 127;
+  return (unsigned int)min(max(eb, 1), 254);
+}
+
+// 32-byte node: the children's boxes as 8-bit offsets inside the node's own box (origin + one power-of-two step per axis).
+//   q0 = (origin.x, origin.y, origin.z, bits: ex | ey << 8 | ez << 16 | leaf flags << 24)        flags: 1 = child 0 is a leaf, 2 = child 1
+//   q1 = bits (c0.lo.x, c0.lo.y, c0.lo.z, c0.hi.x), (c0.hi.y, c0.hi.z, c1.lo.x, c1.lo.y), (c1.lo.z, c1.hi.x, c1.hi.y, c1.hi.z), gamma
+// children are (gamma, gamma + 1): internal node index or sorted triangle slot (Karras: the split position names both).
+// Offsets are rounded outward and checked against the decode the traversal performs, so a decoded box always contains the
+// exact one -- boxes only cull, results stay those of the triangle test.
 __global__ void pack_nodes_kernel(int n, const int* __restrict__ vals, const Aabb* __restrict__ tri_boxes, const Aabb* __restrict__ node_boxes,
                                   const int* __restrict__ left, const int* __restrict__ right, float4* __restrict__ nodes) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
   int lc = left[i], rc = right[i];
-  Aabb a = (lc < 0) ? tri_boxes[vals[~lc]] : node_boxes[lc];
-  Aabb b = (rc < 0) ? tri_boxes[vals[~rc]] : node_boxes[rc];
-  nodes[4 * (size_t)i + 0] = make_float4(a.mn[0], a.mn[1], a.mn[2], a.mx[0]);
-  nodes[4 * (size_t)i + 1] = make_float4(a.mx[1], a.mx[2], b.mn[0], b.mn[1]);
-  nodes[4 * (size_t)i + 2] = make_float4(b.mn[2], b.mx[0], b.mx[1], b.mx[2]);
-  nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(lc), __int_as_float(rc), __int_as_float(1), __int_as_float(1));
+  Aabb c[2];
+  c[0] = (lc < 0) ? tri_boxes[vals[~lc]] : node_boxes[lc];
+  c[1] = (rc < 0) ? tri_boxes[vals[~rc]] : node_boxes[rc];
+  const int gamma = (lc < 0) ? ~lc : lc;
+  float org[3]; unsigned int eb[3]; float step[3];
+  for (int k = 0; k < 3; k++) {
+    org[k] = fminf(c[0].mn[k], c[1].mn[k]);
+    const float hi = fmaxf(c[0].mx[k], c[1].mx[k]);
+    eb[k] = quant_exponent(hi - org[k]);
+    step[k] = __uint_as_float(eb[k] << 23);
+    // the top of the box must be reachable with 255 steps under the float arithmetic of the decode
+    while (eb[k] < 254u && !(org[k] + 255.0f * step[k] >= hi)) { eb[k]++; step[k] = __uint_as_float(eb[k] << 23); }
+  }
+  unsigned int q[12];
+  for (int j = 0; j < 2; j++)
+    for (int k = 0; k < 3; k++) {
+      int lo = (int)floorf((c[j].mn[k] - org[k]) / step[k]);
+      lo = min(max(lo, 0), 255);
+      while (lo > 0 && !(org[k] + (float)lo * step[k] <= c[j].mn[k])) lo--;
+      int hi = (int)ceilf((c[j].mx[k] - org[k]) / step[k]);
+      hi = min(max(hi, 0), 255);
+      while (hi < 255 && !(org[k] + (float)hi * step[k] >= c[j].mx[k])) hi++;
+      q[6 * j + k] = (unsigned int)lo; q[6 * j + 3 + k] = (unsigned int)hi;
+    }
+  const unsigned int flags = (lc < 0 ? 1u : 0u) | (rc < 0 ? 2u : 0u);
+  const unsigned int w0 = eb[0] | (eb[1] << 8) | (eb[2] << 16) | (flags << 24);
+  const unsigned int w1 = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+  const unsigned int w2 = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
+  const unsigned int w3 = q[8] | (q[9] << 8) | (q[10] << 16) | (q[11] << 24);
+  nodes[2 * (size_t)i + 0] = make_float4(org[0], org[1], org[2], __uint_as_float(w0));
+  nodes[2 * (size_t)i + 1] = make_float4(__uint_as_float(w1), __uint_as_float(w2), __uint_as_float(w3), __int_as_float(gamma));
 }
 
 __global__ void pack_tris_kernel(int n, const int* __restrict__ vals, const float* __restrict__ verts, const int* __restrict__ tris,
@@ -250,8 +290,8 @@ cudaError_t lbvh_build(const float* d_verts, int nverts, const int* d_tris, int 
     CK(cudaMalloc(&par_i, 4 * (size_t)(n - 1))); CK(cudaMalloc(&par_l, 4 * (size_t)n));
     CK(cudaMalloc(&flags, 4 * (size_t)(n - 1)));
     CK(cudaMemsetAsync(flags, 0, 4 * (size_t)(n - 1), s));
-    CK(cudaMalloc(&out->nodes, 64 * (size_t)(n - 1)));
-    out->nnodes = n - 1; out->root = 0; out->bytes += 64 * (size_t)(n - 1);
+    CK(cudaMalloc(&out->nodes, LBVH_NODE_BYTES * (size_t)(n - 1)));
+    out->nnodes = n - 1; out->root = 0; out->bytes += LBVH_NODE_BYTES * (size_t)(n - 1);
     const int G1 = (n - 1 + B - 1) / B;
     karras_kernel<<<G1, B, 0, s>>>(keys_sorted, n, left, right, par_i, par_l);
     refit_kernel<<<G, B, 0, s>>>(n, vals_sorted, tri_boxes, left, right, par_i, par_l, node_boxes, flags);

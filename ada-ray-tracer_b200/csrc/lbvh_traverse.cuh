@@ -2,12 +2,11 @@
 // BVHNIntersector1 reached through rtcIntersect1 / rtcOccluded1, cpp/embree_connect.cpp:218,
 // cpp/embree3/rtcore_scene.h:128, and scales geometry.adb:266-323 IntersectMeshBF beyond a handful of triangles).
 //
-// Node (64 B = 4 x float4, one 16-byte vector load each):
-//   n0 = (c0.min.x, c0.min.y, c0.min.z, c0.max.x)
-//   n1 = (c0.max.y, c0.max.z, c1.min.x, c1.min.y)
-//   n2 = (c1.min.z, c1.max.x, c1.max.y, c1.max.z)
-//   n3 = (bits child0, bits child1, -, -)      child >= 0: internal node, child < 0: leaf, ~child = first sorted slot,
-//                                              n3.z/w bits = triangle counts of leaf children
+// Node (32 B = 2 x float4 = one DRAM sector, two 16-byte vector loads): both child boxes quantised to 8 bits per bound
+// inside the node's own box, conservatively (a decoded box contains the exact one):
+//   q0 = (origin.x, origin.y, origin.z, bits: ex | ey << 8 | ez << 16 | leaf flags << 24)   step_k = 2^(e_k - 127)
+//   q1 = bits (c0.lo.xyz, c0.hi.x), (c0.hi.yz, c1.lo.xy), (c1.lo.z, c1.hi.xyz), gamma      bound = origin + byte * step
+//   children = (gamma, gamma + 1): node index, or -- leaf flag set -- sorted triangle slot (one triangle per leaf)
 // Triangle slot (48 B = 3 x float4): (A.xyz, bits prim id), (e1.xyz, 0), (e2.xyz, 0) with e1 = B - A, e2 = C - A.
 //
 // Semantics: nearest hit of the reference's one-sided Moeller-Trumbore test (geometry.adb:231-263) inside the
@@ -35,7 +34,25 @@ ART_D bool slab_hit(float bminx, float bminy, float bminz, float bmaxx, float bm
   return tn <= tf * 1.00001f + 1.0e-6f;
 }
 
-struct BvhStats { unsigned int nodes, tris; };     // nodes visited (64 B each), triangle slots tested (48 B each)
+struct BvhStats { unsigned int nodes, tris; };     // nodes visited (32 B each), triangle slots tested (48 B each)
+
+struct BvhNode2 { float b0[6], b1[6]; int c0, c1; };          // decoded: child boxes (min.xyz, max.xyz), child links (>= 0 node, < 0: ~slot)
+
+ART_D BvhNode2 bvh_fetch_node(const BvhView& bv, int node) {
+  const float4 q0 = __ldg(&bv.nodes[2 * node + 0]);
+  const float4 q1 = __ldg(&bv.nodes[2 * node + 1]);
+  const unsigned int w0 = __float_as_uint(q0.w), a = __float_as_uint(q1.x), b = __float_as_uint(q1.y), c = __float_as_uint(q1.z);
+  const float sx = __uint_as_float((w0 & 255u) << 23), sy = __uint_as_float(((w0 >> 8) & 255u) << 23), sz = __uint_as_float(((w0 >> 16) & 255u) << 23);
+  BvhNode2 n;
+  n.b0[0] = q0.x + (float)(a & 255u) * sx;         n.b0[1] = q0.y + (float)((a >> 8) & 255u) * sy;  n.b0[2] = q0.z + (float)((a >> 16) & 255u) * sz;
+  n.b0[3] = q0.x + (float)(a >> 24) * sx;          n.b0[4] = q0.y + (float)(b & 255u) * sy;         n.b0[5] = q0.z + (float)((b >> 8) & 255u) * sz;
+  n.b1[0] = q0.x + (float)((b >> 16) & 255u) * sx; n.b1[1] = q0.y + (float)(b >> 24) * sy;          n.b1[2] = q0.z + (float)(c & 255u) * sz;
+  n.b1[3] = q0.x + (float)((c >> 8) & 255u) * sx;  n.b1[4] = q0.y + (float)((c >> 16) & 255u) * sy; n.b1[5] = q0.z + (float)(c >> 24) * sz;
+  const int gamma = __float_as_int(q1.w);
+  n.c0 = (w0 & (1u << 24)) ? ~gamma : gamma;
+  n.c1 = (w0 & (2u << 24)) ? ~(gamma + 1) : (gamma + 1);
+  return n;
+}
 
 // Moeller-Trumbore without the max(det, 1e-25) back-face rejection: det of either sign (Embree semantics)
 ART_D bool intersect_triangle_two_sided(f3 o, f3 d, f3 A, f3 edge1, f3 edge2, float t_min, float t_max, float& t_o, float& u_o, float& v_o) {
@@ -88,17 +105,14 @@ ART_D void bvh_closest_slot_t(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min
       int node = bv.root;
       for (;;) {
         if (STATS) st.nodes++;
-        float4 n0 = __ldg(&bv.nodes[4 * node + 0]);
-        float4 n1 = __ldg(&bv.nodes[4 * node + 1]);
-        float4 n2 = __ldg(&bv.nodes[4 * node + 2]);
-        float4 n3 = __ldg(&bv.nodes[4 * node + 3]);
-        int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+        const BvhNode2 nd = bvh_fetch_node(bv, node);
+        int c0 = nd.c0, c1 = nd.c1;
         float e0, e1;
-        bool h0 = slab_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, best_t, e0);
-        bool h1 = slab_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, best_t, e1);
-        if (STATS) { if (h0 && c0 < 0) st.tris += __float_as_int(n3.z); if (h1 && c1 < 0) st.tris += __float_as_int(n3.w); }
-        if (h0 && c0 < 0) { bvh_leaf_test<TWO_SIDED>(bv, ~c0, __float_as_int(n3.z), o, d, t_min, best_t, best_prim, best_u, best_v, best_slot); h0 = false; }
-        if (h1 && c1 < 0) { bvh_leaf_test<TWO_SIDED>(bv, ~c1, __float_as_int(n3.w), o, d, t_min, best_t, best_prim, best_u, best_v, best_slot); h1 = false; }
+        bool h0 = slab_hit(nd.b0[0], nd.b0[1], nd.b0[2], nd.b0[3], nd.b0[4], nd.b0[5], o, inv, t_min, best_t, e0);
+        bool h1 = slab_hit(nd.b1[0], nd.b1[1], nd.b1[2], nd.b1[3], nd.b1[4], nd.b1[5], o, inv, t_min, best_t, e1);
+        if (STATS) { if (h0 && c0 < 0) st.tris += 1; if (h1 && c1 < 0) st.tris += 1; }
+        if (h0 && c0 < 0) { bvh_leaf_test<TWO_SIDED>(bv, ~c0, 1, o, d, t_min, best_t, best_prim, best_u, best_v, best_slot); h0 = false; }
+        if (h1 && c1 < 0) { bvh_leaf_test<TWO_SIDED>(bv, ~c1, 1, o, d, t_min, best_t, best_prim, best_u, best_v, best_slot); h1 = false; }
         if (ANY_HIT && best_prim >= 0) break;                           // occlusion query: any hit inside the window will do
         if (h0 && h1) {
           // near child first, far child on the stack
@@ -158,16 +172,13 @@ ART_D bool bvh_state_advance(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min,
 #pragma unroll 1
   for (int step = 0; step < max_steps; step++) {
     st.nodes++;
-    float4 n0 = __ldg(&bv.nodes[4 * node + 0]);
-    float4 n1 = __ldg(&bv.nodes[4 * node + 1]);
-    float4 n2 = __ldg(&bv.nodes[4 * node + 2]);
-    float4 n3 = __ldg(&bv.nodes[4 * node + 3]);
-    int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+    const BvhNode2 nd = bvh_fetch_node(bv, node);
+    int c0 = nd.c0, c1 = nd.c1;
     float e0, e1;
-    bool h0 = slab_hit(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, o, inv, t_min, best_t, e0);
-    bool h1 = slab_hit(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, o, inv, t_min, best_t, e1);
-    if (h0 && c0 < 0) { st.tris += __float_as_int(n3.z); bvh_leaf_test<false>(bv, ~c0, __float_as_int(n3.z), o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h0 = false; }
-    if (h1 && c1 < 0) { st.tris += __float_as_int(n3.w); bvh_leaf_test<false>(bv, ~c1, __float_as_int(n3.w), o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h1 = false; }
+    bool h0 = slab_hit(nd.b0[0], nd.b0[1], nd.b0[2], nd.b0[3], nd.b0[4], nd.b0[5], o, inv, t_min, best_t, e0);
+    bool h1 = slab_hit(nd.b1[0], nd.b1[1], nd.b1[2], nd.b1[3], nd.b1[4], nd.b1[5], o, inv, t_min, best_t, e1);
+    if (h0 && c0 < 0) { st.tris += 1; bvh_leaf_test<false>(bv, ~c0, 1, o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h0 = false; }
+    if (h1 && c1 < 0) { st.tris += 1; bvh_leaf_test<false>(bv, ~c1, 1, o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h1 = false; }
     if (h0 && h1) {
       if (e1 < e0) { int t = c0; c0 = c1; c1 = t; }                    // near child first, far child on the stack
       if (sp < LBVH_SHORT_STACK) { smem_stack[sp * stride] = c1; sp++; }

@@ -265,47 +265,49 @@ cudaError_t launch_resolve_gathered(const RenderArgs& a, const float4* d_all, in
   return cudaGetLastError();
 }
 
-// ---- block-synchronous wavefront render (render_wave.cuh) ----
-template <int RT, int MESHK, int NT>
-static cudaError_t launch_wave_t(const art::WaveArgs& wa, int sm_count, cudaStream_t s) {
-  typedef art::WaveSmem<NT, MESHK == MESHK_BVH> Smem;
-  // a per-device attribute (one host process may drive several GPUs): set it with every launch, it costs a microsecond
-  cudaError_t e = cudaFuncSetAttribute(art::render_wave_kernel<RT, MESHK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-  if (e != cudaSuccess) return e;
-  const int grid = sm_count * (WAVE_TOTAL_THREADS / NT);                     // persistent: one wave of resident blocks
-  art::render_wave_kernel<RT, MESHK, NT><<<grid, NT, sizeof(Smem), s>>>(wa);
-  return cudaGetLastError();
-}
-
-template <int MESHK, int NT>
-static cudaError_t launch_wave_m(int render_type, const art::WaveArgs& wa, int sm_count, cudaStream_t s) {
-  switch (render_type) {
-    case GCORE_PT_STUPID: return launch_wave_t<GCORE_PT_STUPID, MESHK, NT>(wa, sm_count, s);
-    case GCORE_PT_SHADOW: return launch_wave_t<GCORE_PT_SHADOW, MESHK, NT>(wa, sm_count, s);
-    case GCORE_PT_MIS:    return launch_wave_t<GCORE_PT_MIS, MESHK, NT>(wa, sm_count, s);
-    default: return cudaErrorInvalidValue;
-  }
-}
-
+// ---- wavefront render (render_wave.cuh) ----
 #ifndef WAVE_NT_CONST
 #define WAVE_NT_CONST 1024
 #endif
-#ifndef WAVE_NT_BVH
-#define WAVE_NT_BVH 256
-#endif
 
-int wave_total_slots(int sm_count) { return sm_count * WAVE_TOTAL_THREADS; }   // upper bound for every block shape
+template <int RT>
+static cudaError_t launch_wave_const(const art::WaveArgs& wa, int sm_count, cudaStream_t s) {
+  constexpr int NT = WAVE_NT_CONST;
+  typedef art::WaveSmem<NT> Smem;
+  // a per-device attribute (one host process may drive several GPUs): set it with every launch, it costs a microsecond
+  cudaError_t e = cudaFuncSetAttribute(art::render_wave_kernel<RT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  if (e != cudaSuccess) return e;
+  const int grid = sm_count * (WAVE_TOTAL_THREADS / NT);                     // persistent: one wave of resident blocks
+  art::render_wave_kernel<RT, NT><<<grid, NT, sizeof(Smem), s>>>(wa);
+  return cudaGetLastError();
+}
+
+template <int RT>
+static cudaError_t launch_wave_bvh(const art::WaveArgs& wa, int sm_count, cudaStream_t s) {
+  constexpr int NT = BVH_SHADE_THREADS + BVH_TRAV_THREADS;
+  cudaError_t e = cudaFuncSetAttribute(art::render_bvh_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(art::BvhWaveSmem));
+  if (e != cudaSuccess) return e;
+  const int grid = sm_count * (WAVE_TOTAL_THREADS / NT);
+  art::render_bvh_kernel<RT><<<grid, NT, sizeof(art::BvhWaveSmem), s>>>(wa);
+  return cudaGetLastError();
+}
+
+int wave_total_slots(int sm_count) { return sm_count * WAVE_TOTAL_THREADS; }   // path slots resident on a device, either kernel
 int wave_max_depth() { return WAVE_MAX_DEPTH; }
-int wave_stack_overflow_entries() { return LBVH_OVERFLOW; }
 
 cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, int count_mesh, cudaStream_t s) {
   if (a.nslots <= 0 || units <= 0) return cudaSuccess;
   art::WaveArgs wa;
-  wa.r = a; wa.colbuf = wb.colbuf; wa.stackA = wb.stackA; wa.stackB = wb.stackB; wa.next_item = wb.next_item; wa.tstack_ovf = wb.tstack_ovf; wa.units = units; wa.count_mesh = count_mesh;
+  wa.r = a; wa.colbuf = wb.colbuf; wa.stackA = wb.stackA; wa.stackB = wb.stackB; wa.next_item = wb.next_item; wa.units = units; wa.count_mesh = count_mesh;
   cudaError_t e = cudaMemsetAsync(wb.next_item, 0, sizeof(unsigned int), s);
   if (e != cudaSuccess) return e;
-  e = (mesh_kind == 2) ? launch_wave_m<MESHK_BVH, WAVE_NT_BVH>(render_type, wa, wb.sm_count, s)
-                       : launch_wave_m<MESHK_CONST, WAVE_NT_CONST>(render_type, wa, wb.sm_count, s);
+  const bool bvh = (mesh_kind == 2);
+  switch (render_type) {
+    case GCORE_PT_STUPID: e = bvh ? launch_wave_bvh<GCORE_PT_STUPID>(wa, wb.sm_count, s) : launch_wave_const<GCORE_PT_STUPID>(wa, wb.sm_count, s); break;
+    case GCORE_PT_SHADOW: e = bvh ? launch_wave_bvh<GCORE_PT_SHADOW>(wa, wb.sm_count, s) : launch_wave_const<GCORE_PT_SHADOW>(wa, wb.sm_count, s); break;
+    case GCORE_PT_MIS:    e = bvh ? launch_wave_bvh<GCORE_PT_MIS>(wa, wb.sm_count, s) : launch_wave_const<GCORE_PT_MIS>(wa, wb.sm_count, s); break;
+    default: e = cudaErrorInvalidValue;
+  }
   if (e != cudaSuccess) return e;
   art::fold_kernel<<<blocks_for(a.nslots, 256), 256, 0, s>>>(a, wb.colbuf, units);
   return cudaGetLastError();
@@ -315,9 +317,9 @@ int render_kernel_regs(int render_type) {
   cudaFuncAttributes at;
   cudaError_t e;
   switch (render_type) {
-    case GCORE_PT_STUPID: e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_STUPID, MESHK_CONST, WAVE_NT_CONST>); break;
-    case GCORE_PT_SHADOW: e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_SHADOW, MESHK_CONST, WAVE_NT_CONST>); break;
-    default:              e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_MIS, MESHK_CONST, WAVE_NT_CONST>); break;
+    case GCORE_PT_STUPID: e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_STUPID, WAVE_NT_CONST>); break;
+    case GCORE_PT_SHADOW: e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_SHADOW, WAVE_NT_CONST>); break;
+    default:              e = cudaFuncGetAttributes(&at, art::render_wave_kernel<GCORE_PT_MIS, WAVE_NT_CONST>); break;
   }
   if (e != cudaSuccess) { cudaGetLastError(); return -1; }
   return at.numRegs;

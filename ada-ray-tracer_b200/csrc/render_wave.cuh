@@ -1,4 +1,4 @@
-// render_wave.cuh -- the render hot path as a block-synchronous wavefront (K1+K2+K4+K5+K6a of SURVEY 2b).
+// render_wave.cuh -- the render hot path as a wavefront over persistent path slots (K1+K2+K4+K5+K6a of SURVEY 2b).
 //
 // Replaces ray_tracer-integrators.adb:25-301 (DoPass + the three PathTrace variants), ray_tracer.adb:61-132 (camera rays,
 // Compute_Shadow) and the Ada task pool of ray_tracer.adb:142-194.
@@ -6,22 +6,31 @@
 // Why this shape.  A one-thread-per-pixel megakernel of this path runs with 12.7 of 32 lanes active and spends 47 % of
 // its stall samples waiting for instructions (profiles/r01_render.md): lanes of a warp sit on different
 // materials and bounce depths, the 8-triangle mesh loop runs for ~2 lanes, and 60 KB of inlined code thrash the 32 KB
-// instruction cache.  Here a persistent block owns NS path slots whose state lives in shared memory (SoA), and walks
-// all of them through two wide and two narrow stages per bounce, separated by __syncthreads().  Between stages slots
-// are re-packed into dense queues, so every stage runs with full warps on one small piece of code that all warps of the
-// block execute at the same time:
+// instruction cache.  Here a persistent block owns NS path slots whose state lives in shared memory (SoA) and walks them
+// through stages; between stages slots are re-packed into dense queues, so every stage runs with full warps on one small
+// piece of code:
 //
-//   X   extend       all slots with a ray : mesh candidate of M2 merged with spheres, Cornell box, flat light
+//   X   extend       all slots with a resolved path ray : mesh candidate merged with spheres, Cornell box, flat light
 //                    (scene.adb:56-86); miss / emitter -> the path ends (queue R); surface -> Philox draws, Lights.Sample,
 //                    shadow ray (ray_tracer.adb:100-116), bucket by material type
-//   M1  shadow mesh  (shadow ray, triangle) pairs : one triangle test per thread (geometry.adb:231-263) / LBVH traversal
 //   Y   shade        surface slots sorted by material : shadow spheres/box + in_shadow rule (ray_tracer.adb:117-128),
 //                    EvalBxDF/EvalPDF + MIS (integrators.adb:161-178, 251-287), SampleAndEvalBxDF (:116,183,291), next
 //                    ray;  in the same interval the spare threads take queue R: unwind the finished path
 //                    (integrators.adb:124,191,299), add its radiance to the pixel-pass colour in the reference's order
 //                    (:42-51), publish the colour when the pass is complete, fetch the next work item, camera ray
 //                    (ray_tracer.adb:61-97)
-//   M2  path mesh    (path ray, triangle) pairs for the rays made in Y
+//
+// and the mesh queries in between, in one of two ways:
+//
+//   render_wave_kernel  meshes in constant memory (<= 64 triangles, the reference scenes): block-synchronous, two narrow stages
+//                       M1 (shadow rays) / M2 (path rays) of (ray, triangle) pairs, one triangle test per thread
+//                       (geometry.adb:231-263), four __syncthreads() per bounce, 1024 slots x 1024 threads per SM.
+//   render_bvh_kernel   meshes behind the LBVH: traversal is a chain of dependent memory fetches, so it is taken OUT of the
+//                       barrier-synchronous stages.  Half of the block's warps are persistent traversal warps: every lane keeps
+//                       one ray's walk in registers (short stack in shared memory), pops the next pending ray from a
+//                       shared-memory ring the moment its own finishes (ballot over idle lanes + one CAS per warp), and never
+//                       meets a barrier; the other half runs X / Y over the slots whose rays are resolved, synchronised by a
+//                       named barrier of their own.  Slots with a ray in the tree simply sit the shading rounds out.
 //
 // A work item is one DoPass of one pixel (4 fixed sub-pixel paths, or 1): items are handed out from a global counter,
 // so no slot idles while others finish long paths, and the colour of item (pass k, pixel q) goes to colbuf[k][q].
@@ -35,10 +44,8 @@
 
 namespace art {
 
-// Block shape: NT threads = NT path slots per block, 1024 / NT blocks per SM (template parameter of the kernel).
-//   constant-memory meshes: 1024 x 1 -- the biggest slot pool wins (measured 256x4 105 ms, 384x3 93, 512x2 85.5, 1024x1 77.4)
-//   LBVH meshes:            256 x 4 -- the traversal slices are latency-bound, several blocks per SM overlap them with the
-//                           other blocks' stages (C5 with 16-node slices: 128x8 1738 ms, 256x4 1535, 512x2 1582)
+// Block shape of render_wave_kernel: NT threads = NT path slots per block, 1024 / NT blocks per SM.
+//   1024 x 1 -- the biggest slot pool wins (measured 256x4 105 ms, 384x3 93, 512x2 85.5, 1024x1 77.4)
 #define WAVE_TOTAL_THREADS 1024
 #ifndef SPH_UNROLL
 #define SPH_UNROLL 1
@@ -55,52 +62,59 @@ constexpr int kSphereUnroll = SPH_UNROLL;     // unroll factor of the sphere loo
 
 #define WAVE_PAIR_TRIS 8                  // constant-memory meshes up to this size are tested as (ray, triangle) pairs
 
-enum { ST_DEPTH_MASK = 31, ST_SUB_SHIFT = 5, ST_SPEC = 1 << 7, ST_HASRAY = 1 << 8, ST_FOLD = 1 << 9, ST_SURF = 1 << 10,
-       ST_BUCKET_SHIFT = 11 /* 3 bits: material bucket of a surface slot */, ST_READY = 1 << 14 /* LBVH scenes: ranked for this round's Y */ };
-
-#ifndef WAVE_BVH_SLICE
-#define WAVE_BVH_SLICE 16                 // LBVH scenes: nodes a pending ray advances per mesh stage
+// render_bvh_kernel: 512 slots, 256 shading + 256 traversal threads per block, two blocks per SM
+#define BVH_SLOTS 512
+#define BVH_SHADE_THREADS 256
+#define BVH_TRAV_THREADS 256
+#ifndef BVH_REFILL_STEPS
+#define BVH_REFILL_STEPS 4                // nodes a traversal lane walks between two looks at the ring of pending rays
 #endif
 
-// mesh-kind specific part of a block's shared memory
-template <int NT, bool BVH> struct WaveMeshSmem;
-template <int NT> struct WaveMeshSmem<NT, false> {      // constant-memory meshes
+enum { ST_DEPTH_MASK = 31, ST_SUB_SHIFT = 5, ST_SPEC = 1 << 7, ST_HASRAY = 1 << 8, ST_FOLD = 1 << 9, ST_SURF = 1 << 10,
+       ST_BUCKET_SHIFT = 11 /* 3 bits: material bucket of a surface slot */ };
+
+// per-slot path state shared by both kernels (SoA, NS slots)
+template <int NS>
+struct WavePathSmem {
+  // path ray
+  float ox[NS], oy[NS], oz[NS], dx[NS], dy[NS], dz[NS];
+  // surface hit + light sample of the current bounce (X -> Y)
+  float ht[NS], nx[NS], ny[NS], nz[NS];
+  float sx[NS], sy[NS], sz[NS], ls_pdf[NS], sh_thi[NS];
+  float r1[NS], r2[NS];
+  float prev_pdf[NS];
+  float ix[NS], iy[NS], iz[NS];       // 1 / direction of the slot's pending ray: the path ray (Y -> X), then the shadow ray (X -> Y)
+  // colour of the work item so far / radiance at the end of the path
+  float cr[NS], cg[NS], cb[NS], lx[NS], ly[NS], lz[NS];
+  int   item[NS];                    // unit * nslots + q, or -1: no item
+  unsigned int pixel[NS], sample[NS];   // Philox key word 1 / counter word 0 of the current path
+  int   state[NS];                   // depth | sub << 5 | flags
+  short hmat[NS];
+  short q_r[2][NS];                  // slots whose path ended (or that starve): regenerate queue, double-buffered
+  int   cnt_r[2];
+  int   pool_next, pool_end, exhausted, retired;
+};
+
+// render_wave_kernel: + constant-memory mesh stage buffers and the material sort
+template <int NT>
+struct WaveSmem : WavePathSmem<NT> {
   float mesh_res[WAVE_PAIR_TRIS * NT];  // mesh stage results per candidate (see wave_mesh_stage)
   short cand[NT];                    // candidate index of the slot's pending ray in the mesh stage, -1: none
   short mrank[NT];                   // position of a surface slot inside its material bucket (counting sort X -> M1 -> Y)
   short q_cs[NT], q_cp[NT], q_s[NT];
   int   cnt_cs, cnt_cp, cnt_m[5];
 };
-template <int NT> struct WaveMeshSmem<NT, true> {       // LBVH meshes: the traversal state of the slot's pending ray lives here, not in a thread
-  float mesh_res[4 * NT];            // running best, then the result: t, u, v, bits(triangle id or -1)
-  int   tnode[NT];                   // cursor: next node to visit
-  short tsp[NT];                     //         stack depth
-  short pend[NT];                    // traversal in flight for the slot's 1 = path ray, 2 = shadow ray (+4: not started yet)
-  int   tstack[LBVH_SHORT_STACK * NT];   // short stack, entry k of slot s at [k * NT + s]; deeper entries: WaveArgs::tstack_ovf
-  short q_t[2][NT];                  // pending traversals: [0] advanced by M1, [1] by M2 (each stage hands its unfinished rays to the other queue)
-  short q_sb[5][NT];                 // surface slots whose shadow query is resolved, per material bucket (consumed by Y)
-  int   cnt_t[2], cnt_m[2][5];       // cnt_m[parity]: bucket sizes for this round's / the next round's Y
-};
 
-template <int NT, bool BVH>
-struct WaveSmem : WaveMeshSmem<NT, BVH> {
-  // path ray
-  float ox[NT], oy[NT], oz[NT], dx[NT], dy[NT], dz[NT];
-  // surface hit + light sample of the current bounce (X -> Y)
-  float ht[NT], nx[NT], ny[NT], nz[NT];
-  float sx[NT], sy[NT], sz[NT], ls_pdf[NT], sh_thi[NT];
-  float r1[NT], r2[NT];
-  float prev_pdf[NT];
-  float ix[NT], iy[NT], iz[NT];       // 1 / direction of the slot's pending ray: the path ray (Y -> X), then the shadow ray (X -> Y)
-  // colour of the work item so far / radiance at the end of the path
-  float cr[NT], cg[NT], cb[NT], lx[NT], ly[NT], lz[NT];
-  int   item[NT];                    // unit * nslots + q, or -1: no item
-  unsigned int pixel[NT], sample[NT];   // Philox key word 1 / counter word 0 of the current path
-  int   state[NT];                   // depth | sub << 5 | flags
-  short hmat[NT];
-  short q_r[2][NT];
-  int   cnt_r[2];
-  int   pool_next, pool_end, exhausted, retired;
+// render_bvh_kernel: + mesh query results, the ring of pending rays and the traversal lanes' short stacks
+struct BvhWaveSmem : WavePathSmem<BVH_SLOTS> {
+  float mesh_res[4 * BVH_SLOTS];     // result of the slot's last mesh query: t, u, v, bits(triangle id or -1)
+  short pend[BVH_SLOTS];             // 0: no ray in the tree; 1 = path ray, 2 = shadow ray queued / being walked (written back to 0 by the traversal lane)
+  short tq[BVH_SLOTS];               // ring of slots with a pending ray: producers = shading threads, consumers = traversal warps
+  short q_sb[5][BVH_SLOTS];          // surface slots whose shadow query is resolved, per material bucket (consumed by Y)
+  int   tstack[LBVH_SHORT_STACK * BVH_TRAV_THREADS];   // short stack of traversal lane g: entry k at [k * BVH_TRAV_THREADS + g]
+  int   tq_head, tq_tail, tq_pub;    // consumed / reserved by producers / published (entries below tq_pub are written)
+  int   cnt_m[5];
+  int   done, xwork[2];              // xwork[parity]: did this round's X find a slot to extend?
 };
 
 // warp-aggregated append of `slot` to a shared-memory queue (one atomic per warp); returns the position
@@ -117,13 +131,38 @@ ART_D int queue_push(bool pred, short* q, int* cnt, int slot) {
   return pred ? pos : -1;
 }
 
+// the same into a ring of `size` entries (power of two) with a free-running reservation counter
+ART_D void ring_push(bool pred, short* q, int* tail, int size, int slot) {
+  const unsigned m = __ballot_sync(0xffffffffu, pred);
+  if (m == 0u) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(tail, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) q[(base + __popc(m & ((1u << lane) - 1u))) & (size - 1)] = (short)slot;
+}
+
+// rank `slot` inside the material bucket of its warp peers and file it in that bucket's queue (the counting sort of the surface
+// slots, done at the moment a slot is known to be ready for Y).  All 32 lanes call; pred selects.
+ART_D void bucket_push(bool pred, int bucket, int slot, int* cnt5, short* q, int stride) {
+  const int lane = threadIdx.x & 31;
+  const unsigned m = __match_any_sync(0xffffffffu, pred ? bucket : (-1 - lane));
+  if (pred) {
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&cnt5[bucket], __popc(m));
+    base = __shfl_sync(m, base, leader);
+    q[bucket * stride + base + __popc(m & ((1u << lane) - 1u))] = (short)slot;
+  }
+}
+
 struct WaveArgs {
   gcore_dev::RenderArgs r;
   float4* colbuf;                         // [units][nslots]
   float4* stackA;                         // [WAVE_MAX_DEPTH][total_slots]  (E.xyz, W.x)
   float2* stackB;                         // [WAVE_MAX_DEPTH][total_slots]  (W.y, W.z)
   unsigned int* next_item;                // global work counter
-  int*    tstack_ovf;                     // LBVH scenes: [total_slots][LBVH_OVERFLOW] traversal stack entries beyond the shared short stack
   int     units;
   int     count_mesh;                     // statistics level 2: count reference-bbox entries (see mesh_candidate)
 };
@@ -297,12 +336,282 @@ ART_D void triangle_tuv(f3 o, f3 d, f3 A, f3 edge1, f3 edge2, float& t, float& u
   t = dot(edge2, qvec) * invDet;
 }
 
-// mesh stage (M1 / M2) of constant-memory meshes for the rays queued in q_c.  SHADOW: the ray is the shadow ray of the slot's
-// hit.  Meshes of up to WAVE_PAIR_TRIS triangles are tested as (ray, triangle) pairs, one triangle test per thread, so the
-// stage is as short as one triangle test (nothing else runs on the SM meanwhile): mesh_res[c * ntris + i] = t of
-// triangle i if its (u, v) test passes, NaN otherwise.  Bigger meshes: one ray per thread, mesh_res[4c..] = t, u, v, id.
-template <int MESHK, bool SHADOW, int NT>
-ART_D void wave_mesh_stage(WaveSmem<NT, false>& S, const short* q_c, int n_c, int tid) {
+// ---------------------------------------------------------------------------------------------------------------------
+// the three per-slot pieces of the integrators, shared by both kernels (S: any shared-memory struct built on WavePathSmem)
+// ---------------------------------------------------------------------------------------------------------------------
+
+struct ExtendOut { bool ended, surf, push_cs; int bucket; };
+
+// stage X for slot s whose path ray is resolved: (tri_*) = its mesh candidate.  Scene.Find_Closest_Hit, then path end
+// (miss / emitter: integrators.adb:98-108, 151-157, 218-247) or, on a surface, the Philox draws, Lights.Sample and the shadow
+// ray of Compute_Shadow (ray_tracer.adb:100-116).  Writes the slot's state word.
+template <int RT, int MESHK, class SM>
+ART_D ExtendOut wave_extend(SM& S, int s, int st, const gcore_dev::RenderArgs& a, int tri_id, float tri_t, float tri_u, float tri_v,
+                            bool cnt, unsigned int& nmesh, unsigned int& nbounce) {
+  ExtendOut out; out.ended = false; out.surf = false; out.push_cs = false; out.bucket = -1 - (int)(threadIdx.x & 31);   // distinct per lane: no peers in a match
+  const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
+  const f3 inv = mk3(S.ix[s], S.iy[s], S.iz[s]);                        // 1.0/direction (geometry.adb:154-156), computed when the ray was made
+  DHit h;
+  closest_with_mesh<MESHK>(o, d, inv, tri_id, tri_t, tri_u, tri_v, true, h);
+  st &= ~(ST_SURF | (7 << ST_BUCKET_SHIFT));
+  f3 Lterm = mk3(0.f, 0.f, 0.f);
+  if (!h.is_hit) {                                                      // integrators.adb:98,151,218
+    out.ended = true;
+  } else if (g_scn.mats[h.mat].type == MAT_LIGHT) {
+    out.ended = true;
+    if (RT != GCORE_PT_SHADOW && !(dot(neg(d), h.normal) < 0.0f)) {     // :155-157 ; :103, :224
+      f3 emit = (g_scn.mats[h.mat].light < 0) ? mk3(0.f, 0.f, 0.f) : ld3(g_scn.l_intensity);   // materials.adb:147-156
+      if (RT == GCORE_PT_STUPID) Lterm = emit;                          // :106
+      else {                                                            // :230-243
+        float lgtPdf = light_eval_pdf(o, d, h.t);
+        float bsdfPdf = S.prev_pdf[s];
+        float misWeight = (st & ST_SPEC) ? 1.0f : (bsdfPdf * bsdfPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf));
+        Lterm = emit * misWeight;
+      }
+    }
+  } else {
+    // ---- surface: Philox draws, light sample + shadow ray (Compute_Shadow, ray_tracer.adb:100-116)
+    nbounce++;
+    out.surf = true;
+    st |= ST_SURF;
+    const BounceRand br = bounce_rand(a.seed, S.pixel[s], S.sample[s], (uint32_t)(st & ST_DEPTH_MASK));
+    S.r1[s] = br.u2; S.r2[s] = br.u3;
+    S.ht[s] = h.t; S.nx[s] = h.normal.x; S.ny[s] = h.normal.y; S.nz[s] = h.normal.z; S.hmat[s] = (short)h.mat;
+    if (RT != GCORE_PT_STUPID) {                                        // :161-178 / :251-287
+      const f3 hpos = mk3(o.x + h.t * d.x, o.y + h.t * d.y, o.z + h.t * d.z);
+      LightSample ls = light_sample(br.u0, br.u1, hpos);
+      float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
+      epsilon = max2(epsilon, 1.0e-30f);
+      const f3 sdir = normalize(ls.pos - hpos);
+      const f3 so = hpos + sdir * epsilon;
+      float maxDist  = length(hpos - ls.pos);
+      float epsilon2 = max2(maxDist * 0.000001f, 1.0e-30f);
+      S.sx[s] = sdir.x; S.sy[s] = sdir.y; S.sz[s] = sdir.z; S.ls_pdf[s] = ls.pdf; S.sh_thi[s] = maxDist - epsilon2;
+      const f3 sinv = mk3(1.0f / sdir.x, 1.0f / sdir.y, 1.0f / sdir.z);
+      S.ix[s] = sinv.x; S.iy[s] = sinv.y; S.iz[s] = sinv.z;
+      out.push_cs = mesh_candidate<MESHK>(so, sinv, cnt, nmesh);
+    }
+    const int type = g_scn.mats[h.mat].type;
+    out.bucket = (type == MAT_LAMBERT) ? 0 : (type == MAT_PHONG) ? 1 : (type == MAT_GLASS) ? 2 : (type == MAT_MIRROR) ? 3 : 4;
+    st |= out.bucket << ST_BUCKET_SHIFT;
+  }
+  if (out.ended) {
+    S.lx[s] = Lterm.x; S.ly[s] = Lterm.y; S.lz[s] = Lterm.z;
+    st = (st & ~ST_HASRAY) | ST_FOLD;
+  }
+  S.state[s] = st;
+  return out;
+}
+
+struct ShadeOut { bool ended, newray, push_cp; };
+
+// stage Y for surface slot s whose shadow query is resolved: (tri_id, tri_t) = the shadow ray's mesh candidate.  The in_shadow
+// rule, EvalBxDF / EvalPDF / MIS, SampleAndEvalBxDF, the bounce terms onto the slot's stack, the next path ray.
+template <int RT, int MESHK, class SM>
+ART_D ShadeOut wave_shade(SM& S, int s, const WaveArgs& wa, size_t stack_index, int total_slots, int tri_id, float tri_t,
+                          bool cnt, unsigned int& nmesh, unsigned int& nrays) {
+  ShadeOut out; out.ended = false; out.newray = false; out.push_cp = false;
+  int st = S.state[s];
+  const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
+  const float ht = S.ht[s];
+  const f3 hn = mk3(S.nx[s], S.ny[s], S.nz[s]);
+  const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
+  const DMaterial& m = g_scn.mats[S.hmat[s]];
+  // reflect(ray_dir, normal): Phong eval/sample, mirror, glass (materials.adb:251,313,371,394); Lambert never reads it
+  const f3 refl = (m.type == MAT_LAMBERT) ? hn : reflect(d, hn);
+  f3 explicitColor = mk3(0.f, 0.f, 0.f);
+  if (RT != GCORE_PT_STUPID) {
+    const f3 sdir = mk3(S.sx[s], S.sy[s], S.sz[s]);
+    float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
+    epsilon = max2(epsilon, 1.0e-30f);
+    const f3 so = hpos + sdir * epsilon;
+    DHit hs;                                                        // closest hit; only is_hit / t are read (ray_tracer.adb:117-122)
+    closest_with_mesh<MESHK>(so, sdir, mk3(S.ix[s], S.iy[s], S.iz[s]), tri_id, tri_t, 0.0f, 0.0f, false, hs);
+    nrays++;
+    const bool shadowed = hs.is_hit && (hs.t < S.sh_thi[s] && hs.t > 10.0f * epsilon);
+    if (!shadowed) {
+      f3 bxdfVal; float bsdfPdf;
+      mat_eval(m, sdir, hn, refl, bxdfVal, bsdfPdf);
+      float cosTheta1 = max2(dot(sdir, hn), 0.0f);
+      f3 intensity = ld3(g_scn.l_intensity);
+      const float ls_pdf = S.ls_pdf[s];
+      if (RT == GCORE_PT_SHADOW) {
+        explicitColor = intensity * (cosTheta1 * bxdfVal) * (1.0f / max2(ls_pdf, 1.0e-20f));
+      } else {
+        float lgtPdf = ls_pdf;
+        float misWeight = lgtPdf * lgtPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf);
+        explicitColor = intensity * (1.0f / max2(lgtPdf, 1.0e-20f)) * (cosTheta1 * bxdfVal) * misWeight;
+      }
+    }
+  }
+  MatSampleD ms = mat_sample(m, S.r1[s], S.r2[s], d, hn, refl);     // pick up next ray, :116,183,291
+  f3 bxdfVal = ms.color * (1.0f / max2(ms.pdf, 1.0e-20f));
+  float cosTheta = dot(ms.direction, hn);
+  const f3 W = fabsf(cosTheta) * bxdfVal;
+  int depth = st & ST_DEPTH_MASK;
+  wa.stackA[(size_t)depth * total_slots + stack_index] = make_float4(explicitColor.x, explicitColor.y, explicitColor.z, W.x);
+  wa.stackB[(size_t)depth * total_slots + stack_index] = make_float2(W.y, W.z);
+  depth++;
+  const f3 off3 = (sign_ada(cosTheta) * hn) * 1.0e-5f;              // :122,189,297
+  const f3 no = hpos + off3, nd = ms.direction;
+  S.ox[s] = no.x; S.oy[s] = no.y; S.oz[s] = no.z; S.dx[s] = nd.x; S.dy[s] = nd.y; S.dz[s] = nd.z;
+  S.prev_pdf[s] = ms.pdf;
+  st = (st & ~(ST_DEPTH_MASK | ST_SPEC | ST_SURF)) | depth | (ms.pureSpecular ? ST_SPEC : 0);
+  if (depth == wa.r.max_depth) {                                    // recursion_level = 0 -> (0,0,0)
+    S.lx[s] = 0.f; S.ly[s] = 0.f; S.lz[s] = 0.f;
+    st = (st & ~ST_HASRAY) | ST_FOLD;
+    out.ended = true;
+  } else {
+    out.newray = true;
+    const f3 ninv = mk3(1.0f / nd.x, 1.0f / nd.y, 1.0f / nd.z);
+    S.ix[s] = ninv.x; S.iy[s] = ninv.y; S.iz[s] = ninv.z;
+    out.push_cp = mesh_candidate<MESHK>(no, ninv, cnt, nmesh);
+  }
+  S.state[s] = st;
+  return out;
+}
+
+struct RegenOut { bool starved, retire, newray, push_cp; };
+
+// regenerate for the slot at position r of queue R (on: this lane has one; every lane of the warp calls): unwind the finished
+// path innermost-first (integrators.adb:124,191,299), add its radiance to the colour of the pixel pass in the reference's order
+// (:42-51), publish a completed pass, fetch the next work item (one atomic per warp), camera ray (ray_tracer.adb:61-97)
+template <int RT, int MESHK, class SM>
+ART_D RegenOut wave_regen(SM& S, int s, bool on, const WaveArgs& wa, size_t stack_index, int total_slots, bool cnt, unsigned int& nmesh) {
+  const gcore_dev::RenderArgs& a = wa.r;
+  const int aa = a.anti_aliasing;
+  RegenOut out; out.starved = false; out.retire = false; out.newray = false; out.push_cp = false;
+  bool need = false, padded = false;
+  int st = 0, item = -1;
+  if (on) {
+    st = S.state[s];
+    item = S.item[s];
+    if (st & ST_FOLD) {                                               // unwind the recursion: integrators.adb:124,191,299
+      f3 L = mk3(S.lx[s], S.ly[s], S.lz[s]);
+      const int depth = st & ST_DEPTH_MASK;
+#pragma unroll 1
+      for (int k0 = depth - 1; k0 >= 0; k0 -= 4) {                    // four levels of loads in flight at a time
+        float4 A[4]; float2 B[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int k = (k0 - j >= 0) ? (k0 - j) : 0;
+          A[j] = wa.stackA[(size_t)k * total_slots + stack_index];
+          B[j] = wa.stackB[(size_t)k * total_slots + stack_index];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (k0 - j >= 0) {
+            const f3 W = mk3(A[j].w, B[j].x, B[j].y);
+            if (RT == GCORE_PT_STUPID) L = W * L;
+            else L = mk3(A[j].x, A[j].y, A[j].z) + W * L;
+          }
+        }
+      }
+      const int sub = (st >> ST_SUB_SHIFT) & 3;
+      f3 color = mk3(S.cr[s], S.cg[s], S.cb[s]);
+      bool done;
+      if (aa) {
+        if (sub == 0) color = mk3(a.bg[0], a.bg[1], a.bg[2]);         // :42
+        color = color + L;                                            // :47
+        done = (sub == 3);
+      } else { color = L; done = true; }                              // :60
+      if (done) { wa.colbuf[item] = make_float4(color.x, color.y, color.z, 0.0f); item = -1; }
+      else { S.cr[s] = color.x; S.cg[s] = color.y; S.cb[s] = color.z; }
+      st = (st & ~(ST_FOLD | (3 << ST_SUB_SHIFT))) | (((sub + 1) & 3) << ST_SUB_SHIFT);
+    }
+    need = item < 0;
+    if (!need) S.sample[s] = S.sample[s] + 1u;                        // next sub-pixel sample of the same pass
+  }
+  {                                                                   // next work item (pass, pixel): one atomic per warp
+    const unsigned nm = __ballot_sync(0xffffffffu, need);
+    if (nm) {
+      const int lane = threadIdx.x & 31, leader = __ffs(nm) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&S.pool_next, __popc(nm));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (need) {
+        const int got = base + __popc(nm & ((1u << lane) - 1u));
+        out.starved = true;
+        if (got < S.pool_end) {
+          const int q = got % a.nslots, unit = got / a.nslots;
+          const WavePixel px = wave_slot_to_pixel(a, q);
+          if (px.active) {                                            // (an item of a padding pixel is dropped; the slot asks again next round)
+            out.starved = false;
+            item = got;
+            S.pixel[s] = (unsigned int)(px.y * a.width + px.x);
+            S.sample[s] = (unsigned int)(a.first_sample + (aa ? unit * 4 : unit));
+          } else padded = true;
+        }
+        st &= ~(3 << ST_SUB_SHIFT);
+      }
+    }
+  }
+  if (on) {
+    S.item[s] = item;
+    if (!out.starved) {
+      const int sub = (st >> ST_SUB_SHIFT) & 3;
+      const unsigned int pixel = S.pixel[s];
+      const int py = (int)(pixel / (unsigned int)a.width), pxx = (int)(pixel - (unsigned int)py * (unsigned int)a.width);
+      const f3 o = ld3(g_scn.cam_pos);
+      const f3 d = wave_eye_ray_dir(a, pxx, py, aa ? sub : -1);
+      S.ox[s] = o.x; S.oy[s] = o.y; S.oz[s] = o.z; S.dx[s] = d.x; S.dy[s] = d.y; S.dz[s] = d.z;
+      S.prev_pdf[s] = 1.0f;                                           // StartSample, materials.ads:25
+      st = (st & (3 << ST_SUB_SHIFT)) | ST_SPEC | ST_HASRAY;          // depth 0
+      out.newray = true;
+      const f3 cinv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+      S.ix[s] = cinv.x; S.iy[s] = cinv.y; S.iz[s] = cinv.z;
+      out.push_cp = mesh_candidate<MESHK>(o, cinv, cnt, nmesh);
+    } else {
+      st &= ~(ST_HASRAY | ST_FOLD);
+      out.retire = (S.exhausted != 0) && !padded;                     // no work left anywhere: the slot retires
+    }
+    S.state[s] = st;
+  }
+  return out;
+}
+
+// work items are fetched from the global counter in batches that shrink towards the end of the launch (guided
+// self-scheduling): 2 NS while there is plenty, down to 64, so that the blocks run dry together.  Thread 0 only.
+template <class SM>
+ART_D void wave_refill_pool(SM& S, const WaveArgs& wa, unsigned int total_items, unsigned int ns) {
+  const unsigned int seen = *(volatile unsigned int*)wa.next_item;
+  const unsigned int rem = (seen < total_items) ? (total_items - seen) : 0u;
+  unsigned int want = rem / (2u * gridDim.x);
+  want = want < 64u ? 64u : (want > 2u * ns ? 2u * ns : want);
+  const unsigned int base = atomicAdd(wa.next_item, want);
+  if (base >= total_items) { S.exhausted = 1; S.pool_next = 0; S.pool_end = 0; }
+  else { S.pool_next = (int)base; S.pool_end = (int)min(base + want, total_items); }
+}
+
+// statistics: one atomic per warp and counter
+ART_D void wave_flush_counters(const gcore_dev::RenderArgs& a, unsigned int nrays, unsigned int nmesh, unsigned int nbounce,
+                               unsigned int tnodes, unsigned int ttris, unsigned int ntrav) {
+  unsigned int total_rays = __reduce_add_sync(0xffffffffu, nrays);
+  unsigned int total_mesh = __reduce_add_sync(0xffffffffu, nmesh);
+  unsigned int total_bnc  = __reduce_add_sync(0xffffffffu, nbounce);
+  unsigned int tn = __reduce_add_sync(0xffffffffu, tnodes), tt = __reduce_add_sync(0xffffffffu, ttris), tv = __reduce_add_sync(0xffffffffu, ntrav);
+  if ((threadIdx.x & 31) == 0) {
+    if (total_rays) {
+      atomicAdd(&a.counters[0], (unsigned long long)total_rays);
+      atomicAdd(&a.counters[1], (unsigned long long)total_mesh);
+      atomicAdd(&a.counters[2], (unsigned long long)total_bnc);
+    }
+    if (tn | tv) {
+      atomicAdd(&a.counters[3], (unsigned long long)tn); atomicAdd(&a.counters[4], (unsigned long long)tt); atomicAdd(&a.counters[5], (unsigned long long)tv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// render_wave_kernel: constant-memory meshes, block-synchronous
+// ---------------------------------------------------------------------------------------------------------------------
+
+// mesh stage (M1 / M2) for the rays queued in q_c.  SHADOW: the ray is the shadow ray of the slot's hit.  Meshes of up to
+// WAVE_PAIR_TRIS triangles are tested as (ray, triangle) pairs, one triangle test per thread, so the stage is as short as one
+// triangle test (nothing else runs on the SM meanwhile): mesh_res[c * ntris + i] = t of triangle i if its (u, v) test passes,
+// NaN otherwise.  Bigger meshes (<= 64 triangles): one ray per thread, mesh_res[4c..] = t, u, v, id.
+template <bool SHADOW, int NT>
+ART_D void wave_mesh_stage(WaveSmem<NT>& S, const short* q_c, int n_c, int tid) {
   const int ntris = g_scn.ntris_bf;
   const bool pair_mode = (g_scn.pair_group != 0);
   const int work = pair_mode ? n_c * ntris : n_c;
@@ -325,7 +634,7 @@ ART_D void wave_mesh_stage(WaveSmem<NT, false>& S, const short* q_c, int n_c, in
       S.mesh_res[j] = (v > 0.0f && u > 0.0f && u + v < 1.0f) ? t : __int_as_float(0x7fc00000);
     } else {
       float t, u, v; int id;
-      mesh_query<MESHK>(o, d, t, u, v, id);
+      mesh_query<MESHK_CONST>(o, d, t, u, v, id);
       S.mesh_res[4 * c + 0] = t; S.mesh_res[4 * c + 1] = u; S.mesh_res[4 * c + 2] = v; S.mesh_res[4 * c + 3] = __int_as_float(id);
     }
   }
@@ -333,13 +642,12 @@ ART_D void wave_mesh_stage(WaveSmem<NT, false>& S, const short* q_c, int n_c, in
 
 // the mesh candidate of a ray out of mesh_res: the window walk of IntersectMeshBF (geometry.adb:276-296) over the pair
 // results in triangle order (u, v of the selected triangle are re-derived when the caller needs them), or the stored
-// per-ray result (LBVH scenes: c = the slot)
-template <int MESHK, int NT>
-ART_D void wave_mesh_result(const WaveSmem<NT, MESHK == MESHK_BVH>& S, int c, f3 o, f3 d, bool want_uv, int& id, float& t, float& u, float& v) {
+// per-ray result
+template <int NT>
+ART_D void wave_mesh_result(const WaveSmem<NT>& S, int c, f3 o, f3 d, bool want_uv, int& id, float& t, float& u, float& v) {
   id = -1; t = 0.0f; u = 0.0f; v = 0.0f;
   if (c < 0) return;
-  const bool pair_mode = (MESHK == MESHK_CONST) && (g_scn.pair_group != 0);
-  if (pair_mode) {
+  if (g_scn.pair_group != 0) {
     const int ntris = g_scn.ntris_bf;
     const bool ref_mode = (g_scn.mesh_mode == MESH_REFERENCE_BF);
     float w_min = 0.0f, w_max = 1000000.0f;
@@ -360,118 +668,25 @@ ART_D void wave_mesh_result(const WaveSmem<NT, MESHK == MESHK_BVH>& S, int c, f3
   }
 }
 
-// rank `slot` inside the material bucket of its warp peers and file it in that bucket's queue (LBVH scenes: the counting sort
-// of the surface slots happens at the moment a slot's shadow query is resolved).  All 32 lanes call; pred selects.
-ART_D void bucket_push(bool pred, int bucket, int slot, int* cnt5, short* q, int stride) {
-  const int lane = threadIdx.x & 31;
-  const unsigned m = __match_any_sync(0xffffffffu, pred ? bucket : (-1 - lane));
-  if (pred) {
-    const int leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&cnt5[bucket], __popc(m));
-    base = __shfl_sync(m, base, leader);
-    q[bucket * stride + base + __popc(m & ((1u << lane) - 1u))] = (short)slot;
-  }
-}
-
-template <int RT, int MESHK, int NT>
+template <int RT, int NT>
 __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kernel(const __grid_constant__ WaveArgs wa) {
   constexpr int NS = WAVE_SLOTS(NT);        // path slots of this block
-  constexpr bool BVH = (MESHK == MESHK_BVH);
+  constexpr int MESHK = MESHK_CONST;
   extern __shared__ __align__(16) unsigned char wave_smem_raw[];
-  WaveSmem<NT, BVH>& S = *reinterpret_cast<WaveSmem<NT, BVH>*>(wave_smem_raw);
+  WaveSmem<NT>& S = *reinterpret_cast<WaveSmem<NT>*>(wave_smem_raw);
   const gcore_dev::RenderArgs& a = wa.r;
   const int tid = threadIdx.x;
   const int gslot0 = blockIdx.x * NT;
   const int total_slots = gridDim.x * NT;
   const unsigned int total_items = (unsigned int)wa.units * (unsigned int)a.nslots;
-  // work items are fetched from the global counter in batches that shrink towards the end of the launch (guided
-  // self-scheduling): 2 NS while there is plenty, down to 64, so that the blocks run dry together
-  auto fetch_batch = [&](unsigned int& base, unsigned int& count) {
-    const unsigned int seen = *(volatile unsigned int*)wa.next_item;
-    const unsigned int rem = (seen < total_items) ? (total_items - seen) : 0u;
-    unsigned int want = rem / (2u * gridDim.x);
-    want = want < 64u ? 64u : (want > 2u * NS ? 2u * NS : want);
-    base = atomicAdd(wa.next_item, want);
-    count = want;
-  };
-  const int aa = a.anti_aliasing;
-  const int max_depth = a.max_depth;
-  const f3 bg = mk3(a.bg[0], a.bg[1], a.bg[2]);
   unsigned int nrays = 0, nmesh = 0, nbounce = 0;
   const bool cnt = wa.count_mesh != 0;
 
-  // LBVH scenes: the traversal state of a slot's pending ray lives in shared memory (cursor, running best hit, short stack), so
-  // every mesh stage advances a DENSE queue of pending rays by one slice -- full warps on the traversal code -- and hands the
-  // unfinished ones to the other stage's queue.  A slot whose ray is still in flight sits the next X / Y out.
-  static_assert(!BVH || NS == NT, "LBVH scenes: one slot per thread");
-  BvhStats tstat; tstat.nodes = 0; tstat.tris = 0; unsigned int ntrav = 0;      // LBVH nodes visited / triangle slots tested / traversals
-  int bpar = 0;                                                                 // LBVH scenes: which cnt_m set this round's Y reads
-  // one slice of slot s's pending traversal; returns true when the ray is resolved (result in mesh_res[4s..])
-  auto bvh_slice = [&](int s, int p) -> bool {
-    if constexpr (BVH) {
-      f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
-      float t_clip = 1000000.0f;
-      if ((p & 3) == 2) {                                                     // shadow ray of Compute_Shadow, ray_tracer.adb:109-113
-        const float ht = S.ht[s];
-        const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
-        d = mk3(S.sx[s], S.sy[s], S.sz[s]);
-        float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
-        epsilon = max2(epsilon, 1.0e-30f);
-        o = hpos + d * epsilon;
-        // only a hit with t < maxDist - epsilon2 can change in_shadow (ray_tracer.adb:119-128): a mesh hit beyond it either is not
-        // the closest hit or fails that test itself, so the walk is clipped there (the nearest hit below it is still exact)
-        t_clip = S.sh_thi[s];
-      }
-      BvhRayState c;
-      if (p & 4) { bvh_state_begin(g_scn.bvh, t_clip, c); ntrav++; }
-      else {
-        c.node = S.tnode[s]; c.sp = S.tsp[s];
-        c.best_t = S.mesh_res[4 * s + 0]; c.best_u = S.mesh_res[4 * s + 1]; c.best_v = S.mesh_res[4 * s + 2]; c.best_prim = __float_as_int(S.mesh_res[4 * s + 3]);
-      }
-      const bool done = bvh_state_advance(g_scn.bvh, o, d, mk3(S.ix[s], S.iy[s], S.iz[s]), 0.0f, WAVE_BVH_SLICE, c, &S.tstack[s], NT,
-                                          wa.tstack_ovf + (size_t)(gslot0 + s) * LBVH_OVERFLOW, tstat);
-      S.mesh_res[4 * s + 0] = c.best_t; S.mesh_res[4 * s + 1] = c.best_u; S.mesh_res[4 * s + 2] = c.best_v;
-      S.mesh_res[4 * s + 3] = __int_as_float(c.best_prim);
-      if (done) S.pend[s] = 0;
-      else { S.pend[s] = (short)(p & 3); S.tnode[s] = c.node; S.tsp[s] = (short)c.sp; }
-      return done;
-    } else { (void)s; (void)p; return true; }
-  };
-  // LBVH mesh stage: advance the rays of queue `qi` by one slice; unfinished -> the other queue, resolved shadow rays make their
-  // slot ready for the Y that reads cnt_m[ypar]
-  auto bvh_stage = [&](int qi, int ypar) {
-    if constexpr (BVH) {
-      const int n = S.cnt_t[qi];
-      for (int j0 = 0; j0 < n; j0 += NT) {
-        const int j = j0 + tid;
-        bool more = false, ready = false; int s = 0, bucket = 0;
-        if (j < n) {
-          s = S.q_t[qi][j];
-          const int p = S.pend[s];
-          const bool done = bvh_slice(s, p);
-          more = !done;
-          ready = done && ((p & 3) == 2);
-          bucket = (S.state[s] >> ST_BUCKET_SHIFT) & 7;
-        }
-        queue_push(more, S.q_t[qi ^ 1], &S.cnt_t[qi ^ 1], s);
-        bucket_push(ready, bucket, s, S.cnt_m[ypar], &S.q_sb[0][0], NT);
-      }
-    } else { (void)qi; (void)ypar; }
-  };
-
-  for (int s = tid; s < NS; s += NT) {
-    S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s;
-    if constexpr (BVH) S.pend[s] = 0; else S.cand[s] = -1;
-  }
+  for (int s = tid; s < NS; s += NT) { S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s; S.cand[s] = -1; }
   if (tid == 0) {
-    S.cnt_r[0] = NS; S.cnt_r[1] = 0; S.retired = 0; S.exhausted = 0;
-    if constexpr (BVH) { S.cnt_t[0] = 0; S.cnt_t[1] = 0; for (int b = 0; b < 5; b++) { S.cnt_m[0][b] = 0; S.cnt_m[1][b] = 0; } }
-    else { S.cnt_cs = 0; S.cnt_cp = 0; for (int b = 0; b < 5; b++) S.cnt_m[b] = 0; }
-    unsigned int base, count;
-    fetch_batch(base, count);
-    if (base >= total_items) { S.exhausted = 1; S.pool_next = 0; S.pool_end = 0; }
-    else { S.pool_next = (int)base; S.pool_end = (int)min(base + count, total_items); }
+    S.cnt_r[0] = NS; S.cnt_r[1] = 0; S.cnt_cs = 0; S.cnt_cp = 0; S.retired = 0; S.exhausted = 0;
+    for (int b = 0; b < 5; b++) S.cnt_m[b] = 0;
+    wave_refill_pool(S, wa, total_items, NS);
   }
   __syncthreads();
 
@@ -479,110 +694,39 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
   for (;;) {
     // ================================================================= X: closest hit, path end or light sample
     if (tid == 0) {
-      if constexpr (BVH) S.cnt_t[1] = 0;                                      // consumed by M2 of the previous round
-      else S.cnt_cp = 0;
-      if (!S.exhausted && S.pool_next >= S.pool_end) {                        // refill the item pool (fetched from in Y only)
-        unsigned int base, count;
-        fetch_batch(base, count);
-        if (base >= total_items) S.exhausted = 1;
-        else { S.pool_next = (int)base; S.pool_end = (int)min(base + count, total_items); }
-      }
+      S.cnt_cp = 0;                                                           // consumed by M2 of the previous round
+      if (!S.exhausted && S.pool_next >= S.pool_end) wave_refill_pool(S, wa, total_items, NS);   // (fetched from in Y only)
     }
     for (int s = tid; s < NS; s += NT) {
-      int st = S.state[s];
-      // LBVH scenes: a slot whose path ray is still being traversed, or that waits for Y (shadow ray in flight), sits this X out
-      bool on;
-      if constexpr (BVH) on = ((st & (ST_HASRAY | ST_SURF)) == ST_HASRAY) && S.pend[s] == 0;
-      else on = (st & ST_HASRAY) != 0;
-      bool ended = false, push_cs = false, surf = false;
-      int bucket = -1 - (tid & 31);                                           // distinct per lane: no peers in the match below
+      const int st = S.state[s];
+      const bool on = (st & ST_HASRAY) != 0;
+      ExtendOut x; x.ended = false; x.surf = false; x.push_cs = false; x.bucket = -1 - (tid & 31);
       if (on) {
         const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
-        const f3 inv = mk3(S.ix[s], S.iy[s], S.iz[s]);                        // 1.0/direction (geometry.adb:154-156), computed when the ray was made
         int tri_id; float tri_t, tri_u, tri_v;
-        int cidx;
-        if constexpr (BVH) cidx = s; else cidx = (int)S.cand[s];
-        wave_mesh_result<MESHK, NT>(S, cidx, o, d, true, tri_id, tri_t, tri_u, tri_v);
-        DHit h;
-        closest_with_mesh<MESHK>(o, d, inv, tri_id, tri_t, tri_u, tri_v, true, h);
+        wave_mesh_result<NT>(S, (int)S.cand[s], o, d, true, tri_id, tri_t, tri_u, tri_v);
+        x = wave_extend<RT, MESHK>(S, s, st, a, tri_id, tri_t, tri_u, tri_v, cnt, nmesh, nbounce);
         nrays++;
-        st &= ~(ST_SURF | (7 << ST_BUCKET_SHIFT));
-        f3 Lterm = mk3(0.f, 0.f, 0.f);
-        if (!h.is_hit) {                                                      // integrators.adb:98,151,218
-          ended = true;
-        } else if (g_scn.mats[h.mat].type == MAT_LIGHT) {
-          ended = true;
-          if (RT != GCORE_PT_SHADOW && !(dot(neg(d), h.normal) < 0.0f)) {     // :155-157 ; :103, :224
-            f3 emit = (g_scn.mats[h.mat].light < 0) ? mk3(0.f, 0.f, 0.f) : ld3(g_scn.l_intensity);   // materials.adb:147-156
-            if (RT == GCORE_PT_STUPID) Lterm = emit;                          // :106
-            else {                                                            // :230-243
-              float lgtPdf = light_eval_pdf(o, d, h.t);
-              float bsdfPdf = S.prev_pdf[s];
-              float misWeight = (st & ST_SPEC) ? 1.0f : (bsdfPdf * bsdfPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf));
-              Lterm = emit * misWeight;
-            }
-          }
-        } else {
-          // ---- surface: Philox draws, light sample + shadow ray (Compute_Shadow, ray_tracer.adb:100-116)
-          nbounce++;
-          surf = true;
-          st |= ST_SURF;
-          const BounceRand br = bounce_rand(a.seed, S.pixel[s], S.sample[s], (uint32_t)(st & ST_DEPTH_MASK));
-          S.r1[s] = br.u2; S.r2[s] = br.u3;
-          S.ht[s] = h.t; S.nx[s] = h.normal.x; S.ny[s] = h.normal.y; S.nz[s] = h.normal.z; S.hmat[s] = (short)h.mat;
-          if (RT != GCORE_PT_STUPID) {                                        // :161-178 / :251-287
-            const f3 hpos = mk3(o.x + h.t * d.x, o.y + h.t * d.y, o.z + h.t * d.z);
-            LightSample ls = light_sample(br.u0, br.u1, hpos);
-            float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
-            epsilon = max2(epsilon, 1.0e-30f);
-            const f3 sdir = normalize(ls.pos - hpos);
-            const f3 so = hpos + sdir * epsilon;
-            float maxDist  = length(hpos - ls.pos);
-            float epsilon2 = max2(maxDist * 0.000001f, 1.0e-30f);
-            S.sx[s] = sdir.x; S.sy[s] = sdir.y; S.sz[s] = sdir.z; S.ls_pdf[s] = ls.pdf; S.sh_thi[s] = maxDist - epsilon2;
-            const f3 sinv = mk3(1.0f / sdir.x, 1.0f / sdir.y, 1.0f / sdir.z);
-            S.ix[s] = sinv.x; S.iy[s] = sinv.y; S.iz[s] = sinv.z;
-            push_cs = mesh_candidate<MESHK>(so, sinv, cnt, nmesh);
-          }
-          const int type = g_scn.mats[h.mat].type;
-          bucket = (type == MAT_LAMBERT) ? 0 : (type == MAT_PHONG) ? 1 : (type == MAT_GLASS) ? 2 : (type == MAT_MIRROR) ? 3 : 4;
-          st |= bucket << ST_BUCKET_SHIFT;
-        }
-        if (ended) {
-          S.lx[s] = Lterm.x; S.ly[s] = Lterm.y; S.lz[s] = Lterm.z;
-          st = (st & ~ST_HASRAY) | ST_FOLD;
-        }
-        S.state[s] = st;
       }
-      queue_push(ended, S.q_r[par], &S.cnt_r[par], s);
-      if constexpr (BVH) {
-        // a surface slot either starts its shadow traversal (queue of M1) or -- no mesh candidate, or no shadow ray at all -- is ready for Y
-        if (surf) { if (push_cs) S.pend[s] = 2 | 4; else S.mesh_res[4 * s + 3] = __int_as_float(-1); }
-        queue_push(surf && push_cs, S.q_t[0], &S.cnt_t[0], s);
-        bucket_push(surf && !push_cs, bucket, s, S.cnt_m[bpar], &S.q_sb[0][0], NT);
-      } else {
-        if (RT != GCORE_PT_STUPID) {
-          const int c = queue_push(push_cs, S.q_cs, &S.cnt_cs, s);
-          if (on) S.cand[s] = (short)c;                                       // -1 when the shadow ray skips the mesh
-        }
-        // counting sort by material type: rank inside the bucket
-        const unsigned m = __match_any_sync(0xffffffffu, bucket);
-        if (bucket >= 0) {
-          const int lane = tid & 31, leader = __ffs(m) - 1;
-          int base = 0;
-          if (lane == leader) base = atomicAdd(&S.cnt_m[bucket], __popc(m));
-          base = __shfl_sync(m, base, leader);
-          S.mrank[s] = (short)(base + __popc(m & ((1u << lane) - 1u)));
-        }
+      queue_push(x.ended, S.q_r[par], &S.cnt_r[par], s);
+      if (RT != GCORE_PT_STUPID) {
+        const int c = queue_push(x.push_cs, S.q_cs, &S.cnt_cs, s);
+        if (on) S.cand[s] = (short)c;                                         // -1 when the shadow ray skips the mesh
+      }
+      // counting sort by material type: rank inside the bucket
+      const unsigned m = __match_any_sync(0xffffffffu, x.bucket);
+      if (x.bucket >= 0) {
+        const int lane = tid & 31, leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&S.cnt_m[x.bucket], __popc(m));
+        base = __shfl_sync(m, base, leader);
+        S.mrank[s] = (short)(base + __popc(m & ((1u << lane) - 1u)));
       }
     }
     __syncthreads();
 
-    // ================================================================= M1: mesh stage of the shadow rays
-    if constexpr (BVH) {
-      bvh_stage(0, bpar);
-    } else {
-      // scatter of the material sort + (ray, triangle) pairs
+    // ================================================================= M1: scatter of the material sort + mesh stage of the shadow rays
+    {
       const int c0 = S.cnt_m[0], c1 = S.cnt_m[1], c2 = S.cnt_m[2], c3 = S.cnt_m[3];
       for (int s = tid; s < NS; s += NT) {
         const int st = S.state[s];
@@ -592,18 +736,16 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
           S.q_s[off_b + S.mrank[s]] = (short)s;
         }
       }
-      if (RT != GCORE_PT_STUPID) wave_mesh_stage<MESHK, true, NT>(S, S.q_cs, S.cnt_cs, tid);
+      if (RT != GCORE_PT_STUPID) wave_mesh_stage<true, NT>(S, S.q_cs, S.cnt_cs, tid);
     }
     __syncthreads();
 
     // ================================================================= Y: shade (slots sorted by material) + regenerate (queue R)
     {
-      int c0, c1, c2, c3, c4;
-      if constexpr (BVH) { c0 = S.cnt_m[bpar][0]; c1 = S.cnt_m[bpar][1]; c2 = S.cnt_m[bpar][2]; c3 = S.cnt_m[bpar][3]; c4 = S.cnt_m[bpar][4]; if (tid == 0) S.cnt_t[0] = 0; }
-      else { c0 = S.cnt_m[0]; c1 = S.cnt_m[1]; c2 = S.cnt_m[2]; c3 = S.cnt_m[3]; c4 = S.cnt_m[4]; if (tid == 0) S.cnt_cs = 0; }
+      if (tid == 0) S.cnt_cs = 0;
       // surface slots sorted by material type (buckets back to back: only the warps on a bucket boundary see two types),
       // one padding gap, then queue R
-      const int n_surf = c0 + c1 + c2 + c3 + c4;
+      const int n_surf = S.cnt_m[0] + S.cnt_m[1] + S.cnt_m[2] + S.cnt_m[3] + S.cnt_m[4];
       const int n_m = (n_surf + 31) & ~31;
       const int n_r = S.cnt_r[par];
       const int n_all = n_m + ((n_r + 31) & ~31);
@@ -611,175 +753,31 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
         bool ended = false, push_cp = false, starved = false, retire = false, newray = false;
         int s = 0;
         if (i < n_m) {
-          // ------------------------------------------------------------- shade
-          const bool on = i < n_surf;
-          if (on) {
-            if constexpr (BVH) {
-              int b = 0, off = 0;
-              if (i >= c0) { b = 1; off = c0; if (i >= c0 + c1) { b = 2; off = c0 + c1; if (i >= c0 + c1 + c2) { b = 3; off = c0 + c1 + c2; if (i >= c0 + c1 + c2 + c3) { b = 4; off = c0 + c1 + c2 + c3; } } } }
-              s = S.q_sb[b][i - off];
-            } else s = S.q_s[i];
-            int st = S.state[s];
-            const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
-            const float ht = S.ht[s];
-            const f3 hn = mk3(S.nx[s], S.ny[s], S.nz[s]);
-            const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
-            const DMaterial& m = g_scn.mats[S.hmat[s]];
-            // reflect(ray_dir, normal): Phong eval/sample, mirror, glass (materials.adb:251,313,371,394); Lambert never reads it
-            const f3 refl = (m.type == MAT_LAMBERT) ? hn : reflect(d, hn);
-            f3 explicitColor = mk3(0.f, 0.f, 0.f);
+          if (i < n_surf) {
+            s = S.q_s[i];
+            int tri_id = -1; float tri_t = 0.f, tri_u, tri_v;
             if (RT != GCORE_PT_STUPID) {
+              // the shadow ray again (ray_tracer.adb:109-113): the pair results hold t per triangle, the window walk picks the candidate
+              const f3 o = mk3(S.ox[s], S.oy[s], S.oz[s]), d = mk3(S.dx[s], S.dy[s], S.dz[s]);
+              const float ht = S.ht[s];
+              const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
               const f3 sdir = mk3(S.sx[s], S.sy[s], S.sz[s]);
               float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
               epsilon = max2(epsilon, 1.0e-30f);
-              const f3 so = hpos + sdir * epsilon;
-              int tri_id; float tri_t, tri_u, tri_v;
-              int cidx;
-              if constexpr (BVH) cidx = s; else cidx = (int)S.cand[s];
-              wave_mesh_result<MESHK, NT>(S, cidx, so, sdir, false, tri_id, tri_t, tri_u, tri_v);
-              DHit hs;                                                        // closest hit; only is_hit / t are read (ray_tracer.adb:117-122)
-              closest_with_mesh<MESHK>(so, sdir, mk3(S.ix[s], S.iy[s], S.iz[s]), tri_id, tri_t, 0.0f, 0.0f, false, hs);
-              nrays++;
-              const bool shadowed = hs.is_hit && (hs.t < S.sh_thi[s] && hs.t > 10.0f * epsilon);
-              if (!shadowed) {
-                f3 bxdfVal; float bsdfPdf;
-                mat_eval(m, sdir, hn, refl, bxdfVal, bsdfPdf);
-                float cosTheta1 = max2(dot(sdir, hn), 0.0f);
-                f3 intensity = ld3(g_scn.l_intensity);
-                const float ls_pdf = S.ls_pdf[s];
-                if (RT == GCORE_PT_SHADOW) {
-                  explicitColor = intensity * (cosTheta1 * bxdfVal) * (1.0f / max2(ls_pdf, 1.0e-20f));
-                } else {
-                  float lgtPdf = ls_pdf;
-                  float misWeight = lgtPdf * lgtPdf / (lgtPdf * lgtPdf + bsdfPdf * bsdfPdf);
-                  explicitColor = intensity * (1.0f / max2(lgtPdf, 1.0e-20f)) * (cosTheta1 * bxdfVal) * misWeight;
-                }
-              }
+              wave_mesh_result<NT>(S, (int)S.cand[s], hpos + sdir * epsilon, sdir, false, tri_id, tri_t, tri_u, tri_v);
             }
-            MatSampleD ms = mat_sample(m, S.r1[s], S.r2[s], d, hn, refl);     // pick up next ray, :116,183,291
-            f3 bxdfVal = ms.color * (1.0f / max2(ms.pdf, 1.0e-20f));
-            float cosTheta = dot(ms.direction, hn);
-            const f3 W = fabsf(cosTheta) * bxdfVal;
-            int depth = st & ST_DEPTH_MASK;
-            wa.stackA[(size_t)depth * total_slots + gslot0 + s] = make_float4(explicitColor.x, explicitColor.y, explicitColor.z, W.x);
-            wa.stackB[(size_t)depth * total_slots + gslot0 + s] = make_float2(W.y, W.z);
-            depth++;
-            const f3 off3 = (sign_ada(cosTheta) * hn) * 1.0e-5f;              // :122,189,297
-            const f3 no = hpos + off3, nd = ms.direction;
-            S.ox[s] = no.x; S.oy[s] = no.y; S.oz[s] = no.z; S.dx[s] = nd.x; S.dy[s] = nd.y; S.dz[s] = nd.z;
-            S.prev_pdf[s] = ms.pdf;
-            st = (st & ~(ST_DEPTH_MASK | ST_SPEC | ST_SURF | ST_READY)) | depth | (ms.pureSpecular ? ST_SPEC : 0);
-            if (depth == max_depth) {                                         // recursion_level = 0 -> (0,0,0)
-              S.lx[s] = 0.f; S.ly[s] = 0.f; S.lz[s] = 0.f;
-              st = (st & ~ST_HASRAY) | ST_FOLD;
-              ended = true;
-            } else {
-              newray = true;
-              const f3 ninv = mk3(1.0f / nd.x, 1.0f / nd.y, 1.0f / nd.z);
-              S.ix[s] = ninv.x; S.iy[s] = ninv.y; S.iz[s] = ninv.z;
-              push_cp = mesh_candidate<MESHK>(no, ninv, cnt, nmesh);
-            }
-            S.state[s] = st;
+            const ShadeOut y = wave_shade<RT, MESHK>(S, s, wa, (size_t)(gslot0 + s), total_slots, tri_id, tri_t, cnt, nmesh, nrays);
+            ended = y.ended; newray = y.newray; push_cp = y.push_cp;
           }
         } else {
-          // ------------------------------------------------------------- regenerate
           const int r = i - n_m;
           const bool on = r < n_r;
-          bool need = false, padded = false;
-          int st = 0, item = -1;
-          if (on) {
-            s = S.q_r[par][r];
-            st = S.state[s];
-            item = S.item[s];
-            if (st & ST_FOLD) {                                               // unwind the recursion: integrators.adb:124,191,299
-              f3 L = mk3(S.lx[s], S.ly[s], S.lz[s]);
-              const int depth = st & ST_DEPTH_MASK;
-#pragma unroll 1
-              for (int k0 = depth - 1; k0 >= 0; k0 -= 4) {                    // four levels of loads in flight at a time
-                float4 A[4]; float2 B[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                  const int k = (k0 - j >= 0) ? (k0 - j) : 0;
-                  A[j] = wa.stackA[(size_t)k * total_slots + gslot0 + s];
-                  B[j] = wa.stackB[(size_t)k * total_slots + gslot0 + s];
-                }
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                  if (k0 - j >= 0) {
-                    const f3 W = mk3(A[j].w, B[j].x, B[j].y);
-                    if (RT == GCORE_PT_STUPID) L = W * L;
-                    else L = mk3(A[j].x, A[j].y, A[j].z) + W * L;
-                  }
-                }
-              }
-              const int sub = (st >> ST_SUB_SHIFT) & 3;
-              f3 color = mk3(S.cr[s], S.cg[s], S.cb[s]);
-              bool done;
-              if (aa) {
-                if (sub == 0) color = bg;                                     // :42
-                color = color + L;                                            // :47
-                done = (sub == 3);
-              } else { color = L; done = true; }                              // :60
-              if (done) { wa.colbuf[item] = make_float4(color.x, color.y, color.z, 0.0f); item = -1; }
-              else { S.cr[s] = color.x; S.cg[s] = color.y; S.cb[s] = color.z; }
-              st = (st & ~(ST_FOLD | (3 << ST_SUB_SHIFT))) | (((sub + 1) & 3) << ST_SUB_SHIFT);
-            }
-            need = item < 0;
-            if (!need) S.sample[s] = S.sample[s] + 1u;                        // next sub-pixel sample of the same pass
-          }
-          {                                                                   // next work item (pass, pixel): one atomic per warp
-            const unsigned nm = __ballot_sync(0xffffffffu, need);
-            if (nm) {
-              const int lane = tid & 31, leader = __ffs(nm) - 1;
-              int base = 0;
-              if (lane == leader) base = atomicAdd(&S.pool_next, __popc(nm));
-              base = __shfl_sync(0xffffffffu, base, leader);
-              if (need) {
-                const int got = base + __popc(nm & ((1u << lane) - 1u));
-                starved = true;
-                if (got < S.pool_end) {
-                  const int q = got % a.nslots, unit = got / a.nslots;
-                  const WavePixel px = wave_slot_to_pixel(a, q);
-                  if (px.active) {                                            // (an item of a padding pixel is dropped; the slot asks again next round)
-                    starved = false;
-                    item = got;
-                    S.pixel[s] = (unsigned int)(px.y * a.width + px.x);
-                    S.sample[s] = (unsigned int)(a.first_sample + (aa ? unit * 4 : unit));
-                  } else padded = true;
-                }
-                st &= ~(3 << ST_SUB_SHIFT);
-              }
-            }
-          }
-          if (on) {
-            S.item[s] = item;
-            if (!starved) {
-              const int sub = (st >> ST_SUB_SHIFT) & 3;
-              const unsigned int pixel = S.pixel[s];
-              const int py = (int)(pixel / (unsigned int)a.width), pxx = (int)(pixel - (unsigned int)py * (unsigned int)a.width);
-              const f3 o = ld3(g_scn.cam_pos);
-              const f3 d = wave_eye_ray_dir(a, pxx, py, aa ? sub : -1);
-              S.ox[s] = o.x; S.oy[s] = o.y; S.oz[s] = o.z; S.dx[s] = d.x; S.dy[s] = d.y; S.dz[s] = d.z;
-              S.prev_pdf[s] = 1.0f;                                           // StartSample, materials.ads:25
-              st = (st & (3 << ST_SUB_SHIFT)) | ST_SPEC | ST_HASRAY;          // depth 0
-              newray = true;
-              const f3 cinv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-              S.ix[s] = cinv.x; S.iy[s] = cinv.y; S.iz[s] = cinv.z;
-              push_cp = mesh_candidate<MESHK>(o, cinv, cnt, nmesh);
-            } else {
-              st &= ~(ST_HASRAY | ST_FOLD);
-              retire = (S.exhausted != 0) && !padded;                         // no work left anywhere: the slot retires
-            }
-            S.state[s] = st;
-          }
+          if (on) s = S.q_r[par][r];
+          const RegenOut g = wave_regen<RT, MESHK>(S, s, on, wa, (size_t)(gslot0 + s), total_slots, cnt, nmesh);
+          starved = g.starved; retire = g.retire; newray = g.newray; push_cp = g.push_cp;
         }
-        if constexpr (BVH) {
-          if (newray) { if (push_cp) S.pend[s] = 1 | 4; else S.mesh_res[4 * s + 3] = __int_as_float(-1); }
-          queue_push(newray && push_cp, S.q_t[1], &S.cnt_t[1], s);            // the new path ray starts in M2
-        } else {
-          const int c = queue_push(push_cp, S.q_cp, &S.cnt_cp, s);
-          if (newray) S.cand[s] = (short)c;
-        }
+        const int c = queue_push(push_cp, S.q_cp, &S.cnt_cp, s);
+        if (newray) S.cand[s] = (short)c;
         // paths that reached Max_Trace_Depth and starved slots wait for the next round's regenerate
         queue_push(ended || (starved && !retire), S.q_r[par ^ 1], &S.cnt_r[par ^ 1], s);
         const unsigned rm = __ballot_sync(0xffffffffu, retire);
@@ -791,33 +789,193 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
 
     // ================================================================= M2: mesh stage of the new path rays
     if (tid == 0) S.cnt_r[par] = 0;
-    if constexpr (BVH) {
-      if (tid < 5) S.cnt_m[bpar][tid] = 0;                                    // consumed by Y; shadow rays resolved from here on count for the next Y
-      bvh_stage(1, bpar ^ 1);
-      bpar ^= 1;
-    } else {
-      if (tid < 5) S.cnt_m[tid] = 0;
-      wave_mesh_stage<MESHK, false, NT>(S, S.q_cp, S.cnt_cp, tid);
-    }
+    if (tid < 5) S.cnt_m[tid] = 0;
+    wave_mesh_stage<false, NT>(S, S.q_cp, S.cnt_cp, tid);
     par ^= 1;
     __syncthreads();
   }
+  wave_flush_counters(a, nrays, nmesh, nbounce, 0u, 0u, 0u);
+}
 
-  // statistics: one atomic per warp and counter
-  unsigned int total_rays = __reduce_add_sync(0xffffffffu, nrays);
-  unsigned int total_mesh = __reduce_add_sync(0xffffffffu, nmesh);
-  unsigned int total_bnc  = __reduce_add_sync(0xffffffffu, nbounce);
-  if ((threadIdx.x & 31) == 0 && total_rays) {
-    atomicAdd(&a.counters[0], (unsigned long long)total_rays);
-    atomicAdd(&a.counters[1], (unsigned long long)total_mesh);
-    atomicAdd(&a.counters[2], (unsigned long long)total_bnc);
+// ---------------------------------------------------------------------------------------------------------------------
+// render_bvh_kernel: meshes behind the LBVH -- shading warps and persistent traversal warps in one block
+// ---------------------------------------------------------------------------------------------------------------------
+
+ART_D void shade_group_barrier() { asm volatile("bar.sync 1, %0;" :: "n"(BVH_SHADE_THREADS) : "memory"); }
+ART_D int  vload(const int* p)   { return *(const volatile int*)p; }
+ART_D int  vload(const short* p) { return (int)*(const volatile short*)p; }
+
+template <int RT>
+__global__ void __launch_bounds__(BVH_SHADE_THREADS + BVH_TRAV_THREADS, WAVE_TOTAL_THREADS / (BVH_SHADE_THREADS + BVH_TRAV_THREADS))
+render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
+  constexpr int NS = BVH_SLOTS, NSH = BVH_SHADE_THREADS, NTR = BVH_TRAV_THREADS;
+  constexpr int MESHK = MESHK_BVH;
+  static_assert((NS & (NS - 1)) == 0, "the ring of pending rays wants a power of two");
+  extern __shared__ __align__(16) unsigned char wave_smem_raw[];
+  BvhWaveSmem& S = *reinterpret_cast<BvhWaveSmem*>(wave_smem_raw);
+  const gcore_dev::RenderArgs& a = wa.r;
+  const int tid = threadIdx.x;
+  const int gslot0 = blockIdx.x * NS;
+  const int total_slots = gridDim.x * NS;
+  const unsigned int total_items = (unsigned int)wa.units * (unsigned int)a.nslots;
+  unsigned int nrays = 0, nmesh = 0, nbounce = 0, ntrav = 0;
+  BvhStats tstat; tstat.nodes = 0; tstat.tris = 0;
+  const bool cnt = wa.count_mesh != 0;
+
+  for (int s = tid; s < NS; s += NSH + NTR) { S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s; S.pend[s] = 0; }
+  if (tid == 0) {
+    S.cnt_r[0] = NS; S.cnt_r[1] = 0; S.retired = 0; S.exhausted = 0;
+    S.tq_head = 0; S.tq_tail = 0; S.tq_pub = 0; S.done = 0; S.xwork[0] = 0; S.xwork[1] = 0;
+    for (int b = 0; b < 5; b++) S.cnt_m[b] = 0;
+    wave_refill_pool(S, wa, total_items, NS);
   }
-  if (BVH) {
-    unsigned int tn = __reduce_add_sync(0xffffffffu, tstat.nodes), tt = __reduce_add_sync(0xffffffffu, tstat.tris), tv = __reduce_add_sync(0xffffffffu, ntrav);
-    if ((threadIdx.x & 31) == 0 && tn) {
-      atomicAdd(&a.counters[3], (unsigned long long)tn); atomicAdd(&a.counters[4], (unsigned long long)tt); atomicAdd(&a.counters[5], (unsigned long long)tv);
+  __syncthreads();
+
+  if (tid >= NSH) {
+    // ================================================================= traversal warps: one ray per lane, refilled from the ring
+    const int g = tid - NSH, lane = tid & 31;
+    int* my_stack = &S.tstack[g];
+    int ovf[LBVH_OVERFLOW];                                                   // stack entries beyond the shared short stack (rarely touched)
+    bool active = false;
+    int s = 0, p = 0;
+    f3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f), inv = mk3(0.f, 0.f, 0.f);
+    BvhRayState c; c.node = -1; c.sp = 0; c.best_t = 0.f; c.best_prim = -1; c.best_u = 0.f; c.best_v = 0.f;
+    for (;;) {
+      const unsigned idle_m = __ballot_sync(0xffffffffu, !active);
+      if (idle_m) {
+        // compaction of the traversal lanes: the idle lanes of the warp take the next pending rays (one CAS per warp)
+        int take = 0, h = 0;
+        if (lane == 0) {
+          for (;;) {
+            h = vload(&S.tq_head);
+            const int avail = vload(&S.tq_pub) - h;
+            take = min(avail, __popc(idle_m));
+            if (take <= 0) { take = 0; break; }
+            if (atomicCAS(&S.tq_head, h, h + take) == h) break;
+          }
+        }
+        take = __shfl_sync(0xffffffffu, take, 0); h = __shfl_sync(0xffffffffu, h, 0);
+        if (take > 0) {
+          __threadfence_block();                                              // entries and ray data below tq_pub were written before it was published
+          const int r = __popc(idle_m & ((1u << lane) - 1u));
+          if (!active && r < take) {
+            s = vload(&S.tq[(h + r) & (NS - 1)]);
+            p = vload(&S.pend[s]);
+            o = mk3(S.ox[s], S.oy[s], S.oz[s]); d = mk3(S.dx[s], S.dy[s], S.dz[s]);
+            float t_clip = 1000000.0f;
+            if (p == 2) {                                                     // shadow ray of Compute_Shadow, ray_tracer.adb:109-113
+              const float ht = S.ht[s];
+              const f3 hpos = mk3(o.x + ht * d.x, o.y + ht * d.y, o.z + ht * d.z);
+              d = mk3(S.sx[s], S.sy[s], S.sz[s]);
+              float epsilon = max3(fabsf(hpos.x), fabsf(hpos.y), fabsf(hpos.z)) * 0.000000001f;
+              epsilon = max2(epsilon, 1.0e-30f);
+              o = hpos + d * epsilon;
+              // only a hit with t < maxDist - epsilon2 can change in_shadow (ray_tracer.adb:119-128): a mesh hit beyond it either is
+              // not the closest hit or fails that test itself, so the walk is clipped there (the nearest hit below it stays exact)
+              t_clip = S.sh_thi[s];
+            }
+            inv = mk3(S.ix[s], S.iy[s], S.iz[s]);
+            bvh_state_begin(g_scn.bvh, t_clip, c);
+            ntrav++;
+            active = true;
+          }
+        }
+      }
+      if (!__any_sync(0xffffffffu, active)) {
+        if (vload(&S.done)) break;
+        __nanosleep(100);
+        continue;
+      }
+      if (active) {
+        const bool fin = bvh_state_advance(g_scn.bvh, o, d, inv, 0.0f, BVH_REFILL_STEPS, c, my_stack, NTR, ovf, tstat);
+        if (fin) {
+          S.mesh_res[4 * s + 0] = c.best_t; S.mesh_res[4 * s + 1] = c.best_u; S.mesh_res[4 * s + 2] = c.best_v;
+          S.mesh_res[4 * s + 3] = __int_as_float(c.best_prim);
+          __threadfence_block();
+          *(volatile short*)&S.pend[s] = 0;                                   // the slot's owner sees the ray resolved
+          active = false;
+        }
+      }
     }
+    wave_flush_counters(a, 0u, 0u, 0u, tstat.nodes, tstat.tris, ntrav);
+    return;
   }
+
+  // =================================================================== shading warps: X / rank / Y over the slots whose rays are resolved
+  int par = 0;
+  for (;;) {
+    // ---- X: closest hit, path end or light sample + shadow ray
+    if (tid == 0 && !S.exhausted && S.pool_next >= S.pool_end) wave_refill_pool(S, wa, total_items, NS);
+    for (int s = tid; s < NS; s += NSH) {
+      const int st = S.state[s];
+      const bool on = ((st & (ST_HASRAY | ST_SURF)) == ST_HASRAY) && vload(&S.pend[s]) == 0;   // a slot whose path ray is still in the tree sits this X out
+      ExtendOut x; x.ended = false; x.surf = false; x.push_cs = false; x.bucket = -1;
+      if (on) {
+        __threadfence_block();                                                // the traversal lane wrote mesh_res before it cleared pend
+        const float tri_t = S.mesh_res[4 * s + 0], tri_u = S.mesh_res[4 * s + 1], tri_v = S.mesh_res[4 * s + 2];
+        const int tri_id = __float_as_int(S.mesh_res[4 * s + 3]);
+        x = wave_extend<RT, MESHK>(S, s, st, a, tri_id, tri_t, tri_u, tri_v, cnt, nmesh, nbounce);
+        nrays++;
+        S.xwork[par] = 1;
+        if (x.surf) { if (x.push_cs) S.pend[s] = 2; else S.mesh_res[4 * s + 3] = __int_as_float(-1); }
+      }
+      queue_push(x.ended, S.q_r[par], &S.cnt_r[par], s);
+      ring_push(x.surf && x.push_cs, S.tq, &S.tq_tail, NS, s);                // the shadow ray goes to the traversal warps
+    }
+    shade_group_barrier();
+    if (tid == 0) { __threadfence_block(); *(volatile int*)&S.tq_pub = S.tq_tail; }
+    // ---- rank: surface slots whose shadow query is resolved, bucketed by material
+    for (int s = tid; s < NS; s += NSH) {
+      const int st = S.state[s];
+      const bool ready = ((st & (ST_SURF | ST_HASRAY)) == (ST_SURF | ST_HASRAY)) && vload(&S.pend[s]) == 0;
+      bucket_push(ready, (st >> ST_BUCKET_SHIFT) & 7, s, S.cnt_m, &S.q_sb[0][0], NS);
+    }
+    shade_group_barrier();
+    // ---- Y: shade (sorted by material) + regenerate (queue R)
+    {
+      const int c0 = S.cnt_m[0], c1 = S.cnt_m[1], c2 = S.cnt_m[2], c3 = S.cnt_m[3], c4 = S.cnt_m[4];
+      const int n_surf = c0 + c1 + c2 + c3 + c4;
+      const int n_m = (n_surf + 31) & ~31;
+      const int n_r = S.cnt_r[par];
+      const int n_all = n_m + ((n_r + 31) & ~31);
+      if (n_surf == 0 && n_r == 0 && S.xwork[par] == 0) __nanosleep(400);          // every slot is in the tree: leave the issue slots to the traversal warps
+      for (int i = tid; i < n_all; i += NSH) {
+        bool ended = false, push_cp = false, starved = false, retire = false, newray = false;
+        int s = 0;
+        if (i < n_m) {
+          if (i < n_surf) {
+            int b = 0, off = 0;
+            if (i >= c0) { b = 1; off = c0; if (i >= c0 + c1) { b = 2; off = c0 + c1; if (i >= c0 + c1 + c2) { b = 3; off = c0 + c1 + c2; if (i >= c0 + c1 + c2 + c3) { b = 4; off = c0 + c1 + c2 + c3; } } } }
+            s = S.q_sb[b][i - off];
+            __threadfence_block();
+            const float tri_t = S.mesh_res[4 * s + 0];
+            const int tri_id = __float_as_int(S.mesh_res[4 * s + 3]);
+            const ShadeOut y = wave_shade<RT, MESHK>(S, s, wa, (size_t)(gslot0 + s), total_slots, tri_id, tri_t, cnt, nmesh, nrays);
+            ended = y.ended; newray = y.newray; push_cp = y.push_cp;
+          }
+        } else {
+          const int r = i - n_m;
+          const bool on = r < n_r;
+          if (on) s = S.q_r[par][r];
+          const RegenOut g = wave_regen<RT, MESHK>(S, s, on, wa, (size_t)(gslot0 + s), total_slots, cnt, nmesh);
+          starved = g.starved; retire = g.retire; newray = g.newray; push_cp = g.push_cp;
+        }
+        if (newray) { if (push_cp) S.pend[s] = 1; else S.mesh_res[4 * s + 3] = __int_as_float(-1); }
+        ring_push(newray && push_cp, S.tq, &S.tq_tail, NS, s);                // the new path ray goes to the traversal warps
+        // paths that reached Max_Trace_Depth and starved slots wait for the next round's regenerate
+        queue_push(ended || (starved && !retire), S.q_r[par ^ 1], &S.cnt_r[par ^ 1], s);
+        const unsigned rm = __ballot_sync(0xffffffffu, retire);
+        if (rm && (tid & 31) == 0) atomicAdd(&S.retired, __popc(rm));
+      }
+    }
+    shade_group_barrier();
+    if (S.retired >= NS) { if (tid == 0) *(volatile int*)&S.done = 1; break; }   // uniform: `retired` only changes in Y
+    // (no barrier needed here: the next X touches the other halves of q_r / xwork, and cnt_m is next used after X's barrier)
+    if (tid == 0) { __threadfence_block(); *(volatile int*)&S.tq_pub = S.tq_tail; S.cnt_r[par] = 0; S.xwork[par] = 0; }
+    if (tid < 5) S.cnt_m[tid] = 0;
+    par ^= 1;
+  }
+  wave_flush_counters(a, nrays, nmesh, nbounce, 0u, 0u, 0u);
 }
 
 // K6a: acc[q] := colour(pass k, q) + acc[q] for k = 0 .. units-1 -- the additions of integrators.adb:51/:63 in pass order

