@@ -287,12 +287,12 @@ static cudaError_t launch_wave_bvh(const art::WaveArgs& wa, int sm_count, cudaSt
   constexpr int NT = BVH_SHADE_THREADS + BVH_TRAV_THREADS;
   cudaError_t e = cudaFuncSetAttribute(art::render_bvh_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(art::BvhWaveSmem));
   if (e != cudaSuccess) return e;
-  const int grid = sm_count * (WAVE_TOTAL_THREADS / NT);
+  const int grid = sm_count * BVH_BLOCKS_PER_SM;
   art::render_bvh_kernel<RT><<<grid, NT, sizeof(art::BvhWaveSmem), s>>>(wa);
   return cudaGetLastError();
 }
 
-int wave_total_slots(int sm_count) { return sm_count * WAVE_TOTAL_THREADS; }   // path slots resident on a device, either kernel
+int wave_total_slots(int sm_count) { return sm_count * WAVE_MAX_SLOTS_PER_SM; }   // upper bound of the path slots resident on a device, either kernel
 int wave_max_depth() { return WAVE_MAX_DEPTH; }
 
 cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, int count_mesh, cudaStream_t s) {

@@ -47,6 +47,7 @@ namespace art {
 // Block shape of render_wave_kernel: NT threads = NT path slots per block, 1024 / NT blocks per SM.
 //   1024 x 1 -- the biggest slot pool wins (measured 256x4 105 ms, 384x3 93, 512x2 85.5, 1024x1 77.4)
 #define WAVE_TOTAL_THREADS 1024
+#define WAVE_MAX_SLOTS_PER_SM 1536         // what the per-slot bounce stacks in global memory are sized for
 #ifndef SPH_UNROLL
 #define SPH_UNROLL 1
 #endif
@@ -62,12 +63,23 @@ constexpr int kSphereUnroll = SPH_UNROLL;     // unroll factor of the sphere loo
 
 #define WAVE_PAIR_TRIS 8                  // constant-memory meshes up to this size are tested as (ray, triangle) pairs
 
-// render_bvh_kernel: 512 slots, 256 shading + 256 traversal threads per block, two blocks per SM
+// render_bvh_kernel: 512 slots, 288 shading + 288 traversal threads per block, two blocks per SM (measured on C5 at 960x540:
+// 256+256 23.4 ms, 288+288 22.4, 320+192 27.1, 192+320 24.7, 128+384 28.3, 384+128 38.1; one block of 1024 slots 23.5;
+// refill every 2 / 4 / 8 / 16 nodes 24.0 / 23.2 / 23.0 / 23.8)
+#ifndef BVH_SLOTS
 #define BVH_SLOTS 512
-#define BVH_SHADE_THREADS 256
-#define BVH_TRAV_THREADS 256
+#endif
+#ifndef BVH_SHADE_THREADS
+#define BVH_SHADE_THREADS 288
+#endif
+#ifndef BVH_TRAV_THREADS
+#define BVH_TRAV_THREADS 288
+#endif
+#ifndef BVH_BLOCKS_PER_SM
+#define BVH_BLOCKS_PER_SM (WAVE_TOTAL_THREADS / BVH_SLOTS)      // 1024 path slots per SM, like render_wave_kernel
+#endif
 #ifndef BVH_REFILL_STEPS
-#define BVH_REFILL_STEPS 4                // nodes a traversal lane walks between two looks at the ring of pending rays
+#define BVH_REFILL_STEPS 8                // nodes a traversal lane walks between two looks at the ring of pending rays
 #endif
 
 enum { ST_DEPTH_MASK = 31, ST_SUB_SHIFT = 5, ST_SPEC = 1 << 7, ST_HASRAY = 1 << 8, ST_FOLD = 1 << 9, ST_SURF = 1 << 10,
@@ -131,7 +143,7 @@ ART_D int queue_push(bool pred, short* q, int* cnt, int slot) {
   return pred ? pos : -1;
 }
 
-// the same into a ring of `size` entries (power of two) with a free-running reservation counter
+// the same into a ring of `size` entries with a free-running reservation counter
 ART_D void ring_push(bool pred, short* q, int* tail, int size, int slot) {
   const unsigned m = __ballot_sync(0xffffffffu, pred);
   if (m == 0u) return;
@@ -140,7 +152,7 @@ ART_D void ring_push(bool pred, short* q, int* tail, int size, int slot) {
   int base = 0;
   if (lane == leader) base = atomicAdd(tail, __popc(m));
   base = __shfl_sync(0xffffffffu, base, leader);
-  if (pred) q[(base + __popc(m & ((1u << lane) - 1u))) & (size - 1)] = (short)slot;
+  if (pred) q[(unsigned)(base + __popc(m & ((1u << lane) - 1u))) % (unsigned)size] = (short)slot;
 }
 
 // rank `slot` inside the material bucket of its warp peers and file it in that bucket's queue (the counting sort of the surface
@@ -806,11 +818,11 @@ ART_D int  vload(const int* p)   { return *(const volatile int*)p; }
 ART_D int  vload(const short* p) { return (int)*(const volatile short*)p; }
 
 template <int RT>
-__global__ void __launch_bounds__(BVH_SHADE_THREADS + BVH_TRAV_THREADS, WAVE_TOTAL_THREADS / (BVH_SHADE_THREADS + BVH_TRAV_THREADS))
+__global__ void __launch_bounds__(BVH_SHADE_THREADS + BVH_TRAV_THREADS, BVH_BLOCKS_PER_SM)
 render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
   constexpr int NS = BVH_SLOTS, NSH = BVH_SHADE_THREADS, NTR = BVH_TRAV_THREADS;
   constexpr int MESHK = MESHK_BVH;
-  static_assert((NS & (NS - 1)) == 0, "the ring of pending rays wants a power of two");
+  static_assert(NS * BVH_BLOCKS_PER_SM <= WAVE_MAX_SLOTS_PER_SM, "the per-slot stacks are sized for WAVE_MAX_SLOTS_PER_SM slots");
   extern __shared__ __align__(16) unsigned char wave_smem_raw[];
   BvhWaveSmem& S = *reinterpret_cast<BvhWaveSmem*>(wave_smem_raw);
   const gcore_dev::RenderArgs& a = wa.r;
@@ -859,7 +871,7 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
           __threadfence_block();                                              // entries and ray data below tq_pub were written before it was published
           const int r = __popc(idle_m & ((1u << lane) - 1u));
           if (!active && r < take) {
-            s = vload(&S.tq[(h + r) & (NS - 1)]);
+            s = vload(&S.tq[(unsigned)(h + r) % (unsigned)NS]);
             p = vload(&S.pend[s]);
             o = mk3(S.ox[s], S.oy[s], S.oz[s]); d = mk3(S.dx[s], S.dy[s], S.dz[s]);
             float t_clip = 1000000.0f;

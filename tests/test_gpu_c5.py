@@ -66,17 +66,17 @@ def test_c5_scene_queries_match_oracle(c5, pkg, ob):
 
 def test_c5_primary_hits_and_small_render_bit_exact(c5, pkg, ob):
     gs, osc, pos, tris = c5
-    w, h = 192, 108
+    w, h = 384, 216
     g = gs.primary_hits(w, h); o = osc.primary_hits(w, h, mesh_mode=ob.MESH_NEAREST)
     for f in g.dtype.names:
         a, b = g[f], o[f]
         if a.dtype.kind == "f":
             a, b = _bits(a), _bits(b)
         assert np.array_equal(a, b), f
-    rt = pkg.Ray_Tracer(); rt.Threads_Num = 1; rt.seed = 0x5EED0005
+    rt = pkg.Ray_Tracer(); rt.Threads_Num = 2; rt.seed = 0x5EED0005
     rt.Init_Render(pkg.PT_MIS); rt.Resize_Viewport(w, h)
     hdr = rt.Render_Pass(read_hdr=True)
-    acc, rays = osc.render(ob.make_params(w, h, ob.PT_MIS, passes=1, seed=0x5EED0005, mesh_mode=ob.MESH_NEAREST))
+    acc, rays = osc.render(ob.make_params(w, h, ob.PT_MIS, passes=2, seed=0x5EED0005, mesh_mode=ob.MESH_NEAREST))
     assert np.array_equal(_bits(hdr[..., :3]), _bits(acc))
     assert int(rt.last_stats.rays) == rays
 
