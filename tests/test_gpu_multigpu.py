@@ -76,7 +76,7 @@ def test_c_harness_with_all_gpus_writes_the_same_bmp(pkg, tmp_path):
         r = subprocess.run([exe, pkg.LIB_PATH, os.path.join(ROOT, "data", "pyramid2.vsgf"), bmp, "320", "200", "4", "2", str(g)],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr
-        out.append((open(bmp, "rb").read(), r.stdout.split()[:2]))
+        out.append((open(bmp, "rb").read(), r.stdout.strip().splitlines()[-1].split()[:2]))     # (NCCL may print its version banner first)
     assert out[0][0] == out[1][0] and out[0][1] == out[1][1]      # same bytes, same spp and ray count
 
 
