@@ -17,7 +17,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libgcore_b200.so")      # the one product library; experiment builds are loaded by profiles/tools/bench_variant.py
+LIB_PATH = os.path.join(_HERE, "libgcore_b200.so")      # the product library (bit-exact numerics); experiment builds are loaded by profiles/tools/bench_variant.py
+FAST_LIB_PATH = os.path.join(_HERE, "libgcore_b200_fast.so")   # the NUMERICS=fast experiment build of the same sources (csrc/Makefile)
+NUMERICS = "exact"
 DEFAULT_VSGF = os.path.join(ROOT, "data", "pyramid2.vsgf")
 
 # ---- POD layouts of include/gcore.h -------------------------------------------------------------------------------
@@ -65,10 +67,24 @@ EXPORTS = [
     "gcore_primary_hits", "gcore_accum_device_ptr", "gcore_resolve_device", "gcore_resolve_gathered_device",
     "gcore_stream", "gcore_synchronize", "gcore_last_error", "gcore_bvh_info", "gcore_kernel_regs", "gcore_bvh_bench", "gcore_load_frame", "gcore_set_stats_level", "gcore_get_bvh_counters",
     "gcore_set_gpu_count", "gcore_get_gpu_count", "gcore_device_kernel_ms", "gcore_set_seam_two_sided", "gcore_set_mesh_material",
-    "gcore_set_mesh_normals_3f", "gcore_use_committed_scene", "gcore_get_committed_scene", "gcore_bvh_occluded_batch",
+    "gcore_set_mesh_normals_3f", "gcore_use_committed_scene", "gcore_get_committed_scene", "gcore_bvh_occluded_batch", "gcore_seam_stats",
 ]
 
 _lib = None
+
+
+def select_numerics(mode):
+    """"exact" (default, the product): libgcore_b200.so, bit-identical to the reference arithmetic.  "fast": libgcore_b200_fast.so, an
+    EXPERIMENT build of the same sources (FMA contraction, approximate division / square root): 18 % faster, but it shifts image means by
+    up to ~1.6 % and does not meet SURVEY 8d's block-RMSE acceptance (tests/test_gpu_fast_numerics.py says why) -- for measurements only.
+    One library per process: call before anything else of this package."""
+    global LIB_PATH, NUMERICS
+    if _lib is not None:
+        raise GCoreError("select_numerics must be called before the library is loaded")
+    if mode not in ("exact", "fast"):
+        raise GCoreError("numerics mode must be 'exact' or 'fast'")
+    NUMERICS = mode
+    LIB_PATH = FAST_LIB_PATH if mode == "fast" else os.path.join(_HERE, "libgcore_b200.so")
 
 
 def lib():
@@ -127,6 +143,7 @@ def lib():
     L.gcore_use_committed_scene.argtypes = [i32]
     L.gcore_get_committed_scene.argtypes = [vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     L.gcore_bvh_occluded_batch.argtypes = [i32, vp, f32, f32, vp]
+    L.gcore_seam_stats.argtypes = [vp]
     _lib = L
     return L
 

@@ -16,9 +16,13 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using gcore_dev::LbvhBuffers;
@@ -105,6 +109,28 @@ struct State {
 };
 
 State& S() { static State s; return s; }
+
+// ---- the one-ray seam under many host threads (scene_hydra_embree.adb:426-446 calls gcore_closest_hit from every Ada task):
+// flat combining.  A caller files its ray in the open batch; the first caller to find no leader becomes the leader, launches ONE
+// kernel for everything filed so far, hands the answers out and goes on with the next batch while there is one.  T threads thus
+// share a launch + synchronisation per ~T rays instead of queueing for one each.  Waiters spin on their own flag (a render task
+// has nothing else to do, and a futex wake-up costs more than the launch); a new leader that knows of companions on their way in
+// gives them up to 3 us to file before it launches.
+struct Seam {
+  std::mutex m;
+  std::condition_variable cv;
+  gcore_dev::SeamRequest* h_req[2] = {nullptr, nullptr};       // mapped pinned host memory, two batches (one being filled, one in flight)
+  gcore_dev::SeamRequest* d_req[2] = {nullptr, nullptr};       // the same memory as the device sees it
+  struct Waiter { gcore_HitCpp* out; int found; std::atomic<int> done; };
+  Waiter* waiter[2][GC_SEAM_BATCH];
+  int  n_open = 0;                                             // requests filed in the open batch
+  int  open_buf = 0;
+  int  last_n = 1;                                             // size of the previous batch: how many companions to expect
+  bool leader_active = false;
+  std::atomic<int> inside{0};                                  // threads currently inside gcore_closest_hit
+  unsigned long long launches = 0, rays = 0;                   // combined batches launched / rays answered (gcore_seam_stats)
+};
+Seam& seam() { static Seam s; return s; }
 
 int fail(int code, const std::string& text) {
   State& s = S();
@@ -958,13 +984,93 @@ int gcore_bvh_bench(int n, const gcore_ray* rays, float t_near, float t_far, int
   GC_CATCH_INT
 }
 
+// one combined batch: called by the leader without the seam mutex
+static int seam_launch(int buf, int n) {
+  State& s = S();
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  if (int rc = sync_scene(0)) return rc;
+  Device& dv = s.dev[0];
+  if (dv.legacy_bvh.ntris <= 0) { for (int i = 0; i < n; i++) seam().h_req[buf][i].found = 0; return 0; }
+  cudaError_t e = gcore_dev::launch_bvh_seam(n, seam().d_req[buf], s.seam_two_sided, dv.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(dv.stream);
+  if (e != cudaSuccess) return fail_cuda(e, "gcore_closest_hit");
+  return 0;
+}
+
 bool gcore_closest_hit(const float a_rayPos[3], const float a_rayDir[3], float t_near, float t_far, gcore_HitCpp* pHit) {   // :196-238
   if (!a_rayPos || !a_rayDir || !pHit) return false;
-  gcore_ray r; memcpy(r.origin, a_rayPos, 12); memcpy(r.direction, a_rayDir, 12);
-  gcore_HitCpp h = *pHit; int32_t f = 0;
-  if (gcore_bvh_closest_hit_batch(1, &r, t_near, t_far, &h, &f) != 0) return false;
-  if (f) *pHit = h;                                                    // written only on a hit (:222-235)
-  return f != 0;
+  try {
+    Seam& q = seam();
+    std::unique_lock<std::mutex> lk(q.m);
+    if (!q.h_req[0]) {                                                  // first call: the request / answer buffers
+      State& s = S();
+      std::lock_guard<std::recursive_mutex> slk(s.mu);
+      if (ensure_device(0)) return false;
+      for (int b = 0; b < 2; b++) {
+        if (cudaHostAlloc(&q.h_req[b], sizeof(gcore_dev::SeamRequest) * GC_SEAM_BATCH, cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(&q.d_req[b], q.h_req[b], 0) != cudaSuccess) { fail_cuda(cudaGetLastError(), "cudaHostAlloc seam"); q.h_req[0] = nullptr; return false; }
+      }
+    }
+    while (q.n_open >= GC_SEAM_BATCH) q.cv.wait(lk);                    // the open batch is full: wait for the leader to take it
+    struct InsideGuard { std::atomic<int>& c; InsideGuard(std::atomic<int>& x) : c(x) { c.fetch_add(1); } ~InsideGuard() { c.fetch_sub(1); } } inside_guard(q.inside);
+    Seam::Waiter me; me.out = pHit; me.found = 0; me.done.store(0);
+    const int buf = q.open_buf, idx = q.n_open++;
+    gcore_dev::SeamRequest& r = q.h_req[buf][idx];
+    memcpy(r.ray.origin, a_rayPos, 12); memcpy(r.ray.direction, a_rayDir, 12); r.t_near = t_near; r.t_far = t_far; r.found = 0;
+    q.waiter[buf][idx] = &me;
+    if (!q.leader_active) {
+      q.leader_active = true;
+      while (q.n_open > 0) {                                            // lead: one launch per batch until nothing is pending
+        if (q.inside.load() > q.n_open || q.last_n > q.n_open) {        // companions on their way in: a moment to file (a launch costs ~25 us)
+          const int want = q.last_n;
+          lk.unlock();
+          const auto t0 = std::chrono::steady_clock::now();
+          while (*(volatile int*)&q.n_open < want || q.inside.load() > *(volatile int*)&q.n_open) {
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(3)) break;
+          }
+          lk.lock();
+        }
+        const int b = q.open_buf, n = q.n_open;
+        q.last_n = n; q.open_buf ^= 1; q.n_open = 0;                    // later callers file into the other buffer
+        q.cv.notify_all();
+        lk.unlock();
+        const int rc = seam_launch(b, n);
+        lk.lock();
+        q.launches++; q.rays += (unsigned long long)n;
+        for (int i = 0; i < n; i++) {                                   // hand the answers out (records are written only on a hit, :222-235)
+          Seam::Waiter* w = q.waiter[b][i];
+          w->found = (rc == 0) ? q.h_req[b][i].found : 0;
+          if (w->found) *w->out = q.h_req[b][i].hit;
+          w->done.store(1, std::memory_order_release);                  // (the waiter may leave its frame right after this store)
+        }
+      }
+      q.leader_active = false;
+      lk.unlock();
+    } else {
+      lk.unlock();
+      int spins = 0;
+      while (!me.done.load(std::memory_order_acquire)) {
+        if (++spins > (1 << 22)) std::this_thread::yield();             // a stuck device: stop burning the core, keep waiting
+      }
+    }
+    if (!me.found) return false;
+    // flattened triangle id -> (primIndex inside its mesh, instIndex)
+    State& s = S();
+    const int flat = pHit->primIndex;
+    {
+      std::lock_guard<std::recursive_mutex> slk(s.mu);
+      if (flat >= 0 && flat < (int)s.flat.prim.size()) { pHit->primIndex = s.flat.prim[flat]; pHit->instIndex = s.flat.inst[flat]; pHit->geomIndex = 0; }
+    }
+    return true;
+  } catch (...) { fail(GCORE_E_STATE, "gcore_closest_hit: internal error"); return false; }
+}
+
+int gcore_seam_stats(uint64_t* out2) {
+  if (!out2) return fail(GCORE_E_ARG, "gcore_seam_stats: null");
+  Seam& q = seam();
+  std::lock_guard<std::mutex> lk(q.m);
+  out2[0] = q.launches; out2[1] = q.rays;
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------- analytic scene

@@ -46,6 +46,10 @@ cudaError_t launch_closest_batch(int mesh_kind, int n, const gcore_ray* d_rays, 
 // pure triangle query on the committed LBVH (legacy gcore_closest_hit semantics)
 // two_sided: Embree's rtcIntersect1 semantics (both faces) instead of the reference's one-sided triangle test
 cudaError_t launch_bvh_batch(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, int two_sided, cudaStream_t s);
+// the combined batch of pending gcore_closest_hit calls: requests / answers in mapped pinned host memory (n <= GC_SEAM_BATCH)
+#define GC_SEAM_BATCH 64
+struct SeamRequest { gcore_ray ray; float t_near, t_far; gcore_HitCpp hit; int found; };
+cudaError_t launch_bvh_seam(int n, SeamRequest* d_req, int two_sided, cudaStream_t s);
 // occlusion query on the committed legacy scene (rtcOccluded1 semantics: any hit inside (t_near, t_far)); d_occluded[i] = 0 / 1
 cudaError_t launch_bvh_occluded(int n, const gcore_ray* d_rays, float t_near, float t_far, int* d_occluded, int two_sided, cudaStream_t s);
 // the same kernel on either LBVH (which: 0 legacy scene, 1 shaded mesh); d_counters != null: also count nodes visited,

@@ -156,6 +156,31 @@ __global__ void __launch_bounds__(RENDER_BLOCK) bvh_batch_kernel(int n, const gc
   }
 }
 
+// the one-ray seam (gcore_closest_hit): a combined batch of the calls that are pending across the host's threads.  Requests and
+// answers live in mapped pinned host memory -- the kernel reads the rays and writes the hit records over PCIe itself, so a batch
+// costs one launch and one stream synchronisation, no copies.
+template <bool TWO_SIDED>
+__global__ void __launch_bounds__(32) bvh_seam_kernel(int n, gcore_dev::SeamRequest* __restrict__ req) {
+  // one ray per block (lane 0 of its only warp): a handful of latency-bound walks, spread over the SMs instead of serialising in one warp
+  const int i = blockIdx.x;
+  if (i >= n || threadIdx.x != 0) return;
+  const BvhView& bv = g_scn.bvh_legacy;
+  const f3 o = ld3(req[i].ray.origin), d = ld3(req[i].ray.direction);
+  int prim = -1, slot = -1; float t = 0.f, u = 0.f, v = 0.f;
+  BvhStats st; st.nodes = 0; st.tris = 0;
+  bvh_closest_slot_t<false, TWO_SIDED, false>(bv, o, d, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), req[i].t_near, req[i].t_far, prim, t, u, v, slot, st);
+  if (prim >= 0) {
+    gcore_HitCpp hc;
+    hc.primIndex = prim; hc.geomIndex = 0; hc.instIndex = 0; hc.t = t;
+    const float4 e1 = __ldg(&bv.tris[3 * slot + 1]), e2 = __ldg(&bv.tris[3 * slot + 2]);
+    const f3 ng = cross(mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z));
+    hc.normal[0] = ng.x; hc.normal[1] = ng.y; hc.normal[2] = ng.z;
+    hc.texCoord[0] = v; hc.texCoord[1] = u;
+    req[i].hit = hc;
+  }
+  req[i].found = (prim >= 0) ? 1 : 0;
+}
+
 // Ada float -> Unsigned_32 conversion rounds to nearest, ties away from zero (ray_tracer.adb:51-53)
 __device__ __forceinline__ uint32_t to_u32_round(float v) {
   float f = floorf(v);
@@ -235,6 +260,13 @@ cudaError_t launch_bvh_batch(int n, const gcore_ray* d_rays, float t_near, float
   if (n <= 0) return cudaSuccess;
   if (two_sided) bvh_batch_kernel<false, true, false><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, d_hits, d_found, 0, nullptr);
   else bvh_batch_kernel<false, false, false><<<blocks_for(n, RENDER_BLOCK), RENDER_BLOCK, 0, s>>>(n, d_rays, t_near, t_far, d_hits, d_found, 0, nullptr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bvh_seam(int n, SeamRequest* d_req, int two_sided, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  if (two_sided) bvh_seam_kernel<true><<<n, 32, 0, s>>>(n, d_req);
+  else bvh_seam_kernel<false><<<n, 32, 0, s>>>(n, d_req);
   return cudaGetLastError();
 }
 

@@ -266,6 +266,7 @@ def main():
     ap.add_argument("--workload", default="C4_1024", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the short C5_small (LBVH scene) block of the default line")
+    ap.add_argument("--numerics", default="exact", choices=["exact", "fast"], help="exact: the bit-exact product build (default); fast: the opt-in FMA / approximate-division build")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -288,6 +289,7 @@ def main():
         cpu_group = dist.new_group(backend="gloo")           # host-side barrier for the phase in which rank 0 drives every GPU itself
 
     pkg = ge.load_package()
+    pkg.select_numerics(args.numerics)
     L = pkg.lib()
     rt = pkg.Ray_Tracer()
     rt.Threads_Num = units; rt.Anti_Aliasing_On = bool(aa); rt.Max_Trace_Depth = depth; rt.seed = SEED
@@ -429,7 +431,8 @@ def main():
                                                      if args.workload.startswith("C5") else "scene.adb Cornell box + 2 spheres + sphere light + data/pyramid2.vsgf"),
                            "seed": SEED, "parallelism": "tiles32x32_rr%d" % world,
                            "l2": "256 MiB buffer written between timed steps (outside the per-step CUDA events); inputs are < L2",
-                           "numerics": "bit-exact mode (-fmad=false, IEEE div/sqrt), identical to the CPU oracle",
+                           "numerics": ("bit-exact mode (-fmad=false, IEEE div/sqrt), identical to the CPU oracle" if args.numerics == "exact" else
+                                        "NUMERICS=fast build (FMA contraction, approximate div/sqrt, FTZ): Monte-Carlo tolerance of SURVEY 8d, not bit-exact"),
                            "value_path": "one process per GPU (torchrun), torch.distributed/NCCL gather of the accumulators" if world > 1 else "one process, one GPU",
                            "e2e_path": "ONE host process: gcore_render() with host buffers; N > 1: gcore_set_gpu_count(N), the library drives every GPU and gathers over NCCL"},
                 "msamples_per_s": (npx * units * (4 if aa else 1)) / (step_ms / args.steps * 1e-3) / 1e6,

@@ -151,6 +151,9 @@ GCORE_API int gcore_closest_hit_batch(int n, const gcore_ray* rays, gcore_hit* h
 /* triangle-only query on the committed legacy scene (section 1) for n host rays; found[i] != 0 on a hit */
 GCORE_API int gcore_bvh_closest_hit_batch(int n, const gcore_ray* rays, float t_near, float t_far,
                                           gcore_HitCpp* hits, int32_t* found);
+/* gcore_closest_hit combines the calls that are pending across the host's threads into one kernel launch (flat combining):
+ * out2 = {launches so far, rays answered so far}; rays / launches = the average batch */
+GCORE_API int gcore_seam_stats(uint64_t* out2);
 /* occlusion query on the committed scene for n host rays (the rtcOccluded1 counterpart, cpp/embree3/rtcore_scene.h:128, which the
  * reference's shim never exposed): occluded[i] = 1 if ANY triangle is hit with t in (t_near, t_far) */
 GCORE_API int gcore_bvh_occluded_batch(int n, const gcore_ray* rays, float t_near, float t_far, int32_t* occluded);

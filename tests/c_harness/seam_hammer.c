@@ -15,6 +15,7 @@ typedef struct { int primIndex, geomIndex, instIndex; float t, normal[3], texCoo
 typedef void (*fn_void)(void);
 typedef int (*fn_add)(const float*, int, const int*, int);
 typedef bool (*fn_hit)(const float*, const float*, float, float, HitCpp*);
+typedef int (*fn_stats)(unsigned long long*);
 
 static fn_hit closest_hit;
 static int per_thread;
@@ -68,10 +69,14 @@ int main(int argc, char** argv) {
   for (int i = 0; i < n; i++) { wp[i] = -2; wt[i] = 0; }
   for (int i = 0; i < nref; i++) { HitCpp h; memset(&h, 0, sizeof h); h.primIndex = -1; closest_hit(ray_o + 3 * i, ray_d + 3 * i, 0.0f, 100000.0f, &h); wp[i] = h.primIndex; wt[i] = h.t; }
   pthread_t* th = malloc(sizeof(pthread_t) * threads);
+  fn_stats seam_stats = (fn_stats)dlsym(L, "gcore_seam_stats");
+  unsigned long long s0[2] = {0, 0}, s1[2] = {0, 0};
+  if (seam_stats) seam_stats(s0);
   double t0 = now();
   for (long k = 0; k < threads; k++) pthread_create(&th[k], NULL, worker, (void*)k);
   for (int k = 0; k < threads; k++) pthread_join(th[k], NULL);
   double dt = now() - t0;
+  if (seam_stats) seam_stats(s1);
   /* correctness pass: same rays again from all threads, compared with the single-threaded answers where known */
   for (int i = nref; i < n; i++) { wp[i] = -2; }
   want_prim = NULL;
@@ -87,8 +92,8 @@ int main(int argc, char** argv) {
     per_thread = save;
     for (int i = 0; i < nref; i++) hits += wp[i] >= 0;
   }
-  printf("{\"threads\": %d, \"rays\": %d, \"seconds\": %.4f, \"rays_per_s\": %.1f, \"us_per_ray_per_thread\": %.2f, \"mismatches\": %ld, \"hit_rate\": %.3f}\n",
-         threads, n, dt, n / dt, 1e6 * dt * threads / n, bad, (double)hits / nref);
+  printf("{\"threads\": %d, \"rays\": %d, \"seconds\": %.4f, \"rays_per_s\": %.1f, \"us_per_ray_per_thread\": %.2f, \"mismatches\": %ld, \"hit_rate\": %.3f, \"launches\": %llu, \"rays_per_launch\": %.2f}\n",
+         threads, n, dt, n / dt, 1e6 * dt * threads / n, bad, (double)hits / nref, s1[0] - s0[0], (double)(s1[1] - s0[1]) / (double)(s1[0] - s0[0] ? s1[0] - s0[0] : 1));
   destroy();
   return bad ? 1 : 0;
 }
