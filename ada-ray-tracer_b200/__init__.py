@@ -84,7 +84,8 @@ def select_numerics(mode):
     if mode not in ("exact", "fast"):
         raise GCoreError("numerics mode must be 'exact' or 'fast'")
     NUMERICS = mode
-    LIB_PATH = FAST_LIB_PATH if mode == "fast" else os.path.join(_HERE, "libgcore_b200.so")
+    if mode == "fast":
+        LIB_PATH = FAST_LIB_PATH
 
 
 def lib():

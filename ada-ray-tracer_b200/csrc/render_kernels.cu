@@ -309,7 +309,7 @@ static cudaError_t launch_wave_const(const art::WaveArgs& wa, int sm_count, cuda
   // a per-device attribute (one host process may drive several GPUs): set it with every launch, it costs a microsecond
   cudaError_t e = cudaFuncSetAttribute(art::render_wave_kernel<RT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
   if (e != cudaSuccess) return e;
-  const int grid = sm_count * (WAVE_TOTAL_THREADS / NT);                     // persistent: one wave of resident blocks
+  const int grid = sm_count * WAVE_BLOCKS_PER_SM(NT);                        // persistent: one wave of resident blocks
   art::render_wave_kernel<RT, NT><<<grid, NT, sizeof(Smem), s>>>(wa);
   return cudaGetLastError();
 }

@@ -82,6 +82,15 @@ constexpr int kSphereUnroll = SPH_UNROLL;     // unroll factor of the sphere loo
 #define BVH_REFILL_STEPS 8                // nodes a traversal lane walks between two looks at the ring of pending rays
 #endif
 
+// material bucket of a surface slot = its place in stage Y's thread order (measured on the bench workload: Lambert, Phong, glass,
+// mirror 77.8 ms; Phong first 83.4 ms)
+#if defined(BUCKET_ORDER_PHONG_FIRST)
+#define BUCKET_OF(type) ((type) == MAT_PHONG ? 0 : (type) == MAT_GLASS ? 1 : (type) == MAT_LAMBERT ? 2 : (type) == MAT_MIRROR ? 3 : 4)
+#elif defined(BUCKET_ORDER_PHONG_LAST)
+#define BUCKET_OF(type) ((type) == MAT_LAMBERT ? 0 : (type) == MAT_GLASS ? 1 : (type) == MAT_MIRROR ? 2 : (type) == MAT_PHONG ? 4 : 3)
+#else
+#define BUCKET_OF(type) ((type) == MAT_LAMBERT ? 0 : (type) == MAT_PHONG ? 1 : (type) == MAT_GLASS ? 2 : (type) == MAT_MIRROR ? 3 : 4)
+#endif
 enum { ST_DEPTH_MASK = 31, ST_SUB_SHIFT = 5, ST_SPEC = 1 << 7, ST_HASRAY = 1 << 8, ST_FOLD = 1 << 9, ST_SURF = 1 << 10,
        ST_BUCKET_SHIFT = 11 /* 3 bits: material bucket of a surface slot */ };
 
@@ -122,9 +131,11 @@ struct BvhWaveSmem : WavePathSmem<BVH_SLOTS> {
   float mesh_res[4 * BVH_SLOTS];     // result of the slot's last mesh query: t, u, v, bits(triangle id or -1)
   short pend[BVH_SLOTS];             // 0: no ray in the tree; 1 = path ray, 2 = shadow ray queued / being walked (written back to 0 by the traversal lane)
   short tq[BVH_SLOTS];               // ring of slots with a pending ray: producers = shading threads, consumers = traversal warps
+  short xq[BVH_SLOTS];               // ring of slots whose path ray is resolved (ready for X): producers = traversal lanes and Y, -1 = not written yet
   short q_sb[5][BVH_SLOTS];          // surface slots whose shadow query is resolved, per material bucket (consumed by Y)
   int   tstack[LBVH_SHORT_STACK * BVH_TRAV_THREADS];   // short stack of traversal lane g: entry k at [k * BVH_TRAV_THREADS + g]
   int   tq_head, tq_tail, tq_pub;    // consumed / reserved by producers / published (entries below tq_pub are written)
+  int   xq_tail, xq_hi;              // reserved by producers / snapshot taken for this round's X
   int   cnt_m[5];
   int   done, xwork[2];              // xwork[parity]: did this round's X find a slot to extend?
 };
@@ -404,7 +415,7 @@ ART_D ExtendOut wave_extend(SM& S, int s, int st, const gcore_dev::RenderArgs& a
       out.push_cs = mesh_candidate<MESHK>(so, sinv, cnt, nmesh);
     }
     const int type = g_scn.mats[h.mat].type;
-    out.bucket = (type == MAT_LAMBERT) ? 0 : (type == MAT_PHONG) ? 1 : (type == MAT_GLASS) ? 2 : (type == MAT_MIRROR) ? 3 : 4;
+    out.bucket = BUCKET_OF(type);
     st |= out.bucket << ST_BUCKET_SHIFT;
   }
   if (out.ended) {
@@ -680,8 +691,13 @@ ART_D void wave_mesh_result(const WaveSmem<NT>& S, int c, f3 o, f3 d, bool want_
   }
 }
 
+#ifdef WAVE_BLOCKS_CONST
+#define WAVE_BLOCKS_PER_SM(NT) WAVE_BLOCKS_CONST
+#else
+#define WAVE_BLOCKS_PER_SM(NT) (WAVE_TOTAL_THREADS / (NT))
+#endif
 template <int RT, int NT>
-__global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kernel(const __grid_constant__ WaveArgs wa) {
+__global__ void __launch_bounds__(NT, WAVE_BLOCKS_PER_SM(NT)) render_wave_kernel(const __grid_constant__ WaveArgs wa) {
   constexpr int NS = WAVE_SLOTS(NT);        // path slots of this block
   constexpr int MESHK = MESHK_CONST;
   extern __shared__ __align__(16) unsigned char wave_smem_raw[];
@@ -761,9 +777,15 @@ __global__ void __launch_bounds__(NT, WAVE_TOTAL_THREADS / NT) render_wave_kerne
       const int n_m = (n_surf + 31) & ~31;
       const int n_r = S.cnt_r[par];
       const int n_all = n_m + ((n_r + 31) & ~31);
-      for (int i = tid; i < n_all; i += NT) {
+      for (int i0 = tid; i0 < n_all; i0 += NT) {
         bool ended = false, push_cp = false, starved = false, retire = false, newray = false;
         int s = 0;
+#ifdef WAVE_REGEN_FIRST
+        const int n_rp = n_all - n_m;
+        const int i = (i0 < n_rp) ? (n_m + i0) : (i0 - n_rp);                // queue R on the first threads, the shaded slots behind it
+#else
+        const int i = i0;
+#endif
         if (i < n_m) {
           if (i < n_surf) {
             s = S.q_s[i];
@@ -834,10 +856,10 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
   BvhStats tstat; tstat.nodes = 0; tstat.tris = 0;
   const bool cnt = wa.count_mesh != 0;
 
-  for (int s = tid; s < NS; s += NSH + NTR) { S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s; S.pend[s] = 0; }
+  for (int s = tid; s < NS; s += NSH + NTR) { S.item[s] = -1; S.state[s] = 0; S.q_r[0][s] = (short)s; S.pend[s] = 0; S.xq[s] = -1; }
   if (tid == 0) {
     S.cnt_r[0] = NS; S.cnt_r[1] = 0; S.retired = 0; S.exhausted = 0;
-    S.tq_head = 0; S.tq_tail = 0; S.tq_pub = 0; S.done = 0; S.xwork[0] = 0; S.xwork[1] = 0;
+    S.tq_head = 0; S.tq_tail = 0; S.tq_pub = 0; S.xq_tail = 0; S.xq_hi = 0; S.done = 0; S.xwork[0] = 0; S.xwork[1] = 0;
     for (int b = 0; b < 5; b++) S.cnt_m[b] = 0;
     wave_refill_pool(S, wa, total_items, NS);
   }
@@ -905,6 +927,10 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
           S.mesh_res[4 * s + 3] = __int_as_float(c.best_prim);
           __threadfence_block();
           *(volatile short*)&S.pend[s] = 0;                                   // the slot's owner sees the ray resolved
+          if (p == 1) {                                                       // a path ray: the slot is ready for X
+            const int at = atomicAdd(&S.xq_tail, 1);
+            *(volatile short*)&S.xq[(unsigned)at % (unsigned)NS] = (short)s;
+          }
           active = false;
         }
       }
@@ -914,16 +940,24 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
   }
 
   // =================================================================== shading warps: X / rank / Y over the slots whose rays are resolved
-  int par = 0;
+  int par = 0, x_lo = 0;
   for (;;) {
     // ---- X: closest hit, path end or light sample + shadow ray
     if (tid == 0 && !S.exhausted && S.pool_next >= S.pool_end) wave_refill_pool(S, wa, total_items, NS);
-    for (int s = tid; s < NS; s += NSH) {
-      const int st = S.state[s];
-      const bool on = ((st & (ST_HASRAY | ST_SURF)) == ST_HASRAY) && vload(&S.pend[s]) == 0;   // a slot whose path ray is still in the tree sits this X out
+    // the slots whose path ray is resolved come in a ring (filed by the traversal lanes as their walks end, and by Y for rays
+    // that need no walk): X runs over a dense list, full warps
+    const int x_hi = S.xq_hi;
+    for (int i0 = x_lo; i0 < x_hi; i0 += NSH) {
+      const int i = i0 + tid;
+      const bool on = i < x_hi;
+      int s = 0;
       ExtendOut x; x.ended = false; x.surf = false; x.push_cs = false; x.bucket = -1;
       if (on) {
-        __threadfence_block();                                                // the traversal lane wrote mesh_res before it cleared pend
+        short* e = &S.xq[(unsigned)i % (unsigned)NS];
+        while ((s = vload(e)) < 0) { }                                        // reserved a moment ago, written in a moment
+        *(volatile short*)e = -1;
+        __threadfence_block();                                                // the traversal lane wrote mesh_res before it filed the slot
+        const int st = S.state[s];
         const float tri_t = S.mesh_res[4 * s + 0], tri_u = S.mesh_res[4 * s + 1], tri_v = S.mesh_res[4 * s + 2];
         const int tri_id = __float_as_int(S.mesh_res[4 * s + 3]);
         x = wave_extend<RT, MESHK>(S, s, st, a, tri_id, tri_t, tri_u, tri_v, cnt, nmesh, nbounce);
@@ -934,6 +968,7 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
       queue_push(x.ended, S.q_r[par], &S.cnt_r[par], s);
       ring_push(x.surf && x.push_cs, S.tq, &S.tq_tail, NS, s);                // the shadow ray goes to the traversal warps
     }
+    x_lo = x_hi;
     shade_group_barrier();
     if (tid == 0) { __threadfence_block(); *(volatile int*)&S.tq_pub = S.tq_tail; }
     // ---- rank: surface slots whose shadow query is resolved, bucketed by material
@@ -973,7 +1008,8 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
           starved = g.starved; retire = g.retire; newray = g.newray; push_cp = g.push_cp;
         }
         if (newray) { if (push_cp) S.pend[s] = 1; else S.mesh_res[4 * s + 3] = __int_as_float(-1); }
-        ring_push(newray && push_cp, S.tq, &S.tq_tail, NS, s);                // the new path ray goes to the traversal warps
+        ring_push(newray && push_cp, S.tq, &S.tq_tail, NS, s);                // the new path ray goes to the traversal warps ...
+        ring_push(newray && !push_cp, S.xq, &S.xq_tail, NS, s);               // ... or, with no mesh candidate, straight to the next X
         // paths that reached Max_Trace_Depth and starved slots wait for the next round's regenerate
         queue_push(ended || (starved && !retire), S.q_r[par ^ 1], &S.cnt_r[par ^ 1], s);
         const unsigned rm = __ballot_sync(0xffffffffu, retire);
@@ -982,10 +1018,10 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
     }
     shade_group_barrier();
     if (S.retired >= NS) { if (tid == 0) *(volatile int*)&S.done = 1; break; }   // uniform: `retired` only changes in Y
-    // (no barrier needed here: the next X touches the other halves of q_r / xwork, and cnt_m is next used after X's barrier)
-    if (tid == 0) { __threadfence_block(); *(volatile int*)&S.tq_pub = S.tq_tail; S.cnt_r[par] = 0; S.xwork[par] = 0; }
+    if (tid == 0) { __threadfence_block(); *(volatile int*)&S.tq_pub = S.tq_tail; S.cnt_r[par] = 0; S.xwork[par] = 0; S.xq_hi = vload(&S.xq_tail); }
     if (tid < 5) S.cnt_m[tid] = 0;
     par ^= 1;
+    shade_group_barrier();                                                    // X reads the snapshot of its ring
   }
   wave_flush_counters(a, nrays, nmesh, nbounce, 0u, 0u, 0u);
 }
