@@ -72,6 +72,19 @@ package GCore_B200 is
   function gcore_closest_hit_batch (n : int; rays : Address; hits : Address) return int;
   pragma Import (C, gcore_closest_hit_batch, "gcore_closest_hit_batch");
 
+  ------------------------------------------------------------------ extension of the seam (scene_hydra_embree.adb)
+  --  material id / vertex normals of a mesh added with gcore_add_mesh_3f (call before gcore_commit_scene), and the switch that
+  --  makes the integrators trace the committed scene instead of the analytic build's mesh
+  function gcore_set_mesh_material (meshId : int; matId : int) return int;
+  pragma Import (C, gcore_set_mesh_material, "gcore_set_mesh_material");
+  function gcore_set_mesh_normals_3f (meshId : int; a_normals3f : Address; a_vertexNum : int) return int;
+  pragma Import (C, gcore_set_mesh_normals_3f, "gcore_set_mesh_normals_3f");
+  function gcore_use_committed_scene (enable : int) return int;
+  pragma Import (C, gcore_use_committed_scene, "gcore_use_committed_scene");
+  --  0: the reference's one-sided triangle test (default), 1: Embree's two-sided rtcIntersect1 semantics
+  function gcore_set_seam_two_sided (enable : int) return int;
+  pragma Import (C, gcore_set_seam_two_sided, "gcore_set_seam_two_sided");
+
   ------------------------------------------------------------------ rendering
   type Gcore_Render_Config is record                            --  ray_tracer.ads:20-32,40
     render_type   : Integer_32;                                 --  Render_Type'Pos
@@ -91,6 +104,10 @@ package GCore_B200 is
 
   function gcore_set_device (device : int) return int;
   pragma Import (C, gcore_set_device, "gcore_set_device");
+  --  multi-GPU inside this one process: devices [device, device + n) split the tiles of every pass, gcore_read_frame gathers the
+  --  accumulators on the first device over NCCL (include/gcore.h); call once before Resize_Viewport
+  function gcore_set_gpu_count (n : int) return int;
+  pragma Import (C, gcore_set_gpu_count, "gcore_set_gpu_count");
   function gcore_init_render (cfg : access constant Gcore_Render_Config) return int;
   pragma Import (C, gcore_init_render, "gcore_init_render");
   function gcore_resize_viewport (width, height : int) return int;
