@@ -325,6 +325,15 @@ int ensure_wave_buffers(int d, size_t items) {
       cudaFree(a); cudaFree(b); cudaFree(c);
       return fail_cuda(e, "cudaMalloc wave stacks");
     }
+    // the tail of a launch: twice the resident path slots' worth of items go out one sub-pixel path at a time (render_wave.cuh wave_regen)
+    int tail_items = 2 * (int)total_slots;
+    if (const char* e = getenv("GCORE_TAIL_ITEMS")) tail_items = atoi(e) < 0 ? 0 : atoi(e);               // experiments: 0 switches the split off
+    float4* t = nullptr;
+    if ((e = cudaMalloc(&t, sizeof(float4) * 4 * (size_t)(tail_items > 0 ? tail_items : 1))) != cudaSuccess) {
+      cudaFree(a); cudaFree(b); cudaFree(c);
+      return fail_cuda(e, "cudaMalloc wave tail");
+    }
+    dv.wave.tailbuf = t; dv.wave.tail_items = tail_items;
     dv.wave.stackA = a; dv.wave.stackB = b; dv.wave.next_item = c;
     dv.wave.sm_count = dv.sm_count;                             // only now: a failed allocation leaves the buffers unset
   }
@@ -483,8 +492,8 @@ int render_units_locked(int units, gcore_render_stats* stats) {
     chunk = cap_bytes / (sizeof(float4) * nslots);
     if (chunk < 1) chunk = 1;
     if (chunk > (size_t)units) chunk = (size_t)units;
-    while (chunk > 1 && ((chunk * nslots) >> 31)) chunk >>= 1;
-    if ((chunk * nslots) >> 31) return fail(GCORE_E_LIMIT, "viewport too large for the work-item counter");
+    while (chunk > 1 && ((chunk * nslots) >> 30)) chunk >>= 1;                 // (the counter also runs over the tail items' sub-paths)
+    if ((chunk * nslots) >> 30) return fail(GCORE_E_LIMIT, "viewport too large for the work-item counter");
   }
   // every device gets its whole share enqueued before the next one: launches are asynchronous, the devices run concurrently
   for (int d = 0; d < G; d++) {
@@ -619,7 +628,7 @@ void release_device(int d) {
   free_accum(d);
   gcore_dev::lbvh_free(&dv.mesh_bvh); gcore_dev::lbvh_free(&dv.legacy_bvh);
   dv.mesh_version = dv.legacy_version = -1;
-  cudaFree(dv.wave.colbuf); cudaFree(dv.wave.stackA); cudaFree(dv.wave.stackB); cudaFree(dv.wave.next_item);
+  cudaFree(dv.wave.colbuf); cudaFree(dv.wave.stackA); cudaFree(dv.wave.stackB); cudaFree(dv.wave.next_item); cudaFree(dv.wave.tailbuf);
   dv.wave = WaveBuffers();
   dv.scene_dirty = true;
 }

@@ -72,6 +72,8 @@ struct WaveBuffers {
   float4* stackA = nullptr;              // [max_depth][wave_total_slots] per-bounce (explicit.xyz, weight.x)
   float2* stackB = nullptr;              //                                                (weight.y, weight.z)
   unsigned int* next_item = nullptr;     // global work counter
+  float4* tailbuf = nullptr;             // [tail_items][4] radiance of the single-path work items at the end of a launch
+  int     tail_items = 0;                // (pass, pixel) items per launch that are handed out path by path
   int     sm_count = 0;
 };
 int wave_total_slots(int sm_count);      // path slots resident on the device (grid * slots per block)

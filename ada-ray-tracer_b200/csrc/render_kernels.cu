@@ -331,6 +331,13 @@ cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs&
   if (a.nslots <= 0 || units <= 0) return cudaSuccess;
   art::WaveArgs wa;
   wa.r = a; wa.colbuf = wb.colbuf; wa.stackA = wb.stackA; wa.stackB = wb.stackB; wa.next_item = wb.next_item; wa.units = units; wa.count_mesh = count_mesh;
+  wa.tailbuf = wb.tailbuf;
+  wa.total_items = (unsigned int)units * (unsigned int)a.nslots;
+  // the last items of the launch are handed out path by path (4 per item with anti-aliasing on): enough of them to keep every slot busy
+  // while the whole items drain
+  unsigned int tail_items = a.anti_aliasing ? (unsigned int)wb.tail_items : 0u;
+  if (tail_items > wa.total_items) tail_items = wa.total_items;
+  wa.tail_first = wa.total_items - tail_items;
   cudaError_t e = cudaMemsetAsync(wb.next_item, 0, sizeof(unsigned int), s);
   if (e != cudaSuccess) return e;
   const bool bvh = (mesh_kind == 2);
@@ -341,7 +348,7 @@ cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs&
     default: e = cudaErrorInvalidValue;
   }
   if (e != cudaSuccess) return e;
-  art::fold_kernel<<<blocks_for(a.nslots, 256), 256, 0, s>>>(a, wb.colbuf, units);
+  art::fold_kernel<<<blocks_for(a.nslots, 256), 256, 0, s>>>(a, wb.colbuf, wb.tailbuf, wa.tail_first, units);
   return cudaGetLastError();
 }
 

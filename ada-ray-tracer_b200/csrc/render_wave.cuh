@@ -107,7 +107,7 @@ struct WavePathSmem {
   float ix[NS], iy[NS], iz[NS];       // 1 / direction of the slot's pending ray: the path ray (Y -> X), then the shadow ray (X -> Y)
   // colour of the work item so far / radiance at the end of the path
   float cr[NS], cg[NS], cb[NS], lx[NS], ly[NS], lz[NS];
-  int   item[NS];                    // unit * nslots + q, or -1: no item
+  int   item[NS];                    // unit * nslots + q (the colbuf index); -1: no item; <= -2: a single-path tail item, tailbuf index -2 - item
   unsigned int pixel[NS], sample[NS];   // Philox key word 1 / counter word 0 of the current path
   int   state[NS];                   // depth | sub << 5 | flags
   short hmat[NS];
@@ -186,6 +186,9 @@ struct WaveArgs {
   float4* stackA;                         // [WAVE_MAX_DEPTH][total_slots]  (E.xyz, W.x)
   float2* stackB;                         // [WAVE_MAX_DEPTH][total_slots]  (W.y, W.z)
   unsigned int* next_item;                // global work counter
+  float4* tailbuf;                        // [total_items - tail_first][4] radiance of the single-path items of the launch's tail
+  unsigned int total_items;               // units * nslots: the (pass, pixel) work items of this launch
+  unsigned int tail_first;                // hand-out positions >= tail_first go out as 4 single sub-pixel paths each (== total_items: none)
   int     units;
   int     count_mesh;                     // statistics level 2: count reference-bbox entries (see mesh_candidate)
 };
@@ -363,6 +366,37 @@ ART_D void triangle_tuv(f3 o, f3 d, f3 A, f3 edge1, f3 edge2, float& t, float& u
 // the three per-slot pieces of the integrators, shared by both kernels (S: any shared-memory struct built on WavePathSmem)
 // ---------------------------------------------------------------------------------------------------------------------
 
+// The order in which the (pass, pixel) work items of a launch are handed out.  Position p of the work counter -> (unit, slot q):
+// tile-major -- all passes of one 32x32 tile (1024 consecutive slots) before the next tile -- so that the paths in flight on a GPU
+// at any time belong to a few tiles: coherent hit types and materials in the warps of X and Y.  (Pass-major order keeps a band of
+// the image in flight on one GPU but the WHOLE share of a GPU when 8 of them split the tiles; measured 14.4 vs 15.4 Grays/s per GPU.)
+// The colour of an item still goes to colbuf[unit * nslots + q], so fold_kernel's pass order is untouched.
+struct WaveItem { int unit, q; };
+ART_D WaveItem wave_item_at(unsigned int p, int units, int nslots) {
+  WaveItem it;
+#ifdef WAVE_ITEM_ORDER_PASS_MAJOR
+  it.unit = (int)(p / (unsigned int)nslots); it.q = (int)(p - (unsigned int)it.unit * (unsigned int)nslots);
+#elif defined(WAVE_ITEM_ORDER_BLOCK_MAJOR)
+  const unsigned int per_blk = (unsigned int)units << 5;                            // all passes of one 8x4 pixel block before the next block
+  const unsigned int b = p / per_blk, r = p - b * per_blk;
+  it.unit = (int)(r >> 5); it.q = (int)((b << 5) + (r & 31u));
+#else
+  const unsigned int per_tile = (unsigned int)units << 10;
+  const unsigned int tl = p / per_tile, r = p - tl * per_tile;
+  it.unit = (int)(r >> 10); it.q = (int)((tl << 10) + (r & 1023u));
+#endif
+  return it;
+}
+ART_D unsigned int wave_item_position(int unit, int q, int units, int nslots) {     // the inverse: where (unit, q) sits in the hand-out order
+#ifdef WAVE_ITEM_ORDER_PASS_MAJOR
+  return (unsigned int)unit * (unsigned int)nslots + (unsigned int)q;
+#elif defined(WAVE_ITEM_ORDER_BLOCK_MAJOR)
+  return ((unsigned int)(q >> 5) * (unsigned int)units + (unsigned int)unit) * 32u + (unsigned int)(q & 31);
+#else
+  return ((unsigned int)(q >> 10) * (unsigned int)units + (unsigned int)unit) * 1024u + (unsigned int)(q & 1023);
+#endif
+}
+
 struct ExtendOut { bool ended, surf, push_cs; int bucket; };
 
 // stage X for slot s whose path ray is resolved: (tri_*) = its mesh candidate.  Scene.Find_Closest_Hit, then path end
@@ -531,18 +565,25 @@ ART_D RegenOut wave_regen(SM& S, int s, bool on, const WaveArgs& wa, size_t stac
         }
       }
       const int sub = (st >> ST_SUB_SHIFT) & 3;
-      f3 color = mk3(S.cr[s], S.cg[s], S.cb[s]);
-      bool done;
-      if (aa) {
-        if (sub == 0) color = mk3(a.bg[0], a.bg[1], a.bg[2]);         // :42
-        color = color + L;                                            // :47
-        done = (sub == 3);
-      } else { color = L; done = true; }                              // :60
-      if (done) { wa.colbuf[item] = make_float4(color.x, color.y, color.z, 0.0f); item = -1; }
-      else { S.cr[s] = color.x; S.cg[s] = color.y; S.cb[s] = color.z; }
-      st = (st & ~(ST_FOLD | (3 << ST_SUB_SHIFT))) | (((sub + 1) & 3) << ST_SUB_SHIFT);
+      if (item < -1) {
+        // an item of the launch's tail: ONE sub-pixel path; its radiance goes out as it is and fold_kernel adds the four in order
+        wa.tailbuf[-2 - item] = make_float4(L.x, L.y, L.z, 0.0f);
+        item = -1;
+        st &= ~ST_FOLD;
+      } else {
+        f3 color = mk3(S.cr[s], S.cg[s], S.cb[s]);
+        bool done;
+        if (aa) {
+          if (sub == 0) color = mk3(a.bg[0], a.bg[1], a.bg[2]);       // :42
+          color = color + L;                                          // :47
+          done = (sub == 3);
+        } else { color = L; done = true; }                            // :60
+        if (done) { wa.colbuf[item] = make_float4(color.x, color.y, color.z, 0.0f); item = -1; }
+        else { S.cr[s] = color.x; S.cg[s] = color.y; S.cb[s] = color.z; }
+        st = (st & ~(ST_FOLD | (3 << ST_SUB_SHIFT))) | (((sub + 1) & 3) << ST_SUB_SHIFT);
+      }
     }
-    need = item < 0;
+    need = item == -1;
     if (!need) S.sample[s] = S.sample[s] + 1u;                        // next sub-pixel sample of the same pass
   }
   {                                                                   // next work item (pass, pixel): one atomic per warp
@@ -555,17 +596,24 @@ ART_D RegenOut wave_regen(SM& S, int s, bool on, const WaveArgs& wa, size_t stac
       if (need) {
         const int got = base + __popc(nm & ((1u << lane) - 1u));
         out.starved = true;
+        st &= ~(3 << ST_SUB_SHIFT);
         if (got < S.pool_end) {
-          const int q = got % a.nslots, unit = got / a.nslots;
+          // the counter runs over the (pass, pixel) items first and then, for the last items of the launch, over their four
+          // sub-pixel paths one by one: the drain of a launch is then one path long, not four (a slot walks the sub-pixel
+          // paths of an item one after the other)
+          unsigned int pos = (unsigned int)got; int sub = 0, tail_index = -1;
+          if (pos >= wa.tail_first) { const unsigned int t = pos - wa.tail_first; pos = wa.tail_first + (t >> 2); sub = (int)(t & 3u); tail_index = (int)t; }
+          const WaveItem it = wave_item_at(pos, wa.units, a.nslots);
+          const int q = it.q, unit = it.unit;
           const WavePixel px = wave_slot_to_pixel(a, q);
           if (px.active) {                                            // (an item of a padding pixel is dropped; the slot asks again next round)
             out.starved = false;
-            item = got;
+            item = (tail_index >= 0) ? (-2 - tail_index) : (unit * a.nslots + q);
             S.pixel[s] = (unsigned int)(px.y * a.width + px.x);
-            S.sample[s] = (unsigned int)(a.first_sample + (aa ? unit * 4 : unit));
+            S.sample[s] = (unsigned int)(a.first_sample + (aa ? unit * 4 + sub : unit));
+            st |= sub << ST_SUB_SHIFT;
           } else padded = true;
         }
-        st &= ~(3 << ST_SUB_SHIFT);
       }
     }
   }
@@ -596,7 +644,8 @@ ART_D RegenOut wave_regen(SM& S, int s, bool on, const WaveArgs& wa, size_t stac
 // work items are fetched from the global counter in batches that shrink towards the end of the launch (guided
 // self-scheduling): 2 NS while there is plenty, down to 64, so that the blocks run dry together.  Thread 0 only.
 template <class SM>
-ART_D void wave_refill_pool(SM& S, const WaveArgs& wa, unsigned int total_items, unsigned int ns) {
+ART_D void wave_refill_pool(SM& S, const WaveArgs& wa, unsigned int ns) {
+  const unsigned int total_items = wa.tail_first + 4u * (wa.total_items - wa.tail_first);     // work-counter range (see wave_regen)
   const unsigned int seen = *(volatile unsigned int*)wa.next_item;
   const unsigned int rem = (seen < total_items) ? (total_items - seen) : 0u;
   unsigned int want = rem / (2u * gridDim.x);
@@ -706,7 +755,6 @@ __global__ void __launch_bounds__(NT, WAVE_BLOCKS_PER_SM(NT)) render_wave_kernel
   const int tid = threadIdx.x;
   const int gslot0 = blockIdx.x * NT;
   const int total_slots = gridDim.x * NT;
-  const unsigned int total_items = (unsigned int)wa.units * (unsigned int)a.nslots;
   unsigned int nrays = 0, nmesh = 0, nbounce = 0;
   const bool cnt = wa.count_mesh != 0;
 
@@ -714,7 +762,7 @@ __global__ void __launch_bounds__(NT, WAVE_BLOCKS_PER_SM(NT)) render_wave_kernel
   if (tid == 0) {
     S.cnt_r[0] = NS; S.cnt_r[1] = 0; S.cnt_cs = 0; S.cnt_cp = 0; S.retired = 0; S.exhausted = 0;
     for (int b = 0; b < 5; b++) S.cnt_m[b] = 0;
-    wave_refill_pool(S, wa, total_items, NS);
+    wave_refill_pool(S, wa, NS);
   }
   __syncthreads();
 
@@ -723,7 +771,7 @@ __global__ void __launch_bounds__(NT, WAVE_BLOCKS_PER_SM(NT)) render_wave_kernel
     // ================================================================= X: closest hit, path end or light sample
     if (tid == 0) {
       S.cnt_cp = 0;                                                           // consumed by M2 of the previous round
-      if (!S.exhausted && S.pool_next >= S.pool_end) wave_refill_pool(S, wa, total_items, NS);   // (fetched from in Y only)
+      if (!S.exhausted && S.pool_next >= S.pool_end) wave_refill_pool(S, wa, NS);   // (fetched from in Y only)
     }
     for (int s = tid; s < NS; s += NT) {
       const int st = S.state[s];
@@ -851,7 +899,6 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
   const int tid = threadIdx.x;
   const int gslot0 = blockIdx.x * NS;
   const int total_slots = gridDim.x * NS;
-  const unsigned int total_items = (unsigned int)wa.units * (unsigned int)a.nslots;
   unsigned int nrays = 0, nmesh = 0, nbounce = 0, ntrav = 0;
   BvhStats tstat; tstat.nodes = 0; tstat.tris = 0;
   const bool cnt = wa.count_mesh != 0;
@@ -861,7 +908,7 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
     S.cnt_r[0] = NS; S.cnt_r[1] = 0; S.retired = 0; S.exhausted = 0;
     S.tq_head = 0; S.tq_tail = 0; S.tq_pub = 0; S.xq_tail = 0; S.xq_hi = 0; S.done = 0; S.xwork[0] = 0; S.xwork[1] = 0;
     for (int b = 0; b < 5; b++) S.cnt_m[b] = 0;
-    wave_refill_pool(S, wa, total_items, NS);
+    wave_refill_pool(S, wa, NS);
   }
   __syncthreads();
 
@@ -943,7 +990,7 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
   int par = 0, x_lo = 0;
   for (;;) {
     // ---- X: closest hit, path end or light sample + shadow ray
-    if (tid == 0 && !S.exhausted && S.pool_next >= S.pool_end) wave_refill_pool(S, wa, total_items, NS);
+    if (tid == 0 && !S.exhausted && S.pool_next >= S.pool_end) wave_refill_pool(S, wa, NS);
     // the slots whose path ray is resolved come in a ring (filed by the traversal lanes as their walks end, and by Y for rays
     // that need no walk): X runs over a dense list, full warps
     const int x_hi = S.xq_hi;
@@ -1027,7 +1074,8 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
 }
 
 // K6a: acc[q] := colour(pass k, q) + acc[q] for k = 0 .. units-1 -- the additions of integrators.adb:51/:63 in pass order
-__global__ void __launch_bounds__(256) fold_kernel(const __grid_constant__ gcore_dev::RenderArgs a, const float4* __restrict__ colbuf, int units) {
+__global__ void __launch_bounds__(256) fold_kernel(const __grid_constant__ gcore_dev::RenderArgs a, const float4* __restrict__ colbuf,
+                                                   const float4* __restrict__ tailbuf, unsigned int tail_first, int units) {
   const int q = blockIdx.x * 256 + threadIdx.x;
   if (q >= a.nslots) return;
   const WavePixel px = wave_slot_to_pixel(a, q);
@@ -1036,8 +1084,20 @@ __global__ void __launch_bounds__(256) fold_kernel(const __grid_constant__ gcore
   f3 acc = mk3(acc4.x, acc4.y, acc4.z);
 #pragma unroll 4
   for (int k = 0; k < units; k++) {
-    const float4 c = __ldcs(&colbuf[(size_t)k * a.nslots + q]);
-    acc = mk3(c.x, c.y, c.z) + acc;
+    const unsigned int pos = wave_item_position(k, q, units, a.nslots);
+    f3 color;
+    if (pos < tail_first) {
+      const float4 c = __ldcs(&colbuf[(size_t)k * a.nslots + q]);
+      color = mk3(c.x, c.y, c.z);
+    } else {
+      // a tail item: its four sub-pixel paths were traced as separate work items; color := Background_Color, then the four
+      // additions of integrators.adb:42-48 in sub-pixel order
+      const float4* L = tailbuf + 4 * (size_t)(pos - tail_first);
+      color = mk3(a.bg[0], a.bg[1], a.bg[2]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) { const float4 c = __ldcs(&L[j]); color = color + mk3(c.x, c.y, c.z); }
+    }
+    acc = color + acc;
   }
   a.accum[q] = make_float4(acc.x, acc.y, acc.z, acc4.w);
 }

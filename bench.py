@@ -34,6 +34,7 @@ import __graft_entry__ as ge  # noqa: E402
 WORKLOADS = {
     # name: (width, height, render_type, aa, max_depth, units per step, description)
     "C4_1024": (1024, 1024, "PT_MIS", 1, 8, 64, "pyramid2 Cornell scene, PT_MIS depth 8, AA 4 fixed sub-pixels, 1024x1024, 256 spp per step"),
+    "C4_1024_eighth": (1024, 128, "PT_MIS", 1, 8, 64, "scaling analysis: one eighth of the C4_1024 image (rows 0..127) on one GPU, 256 spp per step"),
     "C1": (1024, 768, "PT_MIS", 1, 8, 28, "reference default: 1024x768 PT_MIS depth 8, 28 units (112 spp) per Render_Pass"),
     "C2": (1024, 1024, "RT_DEBUG", 0, 1, 1, "primary-ray cast only (Debug_Ray_Tracing), 1024x1024, 1 spp (pixel centres)"),
     "C3": (1024, 1024, "PT_SHADOW", 1, 1, 4, "direct lighting with shadow rays, 1024x1024, 16 spp"),
@@ -79,14 +80,16 @@ class ClockSampler:
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index=0):
+    def __init__(self, gpu_index=0, ngpus=1):
         self.p = None
         self.gpu_index = gpu_index
+        self.ngpus = ngpus
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
-                                       "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            ids = ",".join(str(self.gpu_index + k) for k in range(self.ngpus))
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50",
+                                       "-i", ids], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
@@ -100,6 +103,7 @@ class ClockSampler:
         except Exception:
             self.p.kill(); out = ""
         sm, mx, pw, reasons = [], [], [], set()
+        per_gpu = {}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
@@ -107,6 +111,7 @@ class ClockSampler:
                 continue
             try:
                 sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                per_gpu.setdefault(f[0], []).append(float(f[1]))
             except ValueError:
                 continue
             for n, v in zip(names, f[5:9]):
@@ -114,8 +119,11 @@ class ClockSampler:
                     reasons.add(n)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        res = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+               "samples": len(sm), "reasons": sorted(reasons)}
+        if len(per_gpu) > 1:
+            res["sm_mhz_per_gpu"] = [float(np.median(v)) for _, v in sorted(per_gpu.items(), key=lambda kv: int(kv[0]))]
+        return res
 
 
 _ORACLE_SCENES = {}
@@ -206,7 +214,7 @@ def measure_device(pkg, tr, rt, args, workload, world, rank, local_rank, barrier
     barrier()
     c0 = pkg.get_counters()
     bv0 = pkg.get_bvh_counters()
-    sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
+    sampler = ClockSampler(local_rank, world) if (rank == 0 and sample_clocks) else None
     if sampler:
         sampler.start()
     ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(steps)]
@@ -228,12 +236,13 @@ def measure_device(pkg, tr, rt, args, workload, world, rank, local_rank, barrier
     t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([rays_local, mesh_local, bounce_local, launches, bv1[0] - bv0[0], bv1[1] - bv0[1], bv1[2] - bv0[2]], dtype=torch.float64, device="cuda")
     per_rank = torch.zeros(world, dtype=torch.float64, device="cuda"); per_rank[rank] = kern_ms / steps
+    per_rank_rays = torch.zeros(world, dtype=torch.float64, device="cuda"); per_rank_rays[rank] = rays_local / steps
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM); dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM); dist.all_reduce(per_rank, op=dist.ReduceOp.SUM); dist.all_reduce(per_rank_rays, op=dist.ReduceOp.SUM)
     rays, _mesh_stage_rays, bounces, launches_all, bvh_nodes, bvh_tris, bvh_trav = (float(x) for x in cnt)
     return {"step_ms": float(t[0]), "kern_ms": float(t[1]), "rays": rays, "bounces": bounces, "mesh_q": mesh_share * rays, "launches": launches_all,
             "bvh_nodes": bvh_nodes, "bvh_tris": bvh_tris, "bvh_trav": bvh_trav, "wall": wall, "clocks": clocks,
-            "kernel_ms_per_rank": [float(x) for x in per_rank]}
+            "kernel_ms_per_rank": [float(x) for x in per_rank], "rays_per_rank": [float(x) for x in per_rank_rays]}
 
 
 def lbvh_roofline(m, steps, world, hbm_bytes, peaks, rtype, achieved_tf, peak_tf, traffic, traffic_note):
@@ -437,7 +446,7 @@ def main():
                            "e2e_path": "ONE host process: gcore_render() with host buffers; N > 1: gcore_set_gpu_count(N), the library drives every GPU and gathers over NCCL"},
                 "msamples_per_s": (npx * units * (4 if aa else 1)) / (step_ms / args.steps * 1e-3) / 1e6,
                 "rays_per_step": rays / args.steps, "bounces_per_step": bounces / args.steps, "mesh_queries_per_step": mesh_q / args.steps,
-                "colbuf_bytes_per_launch": colbuf_bytes, "kernel_ms_per_rank": m["kernel_ms_per_rank"], "kernel_source_sha16": kernel_source_hash(),
+                "colbuf_bytes_per_launch": colbuf_bytes, "kernel_ms_per_rank": m["kernel_ms_per_rank"], "rays_per_step_per_rank": m["rays_per_rank"], "kernel_source_sha16": kernel_source_hash(),
                 "wall_s": m["wall"], "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
                         "kernel_ms_per_device": e2e_dev_ms},

@@ -331,6 +331,29 @@ def test_long_renders_go_in_chunks_of_passes(oscene, ob, tmp_path):
     assert np.array_equal(_bits(hdr[..., :3]), _bits(acc))
 
 
+@pytest.mark.parametrize("tail_items", ["0", "777", "100000000"])
+def test_launch_tail_goes_out_path_by_path(oscene, ob, tmp_path, tail_items):
+    """the last (pass, pixel) items of a launch are handed out as four single sub-pixel paths each, so that the launch drains in one
+    path's time (render_wave.cuh wave_regen; fold_kernel adds the four radiances in the reference's order).  Default: 2 x the resident
+    path slots; here none / a handful / all of the items take that route -- the same bits as the oracle every time.  Fresh process:
+    the setting is read from the environment when the work buffers are made."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import __graft_entry__ as ge; pkg = ge.load_package(); "
+        "pkg.set_device(0); sc = pkg.Scene(); sc.Init(); rt = pkg.Ray_Tracer(); rt.Threads_Num = 5; rt.seed = 4099; "
+        "rt.Background_Color = (0.03125, 0.0625, 0.125); rt.Init_Render(pkg.PT_MIS); rt.Resize_Viewport(96, 80); "
+        "hdr = rt.Render_Pass(read_hdr=True); np.save(%r, hdr); print(rt.last_stats.rays)" % (root, str(tmp_path / "hdr.npy")))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, GCORE_TAIL_ITEMS=tail_items), timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    hdr = np.load(str(tmp_path / "hdr.npy"))
+    acc, orays = oscene.render(ob.make_params(96, 80, ob.PT_MIS, passes=5, seed=4099, background=(0.03125, 0.0625, 0.125)))
+    assert int(r.stdout.split()[-1]) == orays
+    assert np.array_equal(_bits(hdr[..., :3]), _bits(acc))
+
+
 @pytest.mark.parametrize("name,rtype,depth,units,w,h", [
     ("C1", "PT_MIS", 8, 2, 1024, 768),        # the reference's default viewport and integrator, 8 of its 112 spp per pass
     ("C3", "PT_SHADOW", 1, 4, 1024, 1024),    # BASELINE config C3 in full: direct lighting, 16 spp
