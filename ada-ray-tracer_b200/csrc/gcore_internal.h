@@ -83,7 +83,9 @@ int wave_max_depth();
 cudaError_t launch_render_wave(int render_type, int mesh_kind, const RenderArgs& a, const WaveBuffers& wb, int units, int count_mesh, cudaStream_t s);
 
 // ---- lbvh_build.cu ----
-#define LBVH_NODE_BYTES 32                // packed node: see lbvh_traverse.cuh
+#ifndef LBVH_NODE_BYTES
+#define LBVH_NODE_BYTES 32                // packed node: see lbvh_traverse.cuh (64: the full-precision experiment layout)
+#endif
 struct LbvhBuffers {                     // device allocations owned by the builder
   float4* nodes = nullptr; float4* tris = nullptr; float* tri_normals = nullptr; int* tri_mat = nullptr;
   int ntris = 0, nnodes = 0, root = -1;

@@ -201,6 +201,13 @@ __global__ void pack_nodes_kernel(int n, const int* __restrict__ vals, const Aab
       q[6 * j + k] = (unsigned int)lo; q[6 * j + 3 + k] = (unsigned int)hi;
     }
   const unsigned int flags = (lc < 0 ? 1u : 0u) | (rc < 0 ? 2u : 0u);
+#if LBVH_NODE_BYTES == 64
+  nodes[4 * (size_t)i + 0] = make_float4(c[0].mn[0], c[0].mn[1], c[0].mn[2], c[0].mx[0]);
+  nodes[4 * (size_t)i + 1] = make_float4(c[0].mx[1], c[0].mx[2], c[1].mn[0], c[1].mn[1]);
+  nodes[4 * (size_t)i + 2] = make_float4(c[1].mn[2], c[1].mx[0], c[1].mx[1], c[1].mx[2]);
+  nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(gamma), __uint_as_float(flags), 0.0f, 0.0f);
+  return;
+#endif
   const unsigned int w0 = eb[0] | (eb[1] << 8) | (eb[2] << 16) | (flags << 24);
   const unsigned int w1 = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
   const unsigned int w2 = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);

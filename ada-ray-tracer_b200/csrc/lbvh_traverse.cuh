@@ -39,6 +39,21 @@ struct BvhStats { unsigned int nodes, tris; };     // nodes visited (32 B each),
 struct BvhNode2 { float b0[6], b1[6]; int c0, c1; };          // decoded: child boxes (min.xyz, max.xyz), child links (>= 0 node, < 0: ~slot)
 
 ART_D BvhNode2 bvh_fetch_node(const BvhView& bv, int node) {
+#if LBVH_NODE_BYTES == 64
+  // experiment layout: both child boxes in full precision (n0 = c0.min.xyz c0.max.x, n1 = c0.max.yz c1.min.xy, n2 = c1.min.z c1.max.xyz,
+  // n3 = gamma | flags) -- no decode arithmetic, twice the bytes
+  const float4 n0 = __ldg(&bv.nodes[4 * node + 0]);
+  const float4 n1 = __ldg(&bv.nodes[4 * node + 1]);
+  const float4 n2 = __ldg(&bv.nodes[4 * node + 2]);
+  const float4 n3 = __ldg(&bv.nodes[4 * node + 3]);
+  BvhNode2 n;
+  n.b0[0] = n0.x; n.b0[1] = n0.y; n.b0[2] = n0.z; n.b0[3] = n0.w; n.b0[4] = n1.x; n.b0[5] = n1.y;
+  n.b1[0] = n1.z; n.b1[1] = n1.w; n.b1[2] = n2.x; n.b1[3] = n2.y; n.b1[4] = n2.z; n.b1[5] = n2.w;
+  const int gamma = __float_as_int(n3.x); const unsigned int w0 = __float_as_uint(n3.y);
+  n.c0 = (w0 & 1u) ? ~gamma : gamma;
+  n.c1 = (w0 & 2u) ? ~(gamma + 1) : (gamma + 1);
+  return n;
+#else
   const float4 q0 = __ldg(&bv.nodes[2 * node + 0]);
   const float4 q1 = __ldg(&bv.nodes[2 * node + 1]);
   const unsigned int w0 = __float_as_uint(q0.w), a = __float_as_uint(q1.x), b = __float_as_uint(q1.y), c = __float_as_uint(q1.z);
@@ -52,6 +67,7 @@ ART_D BvhNode2 bvh_fetch_node(const BvhView& bv, int node) {
   n.c0 = (w0 & (1u << 24)) ? ~gamma : gamma;
   n.c1 = (w0 & (2u << 24)) ? ~(gamma + 1) : (gamma + 1);
   return n;
+#endif
 }
 
 // Moeller-Trumbore without the max(det, 1e-25) back-face rejection: det of either sign (Embree semantics)
