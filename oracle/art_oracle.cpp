@@ -1,7 +1,11 @@
 // art_oracle.cpp -- CPU oracle: a restatement of the reference renderer's hot path.
 //
 // TEST INFRASTRUCTURE ONLY (see art_oracle.h).  PARITY UNPINNED: the reference has no
-// tests/golden vectors and cannot be built here (no GNAT, no libembree3.a).
+// tests/golden vectors and cannot be built here (no GNAT, no libembree3.a).  What holds it
+// in place instead: tests/test_oracle_kat.py checks it bit for bit against two independent
+// numpy binary32 restatements written from the Ada (tests/ada_numpy.py: rays and hits;
+// tests/ada_numpy_shading.py: lights, BxDFs, sampling maps), against the Random123 vectors
+// and against closed-form radiometry.
 //
 // Every function cites the Ada source it follows (paths relative to the reference
 // checkout).  Numerics contract: IEEE binary32 everywhere, no FMA
@@ -1483,6 +1487,43 @@ void ao_bruteforce_closest(const float* pos3, const int32_t* tris3, int ntris, i
     int prim; float t, u, v;
     bruteforce_closest_one(pos3, tris3, ntris, r, tmin, tmax, &prim, &t, &u, &v);
     out_prim[i] = prim; if (out_t) out_t[i] = t; if (out_u) out_u[i] = u; if (out_v) out_v[i] = v;
+  }
+}
+
+// ---- batched access to the shading pieces, for the independent numpy restatement of tests/ada_numpy_shading.py -----------------
+void ao_sincos_batch(int n, const float* x, float* s, float* c) { for (int i = 0; i < n; i++) sincos_ada(x[i], &s[i], &c[i]); }
+void ao_expon_batch(int n, const float* left, const float* right, float* out) { for (int i = 0; i < n; i++) out[i] = ada_expon(left[i], right[i]); }
+/* Lights.Sample (lights.adb:56-79, 197-240) for n illuminated points; u = (u1, u2) per point */
+void ao_light_sample_batch(const ao_scene* s, int n, const float* u2, const float* p3, float* out_pos3, float* out_pdf) {
+  for (int i = 0; i < n; i++) {
+    BounceRand br; br.u[0] = u2[2 * i]; br.u[1] = u2[2 * i + 1]; br.u[2] = 0.0f; br.u[3] = 0.0f;
+    ShadowSample ss = Light_Sample(s->light, br, f3(p3 + 3 * i));
+    out_pos3[3 * i] = ss.pos.x; out_pos3[3 * i + 1] = ss.pos.y; out_pos3[3 * i + 2] = ss.pos.z; out_pdf[i] = ss.pdf;
+  }
+}
+/* Lights.EvalPDF (lights.adb:81-85, 242-255) */
+void ao_light_eval_pdf_batch(const ao_scene* s, int n, const float* p3, const float* dir3, const float* t, float* out) {
+  for (int i = 0; i < n; i++) out[i] = Light_EvalPDF(s->light, f3(p3 + 3 * i), f3(dir3 + 3 * i), t[i]);
+}
+/* SampleAndEvalBxDF of material mat_id (materials.adb:197-215, 247-254, 295-331, 363-387); r = (r1, r2) per sample */
+void ao_mat_sample_batch(const ao_scene* s, int mat_id, int n, const float* r2, const float* ray_dir3, const float* normal3,
+                         float* out_color3, float* out_dir3, float* out_pdf, int32_t* out_spec) {
+  const ao_material& m = s->materials[mat_id];
+  for (int i = 0; i < n; i++) {
+    BounceRand br; br.u[0] = 0.0f; br.u[1] = 0.0f; br.u[2] = r2[2 * i]; br.u[3] = r2[2 * i + 1];
+    MatSample ms = Mat_SampleAndEvalBxDF(m, br, f3(ray_dir3 + 3 * i), f3(normal3 + 3 * i));
+    out_color3[3 * i] = ms.color.x; out_color3[3 * i + 1] = ms.color.y; out_color3[3 * i + 2] = ms.color.z;
+    out_dir3[3 * i] = ms.direction.x; out_dir3[3 * i + 1] = ms.direction.y; out_dir3[3 * i + 2] = ms.direction.z;
+    out_pdf[i] = ms.pdf; out_spec[i] = ms.pureSpecular ? 1 : 0;
+  }
+}
+/* EvalBxDF / EvalPDF of material mat_id for light direction l, view direction v, normal n (materials.adb:217-226, 389-410, ...) */
+void ao_mat_eval_batch(const ao_scene* s, int mat_id, int n, const float* l3, const float* v3, const float* n3, float* out_bxdf3, float* out_pdf) {
+  const ao_material& m = s->materials[mat_id];
+  for (int i = 0; i < n; i++) {
+    float3 b = Mat_EvalBxDF(m, f3(l3 + 3 * i), f3(v3 + 3 * i), f3(n3 + 3 * i));
+    out_bxdf3[3 * i] = b.x; out_bxdf3[3 * i + 1] = b.y; out_bxdf3[3 * i + 2] = b.z;
+    out_pdf[i] = Mat_EvalPDF(m, f3(l3 + 3 * i), f3(v3 + 3 * i), f3(n3 + 3 * i));
   }
 }
 

@@ -145,6 +145,15 @@ void  ao_sincos(float x, float* s, float* c);
 float ao_pow(float x, float y);
 void  ao_use_libm(int on);   /* 1: sinf/cosf/powf from libm instead of the deterministic kernels */
 
+/* batched access to the shading pieces (tests/ada_numpy_shading.py pins them against an independent numpy restatement) */
+void  ao_sincos_batch(int n, const float* x, float* s, float* c);
+void  ao_expon_batch(int n, const float* left, const float* right, float* out);            /* Left ** Right */
+void  ao_light_sample_batch(const ao_scene*, int n, const float* u2, const float* p3, float* out_pos3, float* out_pdf);
+void  ao_light_eval_pdf_batch(const ao_scene*, int n, const float* p3, const float* dir3, const float* t, float* out);
+void  ao_mat_sample_batch(const ao_scene*, int mat_id, int n, const float* r2, const float* ray_dir3, const float* normal3,
+                          float* out_color3, float* out_dir3, float* out_pdf, int32_t* out_spec);
+void  ao_mat_eval_batch(const ao_scene*, int mat_id, int n, const float* l3, const float* v3, const float* n3, float* out_bxdf3, float* out_pdf);
+
 /* nearest-hit triangle query on an arbitrary mesh through the oracle's own CPU BVH
  * (semantics of SURVEY C5: nearest front-facing hit, lowest index on exact ties); binned-SAH build, single-ray traversal */
 typedef struct ao_bvh ao_bvh;

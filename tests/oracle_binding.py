@@ -95,6 +95,12 @@ def lib():
         L.ao_bvh_free.argtypes = [vp]
         L.ao_bvh_closest.argtypes = [vp, C.c_int, vp, C.c_float, C.c_float, vp, vp, vp, vp, C.c_int]
         L.ao_bruteforce_closest.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_float, C.c_float, vp, vp, vp, vp]
+        L.ao_sincos_batch.argtypes = [C.c_int, vp, vp, vp]
+        L.ao_expon_batch.argtypes = [C.c_int, vp, vp, vp]
+        L.ao_light_sample_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+        L.ao_light_eval_pdf_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+        L.ao_mat_sample_batch.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
+        L.ao_mat_eval_batch.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -161,6 +167,32 @@ class OracleScene:
         self.L.ao_set_mesh_tri_materials(self.h, _p(mats), len(mats))
 
     # --- queries ---------------------------------------------------------------------------------
+    def light_sample_batch(self, u, p):
+        u = np.ascontiguousarray(u, np.float32); p = np.ascontiguousarray(p, np.float32); n = len(p)
+        pos = np.empty((n, 3), np.float32); pdf = np.empty(n, np.float32)
+        self.L.ao_light_sample_batch(self.h, n, _p(u), _p(p), _p(pos), _p(pdf))
+        return pos, pdf
+
+    def light_eval_pdf_batch(self, p, d, t):
+        p = np.ascontiguousarray(p, np.float32); d = np.ascontiguousarray(d, np.float32); t = np.ascontiguousarray(t, np.float32)
+        out = np.empty(len(p), np.float32)
+        self.L.ao_light_eval_pdf_batch(self.h, len(p), _p(p), _p(d), _p(t), _p(out))
+        return out
+
+    def mat_sample_batch(self, mat_id, r, ray_dir, normal):
+        r = np.ascontiguousarray(r, np.float32); ray_dir = np.ascontiguousarray(ray_dir, np.float32)
+        normal = np.ascontiguousarray(normal, np.float32); n = len(r)
+        color = np.empty((n, 3), np.float32); d = np.empty((n, 3), np.float32); pdf = np.empty(n, np.float32)
+        spec = np.empty(n, np.int32)
+        self.L.ao_mat_sample_batch(self.h, mat_id, n, _p(r), _p(ray_dir), _p(normal), _p(color), _p(d), _p(pdf), _p(spec))
+        return color, d, pdf, spec
+
+    def mat_eval_batch(self, mat_id, l, v, n_):
+        l = np.ascontiguousarray(l, np.float32); v = np.ascontiguousarray(v, np.float32); n_ = np.ascontiguousarray(n_, np.float32)
+        bxdf = np.empty((len(l), 3), np.float32); pdf = np.empty(len(l), np.float32)
+        self.L.ao_mat_eval_batch(self.h, mat_id, len(l), _p(l), _p(v), _p(n_), _p(bxdf), _p(pdf))
+        return bxdf, pdf
+
     def closest_hit_batch(self, rays, mesh_mode=MESH_REFERENCE_BF):
         rays = np.ascontiguousarray(rays, ray_dt)
         hits = np.zeros(len(rays), hit_dt)
@@ -215,6 +247,21 @@ def sincos(x):
     s, c = C.c_float(), C.c_float()
     lib().ao_sincos(float(x), C.byref(s), C.byref(c))
     return s.value, c.value
+
+
+def sincos_batch(x):
+    """The repository's fixed binary32 sin/cos sequence (stands in for GNAT's run-time sin/cos) on an array."""
+    x = np.ascontiguousarray(x, np.float32); s = np.empty_like(x); c = np.empty_like(x)
+    lib().ao_sincos_batch(x.size, _p(x), _p(s), _p(c))
+    return s, c
+
+
+def expon_batch(left, right):
+    """Left ** Right (stands in for GNAT's run-time "**") on arrays."""
+    left = np.ascontiguousarray(left, np.float32); right = np.ascontiguousarray(np.broadcast_to(right, left.shape), np.float32)
+    out = np.empty_like(left)
+    lib().ao_expon_batch(left.size, _p(left), _p(right), _p(out))
+    return out
 
 
 def ada_pow(x, y):
