@@ -87,6 +87,59 @@ ART_D bool intersect_triangle_two_sided(f3 o, f3 d, f3 A, f3 edge1, f3 edge2, fl
   return false;
 }
 
+// Both child boxes of `node` against one ray: h0/h1 = the ray's window (t_lo, t_hi) overlaps the child's box, e0/e1 = entry parameters.
+// The 32-byte layout is tested without materialising the boxes: plane parameter t = (origin + q * 2^e - o) * inv is evaluated as
+// fma(q, 2^e * inv, (origin - o) * inv) -- one fused operation per plane instead of multiply, add, subtract, multiply.  Culling only has
+// to be conservative (the triangle tests decide the hit, bit for bit): the rounding differs from slab_hit's by a few ulp of the plane
+// parameter, far inside the 1e-5 relative / 1e-6 absolute slack below; 0 * inf on axis-parallel rays gives NaN, which fminf/fmaxf drop.
+#ifndef LBVH_FUSED_SLABS
+#define LBVH_FUSED_SLABS 1
+#endif
+// 1/d for the slab tests.  An axis-parallel ray has 1/d = +-inf; in the fused form inf * q + (-inf) is NaN on every plane of an axis the
+// ray runs beside, the axis drops out of the test and a walk that should touch a line of boxes touches a whole slab of the tree (measured:
+// one such ray in 5e7 -- a cosine sample with r2 = 0 off an axis-aligned wall -- held a 16 ms launch for 1.5 s).  Clamped to +-1e18 the
+// plane parameters keep their sign and stay finite for any scene below 1e20 units; they only differ from the unclamped ones where
+// |plane - o| < 1e-12, below the resolution of the coordinates.
+ART_D f3 bvh_slab_inv_of(f3 inv) {
+  const float big = 1.0e18f;
+  return mk3(fminf(fmaxf(inv.x, -big), big), fminf(fmaxf(inv.y, -big), big), fminf(fmaxf(inv.z, -big), big));
+}
+ART_D void bvh_node_children(const BvhView& bv, int node, f3 o, f3 inv, float t_lo, float t_hi,
+                             int& c0, int& c1, bool& h0, bool& h1, float& e0, float& e1) {
+#if LBVH_NODE_BYTES == 64 || !LBVH_FUSED_SLABS
+  const BvhNode2 nd = bvh_fetch_node(bv, node);
+  c0 = nd.c0; c1 = nd.c1;
+  h0 = slab_hit(nd.b0[0], nd.b0[1], nd.b0[2], nd.b0[3], nd.b0[4], nd.b0[5], o, inv, t_lo, t_hi, e0);
+  h1 = slab_hit(nd.b1[0], nd.b1[1], nd.b1[2], nd.b1[3], nd.b1[4], nd.b1[5], o, inv, t_lo, t_hi, e1);
+#else
+  const float4 q0 = __ldg(&bv.nodes[2 * node + 0]);
+  const float4 q1 = __ldg(&bv.nodes[2 * node + 1]);
+  const unsigned int w0 = __float_as_uint(q0.w), a = __float_as_uint(q1.x), b = __float_as_uint(q1.y), c = __float_as_uint(q1.z);
+  const float kx = __uint_as_float((w0 & 255u) << 23) * inv.x, ky = __uint_as_float(((w0 >> 8) & 255u) << 23) * inv.y,
+              kz = __uint_as_float(((w0 >> 16) & 255u) << 23) * inv.z;
+  const float bx = (q0.x - o.x) * inv.x, by = (q0.y - o.y) * inv.y, bz = (q0.z - o.z) * inv.z;
+  {
+    const float x0 = __fmaf_rn((float)(a & 255u), kx, bx),         x1 = __fmaf_rn((float)(a >> 24), kx, bx);
+    const float y0 = __fmaf_rn((float)((a >> 8) & 255u), ky, by),  y1 = __fmaf_rn((float)(b & 255u), ky, by);
+    const float z0 = __fmaf_rn((float)((a >> 16) & 255u), kz, bz), z1 = __fmaf_rn((float)((b >> 8) & 255u), kz, bz);
+    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_lo));
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi));
+    e0 = tn; h0 = tn <= __fmaf_rn(tf, 1.00001f, 1.0e-6f);
+  }
+  {
+    const float x0 = __fmaf_rn((float)((b >> 16) & 255u), kx, bx), x1 = __fmaf_rn((float)((c >> 8) & 255u), kx, bx);
+    const float y0 = __fmaf_rn((float)(b >> 24), ky, by),          y1 = __fmaf_rn((float)((c >> 16) & 255u), ky, by);
+    const float z0 = __fmaf_rn((float)(c & 255u), kz, bz),         z1 = __fmaf_rn((float)(c >> 24), kz, bz);
+    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_lo));
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi));
+    e1 = tn; h1 = tn <= __fmaf_rn(tf, 1.00001f, 1.0e-6f);
+  }
+  const int gamma = __float_as_int(q1.w);
+  c0 = (w0 & (1u << 24)) ? ~gamma : gamma;
+  c1 = (w0 & (2u << 24)) ? ~(gamma + 1) : (gamma + 1);
+#endif
+}
+
 template <bool TWO_SIDED>
 ART_D void bvh_leaf_test(const BvhView& bv, int first, int count, f3 o, f3 d, float t_min,
                          float& best_t, int& best_prim, float& best_u, float& best_v, int& best_slot) {
@@ -112,6 +165,7 @@ template <bool STATS, bool TWO_SIDED = false, bool ANY_HIT = false>
 ART_D void bvh_closest_slot_t(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min, float t_max, int& prim_o, float& t_o, float& u_o, float& v_o, int& slot_o,
                               BvhStats& st) {
   float best_t = t_max; int best_prim = -1; float best_u = 0.0f, best_v = 0.0f; int best_slot = -1;
+  inv = bvh_slab_inv_of(inv);
   if (bv.ntris > 0) {
     if (bv.root < 0) {
       bvh_leaf_test<TWO_SIDED>(bv, 0, bv.ntris, o, d, t_min, best_t, best_prim, best_u, best_v, best_slot);
@@ -121,11 +175,8 @@ ART_D void bvh_closest_slot_t(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min
       int node = bv.root;
       for (;;) {
         if (STATS) st.nodes++;
-        const BvhNode2 nd = bvh_fetch_node(bv, node);
-        int c0 = nd.c0, c1 = nd.c1;
-        float e0, e1;
-        bool h0 = slab_hit(nd.b0[0], nd.b0[1], nd.b0[2], nd.b0[3], nd.b0[4], nd.b0[5], o, inv, t_min, best_t, e0);
-        bool h1 = slab_hit(nd.b1[0], nd.b1[1], nd.b1[2], nd.b1[3], nd.b1[4], nd.b1[5], o, inv, t_min, best_t, e1);
+        int c0, c1; float e0, e1; bool h0, h1;
+        bvh_node_children(bv, node, o, inv, t_min, best_t, c0, c1, h0, h1, e0, e1);
         if (STATS) { if (h0 && c0 < 0) st.tris += 1; if (h1 && c1 < 0) st.tris += 1; }
         if (h0 && c0 < 0) { bvh_leaf_test<TWO_SIDED>(bv, ~c0, 1, o, d, t_min, best_t, best_prim, best_u, best_v, best_slot); h0 = false; }
         if (h1 && c1 < 0) { bvh_leaf_test<TWO_SIDED>(bv, ~c1, 1, o, d, t_min, best_t, best_prim, best_u, best_v, best_slot); h1 = false; }
@@ -188,11 +239,8 @@ ART_D bool bvh_state_advance(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min,
 #pragma unroll 1
   for (int step = 0; step < max_steps; step++) {
     st.nodes++;
-    const BvhNode2 nd = bvh_fetch_node(bv, node);
-    int c0 = nd.c0, c1 = nd.c1;
-    float e0, e1;
-    bool h0 = slab_hit(nd.b0[0], nd.b0[1], nd.b0[2], nd.b0[3], nd.b0[4], nd.b0[5], o, inv, t_min, best_t, e0);
-    bool h1 = slab_hit(nd.b1[0], nd.b1[1], nd.b1[2], nd.b1[3], nd.b1[4], nd.b1[5], o, inv, t_min, best_t, e1);
+    int c0, c1; float e0, e1; bool h0, h1;
+    bvh_node_children(bv, node, o, inv, t_min, best_t, c0, c1, h0, h1, e0, e1);
     if (h0 && c0 < 0) { st.tris += 1; bvh_leaf_test<false>(bv, ~c0, 1, o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h0 = false; }
     if (h1 && c1 < 0) { st.tris += 1; bvh_leaf_test<false>(bv, ~c1, 1, o, d, t_min, best_t, best_prim, best_u, best_v, dummy_slot); h1 = false; }
     if (h0 && h1) {
@@ -211,6 +259,33 @@ ART_D bool bvh_state_advance(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min,
   c.node = done ? -1 : node; c.sp = sp;
   c.best_t = best_t; c.best_prim = best_prim; c.best_u = best_u; c.best_v = best_v;
   return done;
+}
+
+// ---- the same walk with the leaves postponed (render_wave.cuh's traversal warps): a warp that tests a triangle the moment ONE lane
+// reaches a leaf runs the ~90-instruction test (and waits for its 48 bytes) at 1-3 lanes almost every step.  Here a step handles inner
+// nodes only; children that are leaves are parked in pend0/pend1 (links < 0; 0 = none) and the warp tests parked leaves together, when
+// enough lanes hold one.  The set of nodes visited, their order and the candidate set are those of bvh_state_advance: the children
+// hit at a node are decided before its leaves are tested there as well, and best_t is current again before the next node is fetched.
+// node: next inner node, -1 = walk complete.
+ART_D void bvh_walk_step(const BvhView& bv, f3 o, f3 inv, float t_min, float best_t, int& node, int& sp, int& pend0, int& pend1, int& pend2,
+                         int* smem_stack, int stride, int* ovf) {
+  int c0, c1; float e0, e1; bool h0, h1;
+  bvh_node_children(bv, node, o, inv, t_min, best_t, c0, c1, h0, h1, e0, e1);
+  // (parked leaves fill pend0, pend1, pend2 in that order; the caller lets a lane walk with at most ONE parked leaf, so three suffice)
+  if (h0 && c0 < 0) { if (pend0 == 0) pend0 = c0; else pend1 = c0; h0 = false; }
+  if (h1 && c1 < 0) { if (pend0 == 0) pend0 = c1; else if (pend1 == 0) pend1 = c1; else pend2 = c1; h1 = false; }
+  if (h0 && h1) {
+    if (e1 < e0) { int t = c0; c0 = c1; c1 = t; }                      // near child first, far child on the stack
+    if (sp < LBVH_SHORT_STACK) { smem_stack[sp * stride] = c1; sp++; }
+    else if (sp < LBVH_STACK) { ovf[sp - LBVH_SHORT_STACK] = c1; sp++; }
+    node = c0;
+  } else if (h0) node = c0;
+  else if (h1) node = c1;
+  else if (sp == 0) node = -1;
+  else {
+    sp--;
+    node = (sp < LBVH_SHORT_STACK) ? smem_stack[sp * stride] : ovf[sp - LBVH_SHORT_STACK];
+  }
 }
 
 }  // namespace art

@@ -78,6 +78,15 @@ constexpr int kSphereUnroll = SPH_UNROLL;     // unroll factor of the sphere loo
 #ifndef BVH_BLOCKS_PER_SM
 #define BVH_BLOCKS_PER_SM (WAVE_TOTAL_THREADS / BVH_SLOTS)      // 1024 path slots per SM, like render_wave_kernel
 #endif
+#ifndef BVH_POSTPONE_LEAVES
+#define BVH_POSTPONE_LEAVES 1             // traversal warps test parked leaves together (lbvh_traverse.cuh: bvh_walk_step)
+#endif
+#ifndef BVH_SPECULATE
+#define BVH_SPECULATE 0
+#endif
+#ifndef BVH_LEAF_LANES
+#define BVH_LEAF_LANES 6                  // lanes holding a parked leaf that end a burst of inner-node steps
+#endif
 #ifndef BVH_REFILL_STEPS
 #define BVH_REFILL_STEPS 8                // nodes a traversal lane walks between two looks at the ring of pending rays
 #endif
@@ -921,6 +930,7 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
     int s = 0, p = 0;
     f3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f), inv = mk3(0.f, 0.f, 0.f);
     BvhRayState c; c.node = -1; c.sp = 0; c.best_t = 0.f; c.best_prim = -1; c.best_u = 0.f; c.best_v = 0.f;
+    int pend0 = 0, pend1 = 0, pend2 = 0;                                      // leaves this lane has reached and not tested yet
     for (;;) {
       const unsigned idle_m = __ballot_sync(0xffffffffu, !active);
       if (idle_m) {
@@ -955,8 +965,11 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
               // not the closest hit or fails that test itself, so the walk is clipped there (the nearest hit below it stays exact)
               t_clip = S.sh_thi[s];
             }
-            inv = mk3(S.ix[s], S.iy[s], S.iz[s]);
+            inv = bvh_slab_inv_of(mk3(S.ix[s], S.iy[s], S.iz[s]));
             bvh_state_begin(g_scn.bvh, t_clip, c);
+#if BVH_POSTPONE_LEAVES
+            if (c.node == -2) { pend0 = ~0; c.node = -1; }                    // a one-triangle mesh has no inner node: its only leaf is slot 0
+#endif
             ntrav++;
             active = true;
           }
@@ -967,9 +980,43 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
         __nanosleep(100);
         continue;
       }
+#if BVH_POSTPONE_LEAVES
+      // ---- inner nodes: lanes holding a leaf wait; the burst ends when enough of them do (or nobody is left walking)
+#pragma unroll 1
+      for (int k = 0; k < BVH_REFILL_STEPS; k++) {
+#if BVH_SPECULATE
+        // a lane with ONE parked leaf walks on with its best_t not yet updated by that leaf: it may visit nodes the leaf would have
+        // culled, never fewer, and the candidate set only grows -- the closest hit and the tie rule do not depend on the order
+        const bool walk = active && pend1 == 0 && c.node >= 0;
+#else
+        const bool walk = active && pend0 == 0 && c.node >= 0;
+#endif
+        if (walk) {
+          tstat.nodes++;
+          bvh_walk_step(g_scn.bvh, o, inv, 0.0f, c.best_t, c.node, c.sp, pend0, pend1, pend2, my_stack, NTR, ovf);
+        }
+#if BVH_SPECULATE
+        const unsigned walk_m = __ballot_sync(0xffffffffu, active && pend1 == 0 && c.node >= 0);
+#else
+        const unsigned walk_m = __ballot_sync(0xffffffffu, active && pend0 == 0 && c.node >= 0);
+#endif
+        const unsigned leaf_m = __ballot_sync(0xffffffffu, pend0 != 0);
+        if (walk_m == 0u || __popc(leaf_m) >= BVH_LEAF_LANES) break;
+      }
+      // ---- parked leaves, together
+      while (pend0 != 0) {
+        int dummy_slot;
+        tstat.tris++;
+        bvh_leaf_test<false>(g_scn.bvh, ~pend0, 1, o, d, 0.0f, c.best_t, c.best_prim, c.best_u, c.best_v, dummy_slot);
+        pend0 = pend1; pend1 = pend2; pend2 = 0;
+      }
+      if (active && c.node < 0) {
+        {
+#else
       if (active) {
         const bool fin = bvh_state_advance(g_scn.bvh, o, d, inv, 0.0f, BVH_REFILL_STEPS, c, my_stack, NTR, ovf, tstat);
         if (fin) {
+#endif
           S.mesh_res[4 * s + 0] = c.best_t; S.mesh_res[4 * s + 1] = c.best_u; S.mesh_res[4 * s + 2] = c.best_v;
           S.mesh_res[4 * s + 3] = __int_as_float(c.best_prim);
           __threadfence_block();

@@ -610,7 +610,8 @@ inline bool slab(const ao_bvh::Node& n, const double o[3], const double inv[3], 
     double hi = ((double)n.bmax[a] - o[a]) * inv[a];
     if (lo > hi) std::swap(lo, hi);
     if (lo != lo || hi != hi) continue;          // 0*inf: axis-parallel ray on a slab plane -> do not cull
-    lo -= 1e-4 * (fabs(lo) + 1.0); hi += 1e-4 * (fabs(hi) + 1.0);
+    if (std::isfinite(lo)) lo -= 1e-4 * (fabs(lo) + 1.0);   // inf - inf would be NaN: an axis-parallel ray BESIDE the slab must still be culled
+    if (std::isfinite(hi)) hi += 1e-4 * (fabs(hi) + 1.0);
     if (lo > t0) t0 = lo;
     if (hi < t1) t1 = hi;
   }

@@ -88,3 +88,38 @@ def test_c5_bvh_facts(c5, pkg):
     info = gc.bvh_info()
     assert info["ntris"] == 10_002_828 and info["nnodes"] == 10_002_827
     assert info["bytes"] == 10_002_828 * (48 + 36) + 10_002_827 * 32        # 48-B triangle slots, 36 B of corner normals, 32-B quantised nodes
+
+
+def test_c5_axis_parallel_rays(c5, pkg, ob):
+    """Rays with one or two exactly-zero direction components (1/d = +-inf; a cosine sample with r2 = 0 off an axis-aligned wall makes
+    one).  The hit must equal the oracle's, and the walk must stay as short as that of the same ray tilted by 1e-4: an axis that drops out
+    of the slab test (inf * 0 = NaN) is still correct but turns a line of boxes into a slab of the tree."""
+    gs, osc, pos, tris = c5
+    rng = np.random.default_rng(77)
+    n = 24_000
+    rr = np.zeros(n, ob.ray_dt)
+    rr["origin"] = rng.uniform([-1.6, 0.2, 0.6], [1.6, 3.2, 4.4], (n, 3)).astype(np.float32)
+    d = np.zeros((n, 3), np.float32)
+    kind = rng.integers(0, 2, n)                                      # 0: two zero components, 1: one zero component
+    ax = rng.integers(0, 3, n); sg = rng.choice(np.float32([-1.0, 1.0]), n)
+    d[np.arange(n), ax] = sg
+    ax2 = (ax + 1 + rng.integers(0, 2, n)) % 3
+    sel = kind == 1
+    d[np.arange(n)[sel], ax2[sel]] = rng.uniform(-1, 1, int(sel.sum())).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    neg0 = rng.random((n, 3)) < 0.3
+    d[(d == 0) & neg0] = np.float32(-0.0)                             # +0.0 and -0.0 (1/d = +inf, -inf)
+    rr["direction"] = d
+    g = gs.Find_Closest_Hit(rr.view(pkg.ray_dt))
+    o = osc.closest_hit_batch(rr, mesh_mode=ob.MESH_NEAREST)
+    for f in g.dtype.names:
+        a, b = g[f], o[f]
+        if a.dtype.kind == "f":
+            a, b = _bits(a), _bits(b)
+        assert np.array_equal(a, b), "axis-parallel " + f
+    assert ((g["prim_type"] == 2) & (g["is_hit"] == 1)).sum() > 1000
+    tilted = rr.copy()
+    t = d + np.float32(1.0e-4) * rng.normal(size=(n, 3)).astype(np.float32)
+    tilted["direction"] = (t / np.linalg.norm(t, axis=1, keepdims=True)).astype(np.float32)
+    a = pkg.bvh_bench(rr.view(pkg.ray_dt), repeat=1); b = pkg.bvh_bench(tilted.view(pkg.ray_dt), repeat=1)
+    assert a["nodes_per_ray"] < 1.25 * b["nodes_per_ray"] + 4.0, (a, b)
