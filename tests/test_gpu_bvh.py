@@ -208,3 +208,56 @@ def test_reference_bf_mode_rejects_big_meshes(pkg, ob):
     with pytest.raises(pkg.GCoreError):
         gs.set_mesh(pos, nrm, tris, mesh_mode=pkg.MESH_REFERENCE_BF)    # brute-force reference semantics: <= 64 triangles
     gs.Init()
+
+
+@pytest.mark.parametrize("seed,nsph", [(5, 96), (7, 16)])
+def test_many_spheres_with_lbvh_mesh(pkg, ob, seed, nsph):
+    """IntersectAllSpheres (geometry.adb:48-115) at the library's limit of 96 spheres next to an LBVH mesh: spheres of very different
+    sizes, overlapping, partly outside the Cornell box; rays from inside and outside their bounds, axis-parallel, lying in and starting
+    on the walls of an 8^3 grid over them (the stress set of the sphere-grid experiment, profiles/tools/experiments/
+    r02_sphere_grid_and_prefetch.patch -- correct, but slower than the plain loop) -- every Hit field against the oracle, then a small
+    PT_MIS render."""
+    gs, osc = _mesh_scene(pkg, ob, 24, pkg.MESH_NEAREST)
+    rng = np.random.default_rng(seed)
+    sp = np.zeros(nsph, pkg.sphere_dt)
+    sp["pos"] = rng.uniform([-3.2, -0.6, -0.8], [3.2, 5.6, 6.0], (nsph, 3)).astype(np.float32)
+    sp["r"] = np.where(rng.random(nsph) < 0.2, rng.uniform(0.4, 1.1, nsph), rng.uniform(0.02, 0.25, nsph)).astype(np.float32)
+    sp["mat"] = rng.choice([1, 5, 8, 0, 3], nsph)
+    sp[nsph - 1] = ((0.0, 4.5, 1.0), 0.5, 4)                                     # the sphere light stays the last sphere
+    d0 = osc.describe()
+    gs.set_analytic(sp, d0["cornell"]); osc.set_spheres(sp.view(ob.sphere_dt))
+    # an 8^3 grid over the spheres' padded bounds, to aim rays at its walls
+    lo = (sp["pos"].astype(np.float64) - sp["r"][:, None]).min(0); hi = (sp["pos"].astype(np.float64) + sp["r"][:, None]).max(0)
+    pad = 1e-2 * (hi - lo).max() + 1e-3
+    lo -= pad; hi += pad
+    cell = (hi - lo) / 8
+    n = 400_000
+    rr = np.zeros(n, ob.ray_dt)
+    o = rng.uniform(lo - 1.0, hi + 1.0, (n, 3))
+    tgt = rng.uniform(lo, hi, (n, 3))
+    d = tgt - o
+    k = rng.integers(0, 6, n)
+    walls = lo + np.round((o - lo) / cell) * cell                                # nearest cell wall / edge / corner
+    on1 = k == 1; o[on1, 0] = walls[on1, 0]                                      # origin on an x wall
+    on2 = k == 2; o[on2] = walls[on2]                                            # origin on a cell corner
+    ax = k == 3; a = rng.integers(0, 3, n); d[ax] = 0.0; d[ax, a[ax]] = rng.choice([-1.0, 1.0], int(ax.sum()))      # axis-parallel
+    inw = k == 4; o[inw, 1] = walls[inw, 1]; d[inw, 1] = 0.0                     # lying in a y wall
+    dg = k == 5; d[dg] = np.sign(d[dg]) * cell                                   # along the cells' diagonals: ties in the DDA
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rr["origin"] = o.astype(np.float32); rr["direction"] = d.astype(np.float32)
+    g = gs.Find_Closest_Hit(rr.view(pkg.ray_dt))
+    oh = osc.closest_hit_batch(rr, mesh_mode=ob.MESH_NEAREST)
+    for f in g.dtype.names:
+        a_, b_ = g[f], oh[f]
+        if a_.dtype.kind == "f":
+            a_, b_ = _bits(a_), _bits(b_)
+        assert np.array_equal(a_, b_), f
+    assert ((g["prim_type"] == 1) & (g["is_hit"] == 1)).sum() > 20_000
+    w, h = 128, 96
+    rt = pkg.Ray_Tracer(); rt.Threads_Num = 2; rt.seed = 77
+    rt.Init_Render(pkg.PT_MIS); rt.Resize_Viewport(w, h)
+    hdr = rt.Render_Pass(read_hdr=True)
+    acc, rays = osc.render(ob.make_params(w, h, ob.PT_MIS, passes=2, seed=77, mesh_mode=ob.MESH_NEAREST))
+    assert np.array_equal(_bits(hdr[..., :3]), _bits(acc))
+    assert int(rt.last_stats.rays) == rays
+    gs.Init()
