@@ -67,7 +67,7 @@ EXPORTS = [
     "gcore_primary_hits", "gcore_accum_device_ptr", "gcore_resolve_device", "gcore_resolve_gathered_device",
     "gcore_stream", "gcore_synchronize", "gcore_last_error", "gcore_bvh_info", "gcore_kernel_regs", "gcore_bvh_bench", "gcore_load_frame", "gcore_set_stats_level", "gcore_get_bvh_counters",
     "gcore_set_gpu_count", "gcore_get_gpu_count", "gcore_device_kernel_ms", "gcore_set_seam_two_sided", "gcore_set_mesh_material",
-    "gcore_set_mesh_normals_3f", "gcore_use_committed_scene", "gcore_get_committed_scene", "gcore_bvh_occluded_batch", "gcore_seam_stats",
+    "gcore_set_mesh_normals_3f", "gcore_use_committed_scene", "gcore_get_committed_scene", "gcore_bvh_occluded_batch", "gcore_seam_stats", "gcore_seam_server_stats",
 ]
 
 _lib = None
@@ -145,6 +145,7 @@ def lib():
     L.gcore_get_committed_scene.argtypes = [vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     L.gcore_bvh_occluded_batch.argtypes = [i32, vp, f32, f32, vp]
     L.gcore_seam_stats.argtypes = [vp]
+    L.gcore_seam_server_stats.argtypes = [vp]
     _lib = L
     return L
 

@@ -116,11 +116,24 @@ State& S() { static State s; return s; }
 // share a launch + synchronisation per ~T rays instead of queueing for one each.  Waiters spin on their own flag (a render task
 // has nothing else to do, and a futex wake-up costs more than the launch); a new leader that knows of companions on their way in
 // gives them up to 3 us to file before it launches.
+// The seam's bookkeeping lock is held for a few dozen instructions at a time by up to Threads_Num callers per batch: a futex-backed mutex
+// puts them to sleep and wakes them at 5-10 us apiece (measured: 49 instead of 22 us per batch at 4 callers), so it spins.
+struct SpinLock {
+  std::atomic<int> f{0};
+  void lock() {
+    int spins = 0;
+    for (;;) {
+      if (!f.exchange(1, std::memory_order_acquire)) return;
+      while (f.load(std::memory_order_relaxed)) { if (++spins > 4096) { std::this_thread::yield(); spins = 0; } }
+    }
+  }
+  void unlock() { f.store(0, std::memory_order_release); }
+};
+
 struct Seam {
-  std::mutex m;
-  std::condition_variable cv;
-  gcore_dev::SeamRequest* h_req[2] = {nullptr, nullptr};       // mapped pinned host memory, two batches (one being filled, one in flight)
-  gcore_dev::SeamRequest* d_req[2] = {nullptr, nullptr};       // the same memory as the device sees it
+  SpinLock m;
+  gcore_dev::SeamBatch* h_req[2] = {nullptr, nullptr};         // mapped pinned host memory, two batches (one being filled, one in flight)
+  gcore_dev::SeamBatch* d_req[2] = {nullptr, nullptr};         // the same memory as the device sees it
   struct Waiter { gcore_HitCpp* out; int found; std::atomic<int> done; };
   Waiter* waiter[2][GC_SEAM_BATCH];
   int  n_open = 0;                                             // requests filed in the open batch
@@ -129,6 +142,13 @@ struct Seam {
   bool leader_active = false;
   std::atomic<int> inside{0};                                  // threads currently inside gcore_closest_hit
   unsigned long long launches = 0, rays = 0;                   // combined batches launched / rays answered (gcore_seam_stats)
+  // the resident server (render_kernels.cu: bvh_seam_server); all of it is touched under State::mu only
+  gcore_dev::SeamMailbox* h_mb = nullptr; gcore_dev::SeamMailbox* d_mb = nullptr;
+  cudaStream_t srv_stream = nullptr;
+  unsigned int seq = 0;                                        // 24-bit sequence number of the last batch posted
+  int  srv_two_sided = 0;                                      // which instantiation is (or was last) resident
+  bool srv_usable = true;                                      // false after a batch the server did not answer: back to one launch per batch
+  unsigned long long srv_starts = 0, srv_batches = 0;
 };
 Seam& seam() { static Seam s; return s; }
 
@@ -241,10 +261,84 @@ void fill_view(art::BvhView& v, const LbvhBuffers& b) {
   v.nodes = b.nodes; v.tris = b.tris; v.tri_normals = b.tri_normals; v.tri_mat = b.tri_mat; v.ntris = b.ntris; v.root = b.root;
 }
 
+// ---- resident seam server.  Host side of the mailbox protocol (gcore_internal.h: SeamMailbox): `alive` goes 0 -> 1 here, before the
+// launch, and 1 -> 0 in the kernel as its last store; a batch is posted by writing cmd and answered when done == its sequence number.
+// The kernel may leave (idle) at the very moment a batch is posted: the poster sees alive == 0 and starts a new one, which finds the
+// command waiting.  Everything here runs under State::mu.
+static inline unsigned int mb_load(const unsigned int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void mb_store(unsigned int* p, unsigned int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+
+static bool seam_server_enabled() {
+  static const bool on = [] { const char* e = getenv("GCORE_SEAM_SERVER"); return !(e && e[0] == '0'); }();
+  return on && seam().srv_usable;
+}
+
+// make the server leave and wait until it has (before the scene block in constant memory changes, before the device is released)
+static void seam_server_stop() {
+  Seam& q = seam();
+  if (!q.h_mb || !q.srv_stream) return;
+  if (mb_load(&q.h_mb->alive)) {
+    mb_store(&q.h_mb->stop, 1u);
+    cudaStreamSynchronize(q.srv_stream);
+    mb_store(&q.h_mb->stop, 0u);
+    mb_store(&q.h_mb->alive, 0u);                                       // (a kernel that died with an error never cleared it)
+  }
+}
+
+static int seam_server_start(int two_sided) {
+  State& s = S(); Seam& q = seam(); Device& dv = s.dev[0];
+  if (!q.h_mb) {
+    if (cudaHostAlloc(&q.h_mb, sizeof(gcore_dev::SeamMailbox), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&q.d_mb, q.h_mb, 0) != cudaSuccess) { q.h_mb = nullptr; return fail_cuda(cudaGetLastError(), "cudaHostAlloc seam mailbox"); }
+    memset(q.h_mb, 0, sizeof(*q.h_mb));
+    CU(cudaStreamCreateWithFlags(&q.srv_stream, cudaStreamNonBlocking), "cudaStreamCreate seam");
+  }
+  (void)dv;
+  mb_store(&q.h_mb->stop, 0u);
+  mb_store(&q.h_mb->alive, 1u);
+  q.srv_two_sided = two_sided;
+  const long long idle_ns = 2000000;                                    // 2 ms without a call: leave the SM (cudaMalloc / cudaFree wait for resident kernels)
+  // `seen` = the last batch answered: a server started to replace one that left under a posted batch must find that batch new
+  cudaError_t e = gcore_dev::launch_seam_server(q.d_mb, q.d_req[0], q.d_req[1], mb_load(&q.h_mb->done), idle_ns, two_sided, q.srv_stream);
+  if (e != cudaSuccess) { mb_store(&q.h_mb->alive, 0u); return fail_cuda(e, "seam server launch"); }
+  q.srv_starts++;
+  return 0;
+}
+
+// post batch `buf` of n requests and wait for the answers; returns 1 when the server did not answer (caller falls back to a launch)
+static int seam_server_batch(int buf, int n, int two_sided) {
+  Seam& q = seam();
+  if (q.h_mb && mb_load(&q.h_mb->alive) && q.srv_two_sided != two_sided) seam_server_stop();
+  if (!q.h_mb || !mb_load(&q.h_mb->alive)) { if (seam_server_start(two_sided)) return 1; }
+  q.seq = (q.seq + 1u) & 0xffffffu;
+  const unsigned int seq = q.seq;
+  mb_store(&q.h_mb->cmd, (seq << 8) | ((unsigned)buf << 7) | (unsigned)n);   // the requests were written before (release)
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned int spins = 1;; spins++) {
+    if (mb_load(&q.h_mb->done) == seq) break;
+    if ((spins & 0xfffu) == 0u) {
+      if (!mb_load(&q.h_mb->alive)) {
+        if (mb_load(&q.h_mb->done) == seq) break;                       // answered just before it left
+        if (cudaStreamQuery(q.srv_stream) == cudaErrorNotReady) continue;   // `alive` cleared, kernel still retiring
+        if (seam_server_start(two_sided)) return 1;                     // left idle while the batch was being posted: the next one finds it
+      }
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) {   // never seen in practice; do not hang the caller on it
+        seam_server_stop();
+        q.srv_usable = false;
+        return 1;
+      }
+    }
+  }
+  q.srv_batches++;
+  return 0;
+}
+
 // make device d see the current scene: LBVHs of the right version + the constant block
 int sync_scene(int d) {
   State& s = S(); Device& dv = s.dev[d];
   if (int rc = ensure_device(d)) return rc;
+  // a resident seam kernel would keep reading the old constant block, and cudaMalloc / cudaFree below would wait for it to idle out
+  if (d == 0 && (dv.scene_dirty || dv.mesh_version != s.mesh_version || dv.legacy_version != s.flat.version)) seam_server_stop();
   if (dv.mesh_version != s.mesh_version) { if (int rc = build_mesh_bvh(d)) return rc; dv.scene_dirty = true; }
   if (dv.legacy_version != s.flat.version) { if (int rc = build_legacy_bvh(d)) return rc; dv.scene_dirty = true; }
   if (dv.scene_dirty) {
@@ -476,6 +570,7 @@ int render_units_locked(int units, gcore_render_stats* stats) {
   if (!s.dev[0].d_accum) return fail(GCORE_E_STATE, "gcore_resize_viewport has not been called");
   if (s.cfg.max_depth < 1 || s.cfg.max_depth > 16) return fail(GCORE_E_ARG, "max_depth must be in 1..16");
   const int G = s.gpu_count;
+  seam_server_stop();                                            // the render kernels want every SM: a resident seam kernel leaves now, not 2 ms from now
   for (int d = 0; d < G; d++) if (int rc = sync_scene(d)) return rc;
   const int mesh_kind = active_mesh_kind();
   int launches = 0;
@@ -623,6 +718,7 @@ int read_frame_locked(float* hdr4, uint32_t* ldr, int* launches) {
 void release_device(int d) {
   State& s = S(); Device& dv = s.dev[d];
   if (!dv.ready) return;
+  if (d == 0) seam_server_stop();
   cudaSetDevice(dv.ordinal);
   cudaStreamSynchronize(dv.stream);
   free_accum(d);
@@ -999,10 +1095,19 @@ static int seam_launch(int buf, int n) {
   std::lock_guard<std::recursive_mutex> lk(s.mu);
   if (int rc = sync_scene(0)) return rc;
   Device& dv = s.dev[0];
-  if (dv.legacy_bvh.ntris <= 0) { for (int i = 0; i < n; i++) seam().h_req[buf][i].found = 0; return 0; }
-  cudaError_t e = gcore_dev::launch_bvh_seam(n, seam().d_req[buf], s.seam_two_sided, dv.stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(dv.stream);
-  if (e != cudaSuccess) return fail_cuda(e, "gcore_closest_hit");
+  if (dv.legacy_bvh.ntris <= 0) { for (int i = 0; i < n; i++) seam().h_req[buf]->out[i].found = 0; return 0; }
+  if (!(seam_server_enabled() && seam_server_batch(buf, n, s.seam_two_sided) == 0)) {
+    cudaError_t e = gcore_dev::launch_bvh_seam(n, seam().d_req[buf], s.seam_two_sided, dv.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dv.stream);
+    if (e != cudaSuccess) return fail_cuda(e, "gcore_closest_hit");
+  }
+  // flattened triangle id -> (primIndex inside its mesh, instIndex), here, under the scene lock the leader already holds: a caller
+  // that took the lock for its own hit would queue behind the next batch in flight
+  for (int i = 0; i < n; i++) {
+    gcore_dev::SeamOut& o = seam().h_req[buf]->out[i];
+    const int flat = o.hit.primIndex;
+    if (o.found && flat >= 0 && flat < (int)s.flat.prim.size()) { o.hit.primIndex = s.flat.prim[flat]; o.hit.instIndex = s.flat.inst[flat]; o.hit.geomIndex = 0; }
+  }
   return 0;
 }
 
@@ -1010,22 +1115,23 @@ bool gcore_closest_hit(const float a_rayPos[3], const float a_rayDir[3], float t
   if (!a_rayPos || !a_rayDir || !pHit) return false;
   try {
     Seam& q = seam();
-    std::unique_lock<std::mutex> lk(q.m);
+    std::unique_lock<SpinLock> lk(q.m);
     if (!q.h_req[0]) {                                                  // first call: the request / answer buffers
       State& s = S();
       std::lock_guard<std::recursive_mutex> slk(s.mu);
       if (ensure_device(0)) return false;
       for (int b = 0; b < 2; b++) {
-        if (cudaHostAlloc(&q.h_req[b], sizeof(gcore_dev::SeamRequest) * GC_SEAM_BATCH, cudaHostAllocMapped) != cudaSuccess ||
+        if (cudaHostAlloc(&q.h_req[b], sizeof(gcore_dev::SeamBatch), cudaHostAllocMapped) != cudaSuccess ||
             cudaHostGetDevicePointer(&q.d_req[b], q.h_req[b], 0) != cudaSuccess) { fail_cuda(cudaGetLastError(), "cudaHostAlloc seam"); q.h_req[0] = nullptr; return false; }
       }
     }
-    while (q.n_open >= GC_SEAM_BATCH) q.cv.wait(lk);                    // the open batch is full: wait for the leader to take it
+    while (q.n_open >= GC_SEAM_BATCH) { lk.unlock(); std::this_thread::yield(); lk.lock(); }   // the open batch is full: the leader takes it in a moment
     struct InsideGuard { std::atomic<int>& c; InsideGuard(std::atomic<int>& x) : c(x) { c.fetch_add(1); } ~InsideGuard() { c.fetch_sub(1); } } inside_guard(q.inside);
     Seam::Waiter me; me.out = pHit; me.found = 0; me.done.store(0);
     const int buf = q.open_buf, idx = q.n_open++;
-    gcore_dev::SeamRequest& r = q.h_req[buf][idx];
-    memcpy(r.ray.origin, a_rayPos, 12); memcpy(r.ray.direction, a_rayDir, 12); r.t_near = t_near; r.t_far = t_far; r.found = 0;
+    gcore_dev::SeamIn& r = q.h_req[buf]->in[idx];
+    memcpy(r.o, a_rayPos, 12); memcpy(r.d, a_rayDir, 12); r.t_near = t_near; r.t_far = t_far;
+    q.h_req[buf]->out[idx].found = 0;
     q.waiter[buf][idx] = &me;
     if (!q.leader_active) {
       q.leader_active = true;
@@ -1041,15 +1147,14 @@ bool gcore_closest_hit(const float a_rayPos[3], const float a_rayDir[3], float t
         }
         const int b = q.open_buf, n = q.n_open;
         q.last_n = n; q.open_buf ^= 1; q.n_open = 0;                    // later callers file into the other buffer
-        q.cv.notify_all();
         lk.unlock();
         const int rc = seam_launch(b, n);
         lk.lock();
         q.launches++; q.rays += (unsigned long long)n;
         for (int i = 0; i < n; i++) {                                   // hand the answers out (records are written only on a hit, :222-235)
           Seam::Waiter* w = q.waiter[b][i];
-          w->found = (rc == 0) ? q.h_req[b][i].found : 0;
-          if (w->found) *w->out = q.h_req[b][i].hit;
+          w->found = (rc == 0) ? q.h_req[b]->out[i].found : 0;
+          if (w->found) *w->out = q.h_req[b]->out[i].hit;
           w->done.store(1, std::memory_order_release);                  // (the waiter may leave its frame right after this store)
         }
       }
@@ -1059,26 +1164,26 @@ bool gcore_closest_hit(const float a_rayPos[3], const float a_rayDir[3], float t
       lk.unlock();
       int spins = 0;
       while (!me.done.load(std::memory_order_acquire)) {
-        if (++spins > (1 << 22)) std::this_thread::yield();             // a stuck device: stop burning the core, keep waiting
+        if (++spins > 2000) std::this_thread::yield();                  // more callers than cores: let the leader (or a filer) have this one
       }
     }
-    if (!me.found) return false;
-    // flattened triangle id -> (primIndex inside its mesh, instIndex)
-    State& s = S();
-    const int flat = pHit->primIndex;
-    {
-      std::lock_guard<std::recursive_mutex> slk(s.mu);
-      if (flat >= 0 && flat < (int)s.flat.prim.size()) { pHit->primIndex = s.flat.prim[flat]; pHit->instIndex = s.flat.inst[flat]; pHit->geomIndex = 0; }
-    }
-    return true;
+    return me.found != 0;
   } catch (...) { fail(GCORE_E_STATE, "gcore_closest_hit: internal error"); return false; }
 }
 
 int gcore_seam_stats(uint64_t* out2) {
   if (!out2) return fail(GCORE_E_ARG, "gcore_seam_stats: null");
   Seam& q = seam();
-  std::lock_guard<std::mutex> lk(q.m);
+  std::lock_guard<SpinLock> lk(q.m);
   out2[0] = q.launches; out2[1] = q.rays;
+  return 0;
+}
+
+int gcore_seam_server_stats(uint64_t* out2) {
+  if (!out2) return fail(GCORE_E_ARG, "gcore_seam_server_stats: null");
+  State& s = S();
+  std::lock_guard<std::recursive_mutex> lk(s.mu);
+  out2[0] = seam().srv_starts; out2[1] = seam().srv_batches;
   return 0;
 }
 

@@ -48,8 +48,18 @@ cudaError_t launch_closest_batch(int mesh_kind, int n, const gcore_ray* d_rays, 
 cudaError_t launch_bvh_batch(int n, const gcore_ray* d_rays, float t_near, float t_far, gcore_HitCpp* d_hits, int* d_found, int two_sided, cudaStream_t s);
 // the combined batch of pending gcore_closest_hit calls: requests / answers in mapped pinned host memory (n <= GC_SEAM_BATCH)
 #define GC_SEAM_BATCH 64
-struct SeamRequest { gcore_ray ray; float t_near, t_far; gcore_HitCpp hit; int found; };
-cudaError_t launch_bvh_seam(int n, SeamRequest* d_req, int two_sided, cudaStream_t s);
+// Requests and answers are two dense arrays so that the device moves them over PCIe in a few wide transactions (32 lanes x 4 B) instead
+// of eighteen 4-byte ones per ray -- measured: the narrow accesses cost ~4 us per ray of a batch, more than the walks themselves.
+struct SeamIn  { float o[3], d[3], t_near, t_far; };            // 8 words
+struct SeamOut { gcore_HitCpp hit; int found; };                 // 10 words
+struct SeamBatch { SeamIn in[GC_SEAM_BATCH]; SeamOut out[GC_SEAM_BATCH]; };
+cudaError_t launch_bvh_seam(int n, SeamBatch* d_batch, int two_sided, cudaStream_t s);
+// the resident form of the same kernel: one block that stays on an SM between calls and takes its batches from a mailbox in
+// mapped pinned host memory (cmd = seq << 8 | buffer << 7 | n), so that a call costs two PCIe round trips instead of a kernel launch
+// and a stream synchronisation.  It leaves by itself after `idle_ns` without a command, or when `stop` is set.
+struct SeamMailbox { unsigned int cmd, stop, pad0[14]; unsigned int done, alive, pad1[14]; };   // host-written line, device-written line
+cudaError_t launch_seam_server(SeamMailbox* d_mb, SeamBatch* d_batch0, SeamBatch* d_batch1, unsigned int seen_seq, long long idle_ns,
+                               int two_sided, cudaStream_t s);
 // occlusion query on the committed legacy scene (rtcOccluded1 semantics: any hit inside (t_near, t_far)); d_occluded[i] = 0 / 1
 cudaError_t launch_bvh_occluded(int n, const gcore_ray* d_rays, float t_near, float t_far, int* d_occluded, int two_sided, cudaStream_t s);
 // the same kernel on either LBVH (which: 0 legacy scene, 1 shaded mesh); d_counters != null: also count nodes visited,

@@ -14,6 +14,7 @@
 #include "gcore_internal.h"
 #include "art_shade.cuh"
 #include "render_wave.cuh"
+#include <cstddef>
 
 using namespace art;
 
@@ -159,26 +160,86 @@ __global__ void __launch_bounds__(RENDER_BLOCK) bvh_batch_kernel(int n, const gc
 // the one-ray seam (gcore_closest_hit): a combined batch of the calls that are pending across the host's threads.  Requests and
 // answers live in mapped pinned host memory -- the kernel reads the rays and writes the hit records over PCIe itself, so a batch
 // costs one launch and one stream synchronisation, no copies.
+static_assert(sizeof(gcore_dev::SeamIn) == 32 && sizeof(gcore_dev::SeamOut) == 40, "the seam kernels move requests / answers as 8 / 10 words");
+
+// one request (8 words: origin, direction, t_near, t_far) -> one answer (10 words: HitCpp, found)
 template <bool TWO_SIDED>
-__global__ void __launch_bounds__(32) bvh_seam_kernel(int n, gcore_dev::SeamRequest* __restrict__ req) {
-  // one ray per block (lane 0 of its only warp): a handful of latency-bound walks, spread over the SMs instead of serialising in one warp
-  const int i = blockIdx.x;
-  if (i >= n || threadIdx.x != 0) return;
+__device__ __forceinline__ void seam_answer(const float* in8, unsigned int* out10) {
   const BvhView& bv = g_scn.bvh_legacy;
-  const f3 o = ld3(req[i].ray.origin), d = ld3(req[i].ray.direction);
+  const f3 o = mk3(in8[0], in8[1], in8[2]), d = mk3(in8[3], in8[4], in8[5]);
   int prim = -1, slot = -1; float t = 0.f, u = 0.f, v = 0.f;
   BvhStats st; st.nodes = 0; st.tris = 0;
-  bvh_closest_slot_t<false, TWO_SIDED, false>(bv, o, d, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), req[i].t_near, req[i].t_far, prim, t, u, v, slot, st);
+  bvh_closest_slot_t<false, TWO_SIDED, false>(bv, o, d, mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z), in8[6], in8[7], prim, t, u, v, slot, st);
+  f3 ng = mk3(0.f, 0.f, 0.f);
   if (prim >= 0) {
-    gcore_HitCpp hc;
-    hc.primIndex = prim; hc.geomIndex = 0; hc.instIndex = 0; hc.t = t;
     const float4 e1 = __ldg(&bv.tris[3 * slot + 1]), e2 = __ldg(&bv.tris[3 * slot + 2]);
-    const f3 ng = cross(mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z));
-    hc.normal[0] = ng.x; hc.normal[1] = ng.y; hc.normal[2] = ng.z;
-    hc.texCoord[0] = v; hc.texCoord[1] = u;
-    req[i].hit = hc;
+    ng = cross(mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z));                 // Ng = (B - A) x (C - A), unnormalised like Embree's
   }
-  req[i].found = (prim >= 0) ? 1 : 0;
+  out10[0] = (unsigned)prim; out10[1] = 0u; out10[2] = 0u;                     // primIndex, geomIndex, instIndex (mapped on the host)
+  out10[3] = __float_as_uint(t);
+  out10[4] = __float_as_uint(ng.x); out10[5] = __float_as_uint(ng.y); out10[6] = __float_as_uint(ng.z);
+  out10[7] = __float_as_uint(v); out10[8] = __float_as_uint(u);               // reference v weighs B, u weighs C (geometry.adb:245-246, 301)
+  out10[9] = (prim >= 0) ? 1u : 0u;
+}
+
+// the one-ray seam (gcore_closest_hit) without the resident kernel: one block of one warp per pending request, so that the handful of
+// latency-bound walks spread over the SMs.  The warp reads its request and writes its answer as ONE access each.
+template <bool TWO_SIDED>
+__global__ void __launch_bounds__(32) bvh_seam_kernel(int n, gcore_dev::SeamBatch* __restrict__ b) {
+  __shared__ float s_in[8];
+  __shared__ unsigned int s_out[10];
+  const int i = blockIdx.x, lane = threadIdx.x;
+  if (i >= n) return;
+  if (lane < 8) s_in[lane] = ((const volatile float*)&b->in[i])[lane];
+  __syncwarp();
+  if (lane == 0) seam_answer<TWO_SIDED>(s_in, s_out);
+  __syncwarp();
+  if (lane < 10) ((volatile unsigned int*)&b->out[i])[lane] = s_out[lane];
+}
+
+// The resident seam: thread 0 polls the mailbox's command word over PCIe; a new sequence number brings a batch of n <= 64 requests in
+// batch buffer 0 or 1 (mapped pinned memory, like the mailbox).  The block copies the n x 8 request words into shared memory with
+// coalesced reads (volatile: the same host addresses carry a new batch every time), request i is answered by lane i / 32 of warp
+// i % 32 -- up to 32 walks in warps of their own: walks that share a warp serialise their node steps and triangle tests -- and the
+// n x 10 answer words go back coalesced; then `done` := the sequence number, after a system-wide fence.  Without a command for idle_ns
+// (or with `stop` set) the kernel clears `alive` and returns: nothing else waits on it for longer than that.
+__device__ __forceinline__ unsigned long long seam_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+template <bool TWO_SIDED>
+__global__ void __launch_bounds__(1024) bvh_seam_server(gcore_dev::SeamMailbox* mb, gcore_dev::SeamBatch* b0, gcore_dev::SeamBatch* b1,
+                                                        unsigned int seen, long long idle_ns) {
+  __shared__ unsigned int s_cmd;
+  __shared__ float s_in[8 * GC_SEAM_BATCH];
+  __shared__ unsigned int s_out[10 * GC_SEAM_BATCH];
+  unsigned long long t_last = seam_now_ns();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (;;) {
+    if (tid == 0) {
+      unsigned int c;
+      for (;;) {
+        c = *(volatile unsigned int*)&mb->cmd;
+        if ((c >> 8) != seen) break;
+        if (*(volatile unsigned int*)&mb->stop != 0u || (long long)(seam_now_ns() - t_last) > idle_ns) { c = 0xffffffffu; break; }
+      }
+      s_cmd = c;
+    }
+    __syncthreads();
+    const unsigned int c = s_cmd;
+    if (c == 0xffffffffu) break;
+    const int n = (int)(c & 127u);
+    gcore_dev::SeamBatch* b = (c & 128u) ? b1 : b0;
+    if (tid < 8 * n) s_in[tid] = ((const volatile float*)b->in)[tid];
+    __syncthreads();
+    const int i = warp + 32 * lane;
+    if (lane < 2 && i < n) seam_answer<TWO_SIDED>(&s_in[8 * i], &s_out[10 * i]);
+    __syncthreads();
+    if (tid < 10 * n) ((volatile unsigned int*)b->out)[tid] = s_out[tid];
+    __threadfence_system();                                                   // the answers are in host memory before `done` says so
+    __syncthreads();
+    seen = c >> 8;
+    if (tid == 0) { *(volatile unsigned int*)&mb->done = seen; t_last = seam_now_ns(); }
+  }
+  if (tid == 0) { __threadfence_system(); *(volatile unsigned int*)&mb->alive = 0u; }
 }
 
 // Ada float -> Unsigned_32 conversion rounds to nearest, ties away from zero (ray_tracer.adb:51-53)
@@ -263,10 +324,17 @@ cudaError_t launch_bvh_batch(int n, const gcore_ray* d_rays, float t_near, float
   return cudaGetLastError();
 }
 
-cudaError_t launch_bvh_seam(int n, SeamRequest* d_req, int two_sided, cudaStream_t s) {
+cudaError_t launch_bvh_seam(int n, SeamBatch* d_batch, int two_sided, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  if (two_sided) bvh_seam_kernel<true><<<n, 32, 0, s>>>(n, d_req);
-  else bvh_seam_kernel<false><<<n, 32, 0, s>>>(n, d_req);
+  if (two_sided) bvh_seam_kernel<true><<<n, 32, 0, s>>>(n, d_batch);
+  else bvh_seam_kernel<false><<<n, 32, 0, s>>>(n, d_batch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_seam_server(SeamMailbox* d_mb, SeamBatch* d_batch0, SeamBatch* d_batch1, unsigned int seen_seq, long long idle_ns,
+                               int two_sided, cudaStream_t s) {
+  if (two_sided) bvh_seam_server<true><<<1, 1024, 0, s>>>(d_mb, d_batch0, d_batch1, seen_seq, idle_ns);
+  else bvh_seam_server<false><<<1, 1024, 0, s>>>(d_mb, d_batch0, d_batch1, seen_seq, idle_ns);
   return cudaGetLastError();
 }
 

@@ -154,6 +154,10 @@ GCORE_API int gcore_bvh_closest_hit_batch(int n, const gcore_ray* rays, float t_
 /* gcore_closest_hit combines the calls that are pending across the host's threads into one kernel launch (flat combining):
  * out2 = {launches so far, rays answered so far}; rays / launches = the average batch */
 GCORE_API int gcore_seam_stats(uint64_t* out2);
+/* the batches are answered by a RESIDENT kernel that takes them from a mailbox in mapped pinned host memory (no launch, no stream
+ * synchronisation per call; it leaves the GPU after 2 ms without a call and is started again on demand; GCORE_SEAM_SERVER=0 in the
+ * environment goes back to one launch per batch): out2 = {times the resident kernel was started, batches it answered} */
+GCORE_API int gcore_seam_server_stats(uint64_t* out2);
 /* occlusion query on the committed scene for n host rays (the rtcOccluded1 counterpart, cpp/embree3/rtcore_scene.h:128, which the
  * reference's shim never exposed): occluded[i] = 1 if ANY triangle is hit with t in (t_near, t_far) */
 GCORE_API int gcore_bvh_occluded_batch(int n, const gcore_ray* rays, float t_near, float t_far, int32_t* occluded);

@@ -92,8 +92,11 @@ int main(int argc, char** argv) {
     per_thread = save;
     for (int i = 0; i < nref; i++) hits += wp[i] >= 0;
   }
-  printf("{\"threads\": %d, \"rays\": %d, \"seconds\": %.4f, \"rays_per_s\": %.1f, \"us_per_ray_per_thread\": %.2f, \"mismatches\": %ld, \"hit_rate\": %.3f, \"launches\": %llu, \"rays_per_launch\": %.2f}\n",
-         threads, n, dt, n / dt, 1e6 * dt * threads / n, bad, (double)hits / nref, s1[0] - s0[0], (double)(s1[1] - s0[1]) / (double)(s1[0] - s0[0] ? s1[0] - s0[0] : 1));
+  fn_stats server_stats = (fn_stats)dlsym(L, "gcore_seam_server_stats");
+  unsigned long long sv[2] = {0, 0};
+  if (server_stats) server_stats(sv);
+  printf("{\"threads\": %d, \"rays\": %d, \"seconds\": %.4f, \"rays_per_s\": %.1f, \"us_per_ray_per_thread\": %.2f, \"mismatches\": %ld, \"hit_rate\": %.3f, \"batches\": %llu, \"rays_per_batch\": %.2f, \"resident_kernel_starts\": %llu, \"resident_kernel_batches\": %llu}\n",
+         threads, n, dt, n / dt, 1e6 * dt * threads / n, bad, (double)hits / nref, s1[0] - s0[0], (double)(s1[1] - s0[1]) / (double)(s1[0] - s0[0] ? s1[0] - s0[0] : 1), sv[0], sv[1]);
   destroy();
   return bad ? 1 : 0;
 }

@@ -203,6 +203,8 @@ def test_closest_hit_seam_16_threads(pkg, ob):
         except Exception as e:                                         # pragma: no cover
             errors.append(e)
 
+    sv_before = np.zeros(2, np.uint64); st_before = np.zeros(2, np.uint64)
+    L.gcore_seam_server_stats(sv_before.ctypes.data); L.gcore_seam_stats(st_before.ctypes.data)
     th = [threading.Thread(target=work, args=(k,)) for k in range(nthreads)]
     for x in th:
         x.start()
@@ -214,4 +216,62 @@ def test_closest_hit_seam_16_threads(pkg, ob):
     assert np.array_equal(got_ok != 0, m)
     assert np.array_equal(got_prim[m], prim[m]) and np.all(got_prim[~m] == -1)
     assert np.array_equal(_bits(got_t[m]), _bits(t[m]))
+    sv = np.zeros(2, np.uint64); st = np.zeros(2, np.uint64)
+    assert L.gcore_seam_server_stats(sv.ctypes.data) == 0 and L.gcore_seam_stats(st.ctypes.data) == 0
+    if os.environ.get("GCORE_SEAM_SERVER", "1") != "0":
+        # every batch went through the resident kernel, not the launch fall-back
+        assert sv[0] >= 1 and sv[1] - sv_before[1] == st[0] - st_before[0] and st[1] - st_before[1] == n, (sv_before, sv, st_before, st)
+    gc.destroy()
+
+
+def test_seam_resident_kernel_sees_scene_changes(pkg, ob):
+    """The resident seam kernel reads the scene from constant memory: it must be gone before that block changes.  One ray at a time
+    (the kernel stays resident in between), then a different scene is committed, then the two-sided test is switched on -- each
+    time every answer equals brute force on the scene of the moment; a pause longer than the kernel's idle limit in between."""
+    import time
+    rng = np.random.default_rng(5)
+    L = pkg.lib()
+    gc = pkg.GeometryCore()
+
+    def soup(nt, off):
+        c = rng.uniform(-2, 2, (nt, 1, 3)) + off
+        return (c + rng.uniform(-0.3, 0.3, (nt, 3, 3))).astype(np.float32).reshape(-1, 3), np.arange(3 * nt, dtype=np.int32).reshape(-1, 3)
+
+    def ask(rays):
+        h = np.zeros(1, pkg.hitcpp_dt); out = np.full(len(rays), -1, np.int32); tt = np.zeros(len(rays), np.float32)
+        for i in range(len(rays)):
+            o = np.ascontiguousarray(rays["origin"][i]); d = np.ascontiguousarray(rays["direction"][i])
+            if L.gcore_closest_hit(o.ctypes.data, d.ctypes.data, 0.0, 100000.0, h.ctypes.data):
+                out[i] = h["primIndex"][0]; tt[i] = h["t"][0]
+        return out, tt
+
+    def brute(verts, tris, rays, two_sided):
+        n = len(rays); prim = np.zeros(n, np.int32); t = np.zeros(n, np.float32); u = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
+        rr = np.ascontiguousarray(rays.view(ob.ray_dt))
+        f = ob.lib().ao_bruteforce_closest_two_sided if two_sided else ob.lib().ao_bruteforce_closest
+        f(verts.ctypes.data, tris.ctypes.data, len(tris), n, rr.ctypes.data, 0.0, 100000.0, prim.ctypes.data, t.ctypes.data, u.ctypes.data, v.ctypes.data)
+        return prim, t
+
+    n = 600
+    rays = np.zeros(n, pkg.ray_dt)
+    rays["origin"] = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)); rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    sv0 = np.zeros(2, np.uint64); L.gcore_seam_server_stats(sv0.ctypes.data)
+    for k, (nt, off, two) in enumerate([(1500, 0.0, False), (2500, 0.4, False), (2500, 0.4, True), (1200, -0.3, False)]):
+        if k != 2:
+            verts, tris = soup(nt, off)
+            gc.init_and_clear(); gc.add_mesh_3f(verts, tris); gc.commit_scene()
+        gc.set_two_sided(two)
+        if k == 3:
+            time.sleep(0.05)                                           # well past the 2 ms idle limit: the kernel has left and is started again
+        got, gt = ask(rays)
+        want, wt = brute(verts, tris, rays, two)
+        m = want >= 0
+        assert m.sum() > 40
+        assert np.array_equal(got, np.where(m, want, -1)), k
+        assert np.array_equal(_bits(gt[m]), _bits(wt[m])), k
+    gc.set_two_sided(False)
+    sv1 = np.zeros(2, np.uint64); L.gcore_seam_server_stats(sv1.ctypes.data)
+    if os.environ.get("GCORE_SEAM_SERVER", "1") != "0":
+        assert sv1[1] - sv0[1] >= 4 * n - 4 and sv1[0] - sv0[0] >= 4, (sv0, sv1)
     gc.destroy()
