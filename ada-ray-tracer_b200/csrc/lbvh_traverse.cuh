@@ -267,13 +267,12 @@ ART_D bool bvh_state_advance(const BvhView& bv, f3 o, f3 d, f3 inv, float t_min,
 // enough lanes hold one.  The set of nodes visited, their order and the candidate set are those of bvh_state_advance: the children
 // hit at a node are decided before its leaves are tested there as well, and best_t is current again before the next node is fetched.
 // node: next inner node, -1 = walk complete.
-ART_D void bvh_walk_step(const BvhView& bv, f3 o, f3 inv, float t_min, float best_t, int& node, int& sp, int& pend0, int& pend1, int& pend2,
+ART_D void bvh_walk_step(const BvhView& bv, f3 o, f3 inv, float t_min, float best_t, int& node, int& sp, int& pend0, int& pend1,
                          int* smem_stack, int stride, int* ovf) {
   int c0, c1; float e0, e1; bool h0, h1;
   bvh_node_children(bv, node, o, inv, t_min, best_t, c0, c1, h0, h1, e0, e1);
-  // (parked leaves fill pend0, pend1, pend2 in that order; the caller lets a lane walk with at most ONE parked leaf, so three suffice)
-  if (h0 && c0 < 0) { if (pend0 == 0) pend0 = c0; else pend1 = c0; h0 = false; }
-  if (h1 && c1 < 0) { if (pend0 == 0) pend0 = c1; else if (pend1 == 0) pend1 = c1; else pend2 = c1; h1 = false; }
+  if (h0 && c0 < 0) { pend0 = c0; h0 = false; }
+  if (h1 && c1 < 0) { if (pend0 == 0) pend0 = c1; else pend1 = c1; h1 = false; }
   if (h0 && h1) {
     if (e1 < e0) { int t = c0; c0 = c1; c1 = t; }                      // near child first, far child on the stack
     if (sp < LBVH_SHORT_STACK) { smem_stack[sp * stride] = c1; sp++; }

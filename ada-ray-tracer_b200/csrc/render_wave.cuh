@@ -81,9 +81,6 @@ constexpr int kSphereUnroll = SPH_UNROLL;     // unroll factor of the sphere loo
 #ifndef BVH_POSTPONE_LEAVES
 #define BVH_POSTPONE_LEAVES 1             // traversal warps test parked leaves together (lbvh_traverse.cuh: bvh_walk_step)
 #endif
-#ifndef BVH_SPECULATE
-#define BVH_SPECULATE 0
-#endif
 #ifndef BVH_LEAF_LANES
 #define BVH_LEAF_LANES 6                  // lanes holding a parked leaf that end a burst of inner-node steps
 #endif
@@ -930,7 +927,7 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
     int s = 0, p = 0;
     f3 o = mk3(0.f, 0.f, 0.f), d = mk3(0.f, 0.f, 1.f), inv = mk3(0.f, 0.f, 0.f);
     BvhRayState c; c.node = -1; c.sp = 0; c.best_t = 0.f; c.best_prim = -1; c.best_u = 0.f; c.best_v = 0.f;
-    int pend0 = 0, pend1 = 0, pend2 = 0;                                      // leaves this lane has reached and not tested yet
+    int pend0 = 0, pend1 = 0;                                                 // leaves this lane has reached and not tested yet
     for (;;) {
       const unsigned idle_m = __ballot_sync(0xffffffffu, !active);
       if (idle_m) {
@@ -984,22 +981,11 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
       // ---- inner nodes: lanes holding a leaf wait; the burst ends when enough of them do (or nobody is left walking)
 #pragma unroll 1
       for (int k = 0; k < BVH_REFILL_STEPS; k++) {
-#if BVH_SPECULATE
-        // a lane with ONE parked leaf walks on with its best_t not yet updated by that leaf: it may visit nodes the leaf would have
-        // culled, never fewer, and the candidate set only grows -- the closest hit and the tie rule do not depend on the order
-        const bool walk = active && pend1 == 0 && c.node >= 0;
-#else
-        const bool walk = active && pend0 == 0 && c.node >= 0;
-#endif
-        if (walk) {
+        if (active && pend0 == 0 && c.node >= 0) {
           tstat.nodes++;
-          bvh_walk_step(g_scn.bvh, o, inv, 0.0f, c.best_t, c.node, c.sp, pend0, pend1, pend2, my_stack, NTR, ovf);
+          bvh_walk_step(g_scn.bvh, o, inv, 0.0f, c.best_t, c.node, c.sp, pend0, pend1, my_stack, NTR, ovf);
         }
-#if BVH_SPECULATE
-        const unsigned walk_m = __ballot_sync(0xffffffffu, active && pend1 == 0 && c.node >= 0);
-#else
         const unsigned walk_m = __ballot_sync(0xffffffffu, active && pend0 == 0 && c.node >= 0);
-#endif
         const unsigned leaf_m = __ballot_sync(0xffffffffu, pend0 != 0);
         if (walk_m == 0u || __popc(leaf_m) >= BVH_LEAF_LANES) break;
       }
@@ -1008,7 +994,7 @@ render_bvh_kernel(const __grid_constant__ WaveArgs wa) {
         int dummy_slot;
         tstat.tris++;
         bvh_leaf_test<false>(g_scn.bvh, ~pend0, 1, o, d, 0.0f, c.best_t, c.best_prim, c.best_u, c.best_v, dummy_slot);
-        pend0 = pend1; pend1 = pend2; pend2 = 0;
+        pend0 = pend1; pend1 = 0;
       }
       if (active && c.node < 0) {
         {

@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -36,3 +38,20 @@ def test_b200_arm_fails_loudly_without_a_gpu():
         return
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU path" in (r.stderr + r.stdout)
+
+
+def test_recorded_ncu_traffic_belongs_to_this_source():
+    """roofline.traffic in the bench line comes from profiles/r02_traffic.json (one `ncu --set full` capture per render kernel).  The
+    file names the hash of the kernel sources it was taken on; bench.py reports null when that is not the source it runs, and this test
+    fails so that a kernel change cannot ship with a stale capture (re-run profiles/tools/r02_final_1gpu_b.sh, or delete the file)."""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(path):
+        pytest.skip("no capture recorded: roofline.traffic is null")
+    tj = json.load(open(path))
+    assert tj["kernel_source_sha16"] == bench.kernel_source_hash()
+    for wl in ("C4_1024", "C5_small"):
+        got = bench.recorded_traffic(wl)
+        assert got[0] == tj["workloads"][wl]["dram_bytes_per_launch"] > 0 and got[1] is None
