@@ -4,8 +4,9 @@
 // tests/golden vectors and cannot be built here (no GNAT, no libembree3.a).  What holds it
 // in place instead: tests/test_oracle_kat.py checks it bit for bit against two independent
 // numpy binary32 restatements written from the Ada (tests/ada_numpy.py: rays and hits;
-// tests/ada_numpy_shading.py: lights, BxDFs, sampling maps), against the Random123 vectors
-// and against closed-form radiometry.
+// tests/ada_numpy_shading.py: lights, BxDFs, sampling maps; tests/ada_numpy_integrators.py:
+// DoPass and the three PathTrace bodies -- whole small frames, every accumulator word and
+// the ray count), against the Random123 vectors and against closed-form radiometry.
 //
 // Every function cites the Ada source it follows (paths relative to the reference
 // checkout).  Numerics contract: IEEE binary32 everywhere, no FMA

@@ -10,6 +10,8 @@ the C++ shim needs the absent libembree3.a), so the oracle is pinned by what can
   * a second restatement of the shading path in numpy binary32 (tests/ada_numpy_shading.py, also from the Ada): Lights.Sample /
     EvalPDF of both light shapes, SampleAndEvalBxDF / EvalBxDF / EvalPDF of all four BxDFs and both MapSampleToCosineDist
     maps agree with the oracle bit for bit on 10^5 random inputs each;
+  * a second restatement of DoPass and the three PathTrace bodies (tests/ada_numpy_integrators.py): small frames of all three
+    integrators equal the oracle's in every accumulator word and in the ray count;
   * hand-derivable rays (centre pixel -> back wall, rays at each sphere, the open front, the pyramid);
   * closed-form radiometry: a Lambert floor point under a fully visible sphere light has radiance
     kd * Le * (r/d)^2 * cos(theta) exactly, which checks Lights.Sample / EvalPDF / Materials.EvalBxDF / Compute_Shadow
@@ -442,3 +444,23 @@ def test_materials_against_numpy(ob, oscene, kind):
             bx_n, pe_n = np.zeros((n, 3), np.float32), np.ones(n, np.float32)        # materials.adb:256-264, 333-341
         _same(bx_o, bx_n, "%s EvalBxDF" % kind)
         _same(pe_o, pe_n, "%s EvalPDF" % kind)
+
+
+# ------------------------------------------------------------------------------------------------ integrators, bit for bit
+@pytest.mark.parametrize("kind,aa,depth,passes", [("PT_MIS", 1, 8, 2), ("PT_MIS", 0, 5, 3), ("PT_SHADOW", 1, 8, 1), ("PT_SHADOW", 0, 1, 2),
+                                                    ("PT_STUPID", 1, 8, 1), ("PT_STUPID", 0, 16, 2)])
+def test_integrators_against_independent_numpy_restatement(ob, oscene, kind, aa, depth, passes):
+    """tests/ada_numpy_integrators.py restates DoPass and the three PathTrace bodies (ray_tracer-integrators.adb:25-301) from the Ada,
+    on top of the other numpy restatements.  A 56x40 frame of the default scene: every accumulator word and the number of
+    Find_Closest_Hit calls must equal the oracle's -- which pins the recursion, the MIS weights, the order of the random draws, the
+    ray offsets and the order of the additions, not just the leaf functions."""
+    import ada_numpy_integrators as ai
+    sc, d = _scene_dict(oscene)
+    w, h, seed = 56, 40, 20240917
+    acc, rays = ai.do_pass(getattr(ob, kind), w, h, passes, bool(aa), depth, seed, sc, d["materials"], d["light"][0],
+                           {"pos": d["camera"]["pos"][0], "matrix": d["camera"]["matrix"][0]}, ob.sincos_batch, ob.expon_batch, first_sample=4)
+    want, want_rays = oscene.render(ob.make_params(w, h, getattr(ob, kind), aa=aa, max_depth=depth, passes=passes, seed=seed, first_sample=4))
+    assert rays == want_rays
+    bad = np.nonzero((_bits(acc) != _bits(want)).any(-1))
+    assert len(bad[0]) == 0, "%d pixels differ, first at (y, x) = (%d, %d): %s vs %s" % (len(bad[0]), bad[0][0], bad[1][0], acc[bad[0][0], bad[1][0]], want[bad[0][0], bad[1][0]])
+    assert (want > 0).any(-1).mean() > 0.05                            # (PT_STUPID finds the light rarely)
