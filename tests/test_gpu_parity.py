@@ -134,6 +134,25 @@ def test_render_bit_exact(gscene, oscene, pkg, ob, rtype, aa, depth, units, w, h
     assert np.array_equal(rt.screen_buffer, ob.resolve(acc, rt.GetSPP()))
 
 
+@pytest.mark.parametrize("rtype,aa,depth,units", [("PT_MIS", 1, 8, 2), ("PT_SHADOW", 0, 4, 3), ("PT_STUPID", 1, 8, 1)])
+def test_render_equals_the_numpy_restatement_directly(gscene, oscene, pkg, ob, rtype, aa, depth, units):
+    """the CUDA path against tests/ada_numpy_integrators.py -- the restatement of the whole render that was written from the Ada
+    sources independently of the oracle -- without the oracle in between (it only supplies the scene constants and sin / cos / **)"""
+    import ada_numpy_integrators as ai
+    w, h = 56, 40
+    rt = pkg.Ray_Tracer()
+    rt.Threads_Num = units; rt.Anti_Aliasing_On = bool(aa); rt.Max_Trace_Depth = depth; rt.seed = 424242
+    rt.Background_Color = (0.0, 0.0, 0.0)
+    rt.Init_Render(getattr(pkg, rtype)); rt.Resize_Viewport(w, h)
+    hdr = rt.Render_Pass(read_hdr=True)
+    d = oscene.describe()
+    sc = {"spheres": d["spheres"], "cornell": d["cornell"][0], "pos": d["pos"], "nrm": d["nrm"], "tris": d["tris"], "bbox": d["bbox"]}
+    acc, rays = ai.do_pass(getattr(ob, rtype), w, h, units, bool(aa), depth, rt.seed, sc, d["materials"], d["light"][0],
+                           {"pos": d["camera"]["pos"][0], "matrix": d["camera"]["matrix"][0]}, ob.sincos_batch, ob.expon_batch)
+    assert np.array_equal(_bits(hdr[..., :3]), _bits(acc))
+    assert int(rt.last_stats.rays) == rays
+
+
 def test_background_colour_and_progressive_passes(gscene, oscene, pkg, ob):
     """two Render_Pass calls == one call with twice the units (sample indices continue); Background_Color is added
     once per AA pixel-pass (integrators.adb:42)"""
