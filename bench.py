@@ -47,12 +47,14 @@ FLOP_QUERY_MESH, FLOP_QUERY_NOMESH, FLOP_BOUNCE = 564.0, 140.0, 200.0      # SUR
 
 
 def kernel_source_hash():
-    """sha256 over the CUDA sources of the library: ties recorded ncu figures (profiles/r02_traffic.json) to the build they were taken on"""
+    """sha256 over the device-side sources of the library (every kernel, every header they include, the compile flags; not gcore_api.cu, the
+    host side of the C ABI): ties recorded ncu figures (profiles/r02_traffic.json) to the kernels they were taken on"""
     import glob
     import hashlib
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(ROOT, "ada-ray-tracer_b200", "csrc", "*.cu")) + glob.glob(os.path.join(ROOT, "ada-ray-tracer_b200", "csrc", "*.cuh"))
-                    + glob.glob(os.path.join(ROOT, "ada-ray-tracer_b200", "csrc", "*.h"))):
+    csrc = os.path.join(ROOT, "ada-ray-tracer_b200", "csrc")
+    for f in sorted([os.path.join(csrc, "render_kernels.cu"), os.path.join(csrc, "lbvh_build.cu"), os.path.join(csrc, "Makefile")]
+                    + glob.glob(os.path.join(csrc, "*.cuh")) + glob.glob(os.path.join(csrc, "*.h"))):
         h.update(os.path.basename(f).encode()); h.update(open(f, "rb").read())
     return h.hexdigest()[:16]
 
