@@ -320,10 +320,13 @@ static int seam_server_batch(int buf, int n, int two_sided) {
       if (!mb_load(&q.h_mb->alive)) {
         if (mb_load(&q.h_mb->done) == seq) break;                       // answered just before it left
         if (cudaStreamQuery(q.srv_stream) == cudaErrorNotReady) continue;   // `alive` cleared, kernel still retiring
-        if (seam_server_start(two_sided)) return 1;                     // left idle while the batch was being posted: the next one finds it
+        // left idle while the batch was being posted: a new one finds the command waiting.  If it cannot be started the batch goes to a
+        // launch; nobody is resident, so `done` is ours to write: the posted command must not look new to a later server
+        if (seam_server_start(two_sided)) { mb_store(&q.h_mb->done, seq); return 1; }
       }
       if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) {   // never seen in practice; do not hang the caller on it
         seam_server_stop();
+        mb_store(&q.h_mb->done, seq);
         q.srv_usable = false;
         return 1;
       }
