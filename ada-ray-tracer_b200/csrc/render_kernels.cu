@@ -197,11 +197,91 @@ __global__ void __launch_bounds__(32) bvh_seam_kernel(int n, gcore_dev::SeamBatc
   if (lane < 10) ((volatile unsigned int*)&b->out[i])[lane] = s_out[lane];
 }
 
+// One ray, one WARP: the walk of a single ray is a chain of 40-100 dependent fetches when one lane does it, and a batch of the seam is as
+// slow as its slowest ray.  Here the warp keeps a frontier of inner nodes in shared memory and every round its lanes take the last (up to)
+// 32 entries: one fetch latency per round for 32 boxes pairs, leaves are tested by the lane that finds them, the lanes' best hits are
+// merged by (t, then lowest triangle id) -- the closest hit and the tie rule of bvh_closest_slot_t do not depend on the order of the
+// visits, and the culling bound is the warp's current minimum (closed, so that equal-t candidates still reach the tie rule).  Near-first
+// order is lost inside a round, so more nodes are touched; what shrinks is the number of DEPENDENT rounds (about the depth of the tree).
+// A frontier that would not fit (SEAM_FRONTIER entries) sends the ray to the one-lane walk instead.
+#define SEAM_FRONTIER 768
+#ifndef SEAM_WARP_WALK
+#define SEAM_WARP_WALK 1
+#endif
+template <bool TWO_SIDED>
+__device__ __forceinline__ void seam_answer_warp(const float* in8, unsigned int* out10, int* frontier, int lane) {
+  const BvhView& bv = g_scn.bvh_legacy;
+  const unsigned int FULL = 0xffffffffu;
+  const f3 o = mk3(in8[0], in8[1], in8[2]), d = mk3(in8[3], in8[4], in8[5]);
+  const float t_near = in8[6], t_far = in8[7];
+  if (bv.ntris <= 0 || bv.root < 0) {                                          // empty or one-triangle scene: nothing to share out
+    if (lane == 0) seam_answer<TWO_SIDED>(in8, out10);
+    __syncwarp();
+    return;
+  }
+  const f3 inv = bvh_slab_inv_of(mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z));
+  float best_t = t_far, best_u = 0.f, best_v = 0.f; int best_prim = -1, best_slot = -1;      // this lane's best
+  float bound = t_far;                                                         // the warp's best so far
+  int count = 1;
+  bool overflow = false;
+  if (lane == 0) frontier[0] = bv.root;
+  __syncwarp();
+  while (count > 0) {
+    const int take = count < 32 ? count : 32;
+    const int node = (lane < take) ? frontier[count - 1 - lane] : -1;
+    count -= take;
+    __syncwarp();
+    int push0 = -1, push1 = -1;
+    if (node >= 0) {
+      int c0, c1; float e0, e1; bool h0, h1;
+      bvh_node_children(bv, node, o, inv, t_near, bound, c0, c1, h0, h1, e0, e1);
+      if (h0) { if (c0 < 0) bvh_leaf_test<TWO_SIDED>(bv, ~c0, 1, o, d, t_near, best_t, best_prim, best_u, best_v, best_slot); else push0 = c0; }
+      if (h1) { if (c1 < 0) bvh_leaf_test<TWO_SIDED>(bv, ~c1, 1, o, d, t_near, best_t, best_prim, best_u, best_v, best_slot); else push1 = c1; }
+      if (push0 >= 0 && push1 >= 0 && e0 < e1) { const int t = push0; push0 = push1; push1 = t; }   // the nearer child is filed last: taken first
+    }
+    float m = best_t;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fminf(m, __shfl_xor_sync(FULL, m, off));
+    bound = m;
+    const unsigned int m0 = __ballot_sync(FULL, push0 >= 0), m1 = __ballot_sync(FULL, push1 >= 0);
+    const int n0 = __popc(m0), n1 = __popc(m1);
+    if (count + n0 + n1 > SEAM_FRONTIER) { overflow = true; break; }
+    const unsigned int below = (1u << lane) - 1u;
+    if (push0 >= 0) frontier[count + __popc(m0 & below)] = push0;
+    if (push1 >= 0) frontier[count + n0 + __popc(m1 & below)] = push1;
+    count += n0 + n1;
+    __syncwarp();
+  }
+  if (overflow) {                                                              // (uniform) never seen on the test scenes; correctness does not depend on it
+    if (lane == 0) seam_answer<TWO_SIDED>(in8, out10);
+    __syncwarp();
+    return;
+  }
+  // the winner: smallest t, ties to the lowest original triangle id (the rule inside bvh_leaf_test)
+  float wt = best_t; int wp = (best_prim >= 0) ? best_prim : 0x7fffffff; int wl = lane;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ot = __shfl_xor_sync(FULL, wt, off); const int op = __shfl_xor_sync(FULL, wp, off); const int ol = __shfl_xor_sync(FULL, wl, off);
+    const bool theirs = (op != 0x7fffffff) && (wp == 0x7fffffff || ot < wt || (ot == wt && op < wp));
+    if (theirs) { wt = ot; wp = op; wl = ol; }
+  }
+  if (wp == 0x7fffffff) {
+    if (lane == 0) { for (int k = 0; k < 9; k++) out10[k] = 0u; out10[0] = (unsigned)-1; out10[9] = 0u; }
+  } else if (lane == wl) {
+    const float4 e1 = __ldg(&bv.tris[3 * best_slot + 1]), e2 = __ldg(&bv.tris[3 * best_slot + 2]);
+    const f3 ng = cross(mk3(e1.x, e1.y, e1.z), mk3(e2.x, e2.y, e2.z));
+    out10[0] = (unsigned)best_prim; out10[1] = 0u; out10[2] = 0u; out10[3] = __float_as_uint(best_t);
+    out10[4] = __float_as_uint(ng.x); out10[5] = __float_as_uint(ng.y); out10[6] = __float_as_uint(ng.z);
+    out10[7] = __float_as_uint(best_v); out10[8] = __float_as_uint(best_u);
+    out10[9] = 1u;
+  }
+  __syncwarp();
+}
+
 // The resident seam: thread 0 polls the mailbox's command word over PCIe; a new sequence number brings a batch of n <= 64 requests in
 // batch buffer 0 or 1 (mapped pinned memory, like the mailbox).  The block copies the n x 8 request words into shared memory with
-// coalesced reads (volatile: the same host addresses carry a new batch every time), request i is answered by lane i / 32 of warp
-// i % 32 -- up to 32 walks in warps of their own: walks that share a warp serialise their node steps and triangle tests -- and the
-// n x 10 answer words go back coalesced; then `done` := the sequence number, after a system-wide fence.  Without a command for idle_ns
+// coalesced reads (volatile: the same host addresses carry a new batch every time), request i is answered by warp i % 32 with all its
+// lanes (seam_answer_warp; requests 32.. in a second round) and the n x 10 answer words go back coalesced; then `done` := the sequence number, after a system-wide fence.  Without a command for idle_ns
 // (or with `stop` set) the kernel clears `alive` and returns: nothing else waits on it for longer than that.
 __device__ __forceinline__ unsigned long long seam_now_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
@@ -211,6 +291,7 @@ __global__ void __launch_bounds__(1024) bvh_seam_server(gcore_dev::SeamMailbox* 
   __shared__ unsigned int s_cmd;
   __shared__ float s_in[8 * GC_SEAM_BATCH];
   __shared__ unsigned int s_out[10 * GC_SEAM_BATCH];
+  extern __shared__ int s_frontier[];                                         // SEAM_FRONTIER entries per warp
   unsigned long long t_last = seam_now_ns();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (;;) {
@@ -230,8 +311,12 @@ __global__ void __launch_bounds__(1024) bvh_seam_server(gcore_dev::SeamMailbox* 
     gcore_dev::SeamBatch* b = (c & 128u) ? b1 : b0;
     if (tid < 8 * n) s_in[tid] = ((const volatile float*)b->in)[tid];
     __syncthreads();
+#if SEAM_WARP_WALK
+    for (int i = warp; i < n; i += 32) seam_answer_warp<TWO_SIDED>(&s_in[8 * i], &s_out[10 * i], &s_frontier[SEAM_FRONTIER * warp], lane);   // (uniform per warp)
+#else
     const int i = warp + 32 * lane;
     if (lane < 2 && i < n) seam_answer<TWO_SIDED>(&s_in[8 * i], &s_out[10 * i]);
+#endif
     __syncthreads();
     if (tid < 10 * n) ((volatile unsigned int*)b->out)[tid] = s_out[tid];
     __threadfence_system();                                                   // the answers are in host memory before `done` says so
@@ -333,8 +418,12 @@ cudaError_t launch_bvh_seam(int n, SeamBatch* d_batch, int two_sided, cudaStream
 
 cudaError_t launch_seam_server(SeamMailbox* d_mb, SeamBatch* d_batch0, SeamBatch* d_batch1, unsigned int seen_seq, long long idle_ns,
                                int two_sided, cudaStream_t s) {
-  if (two_sided) bvh_seam_server<true><<<1, 1024, 0, s>>>(d_mb, d_batch0, d_batch1, seen_seq, idle_ns);
-  else bvh_seam_server<false><<<1, 1024, 0, s>>>(d_mb, d_batch0, d_batch1, seen_seq, idle_ns);
+  const int smem = SEAM_FRONTIER * 32 * (int)sizeof(int);                    // the warps' frontiers (96 KB)
+  cudaError_t e = two_sided ? cudaFuncSetAttribute(bvh_seam_server<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                            : cudaFuncSetAttribute(bvh_seam_server<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  if (two_sided) bvh_seam_server<true><<<1, 1024, smem, s>>>(d_mb, d_batch0, d_batch1, seen_seq, idle_ns);
+  else bvh_seam_server<false><<<1, 1024, smem, s>>>(d_mb, d_batch0, d_batch1, seen_seq, idle_ns);
   return cudaGetLastError();
 }
 
