@@ -134,6 +134,18 @@ def find_closest_hit(o, d, scene):
     b_matid = np.asarray(box["mat_indices"], np.int32).reshape(6)[plane]
     b_nrm = np.asarray(box["normals"], F).reshape(6, 3)[plane]
 
+    # ---- hits(3): IntersectFlatLight, geometry.adb:118-143 -- only in the rect-light variant of the scene (scene.adb:65-67)
+    fl = scene.get("flatlight")
+    if fl is not None:
+        fmin, fmax = np.asarray(fl["boxMin"], F).reshape(3), np.asarray(fl["boxMax"], F).reshape(3)
+        with np.errstate(all="ignore"):
+            inv_dir_y = F(1.0) / d[:, 1]
+            f_t = (fmax[1] - o[:, 1]) * inv_dir_y
+            hp = o + f_t[:, None] * d
+            f_hit = (hp[:, 0] > fmin[0]) & (hp[:, 0] < fmax[0]) & (hp[:, 2] > fmin[2]) & (hp[:, 2] < fmax[2]) & (f_t >= 0)
+    else:
+        f_hit, f_t = None, None
+
     # ---- hits(4): IntersectMeshBF, geometry.adb:266-323 (+ IntersectTriangle :231-263)
     pos, nrm, tris, bbox = scene["pos"], scene["nrm"], scene["tris"], scene["bbox"]
     m_in, _, _ = intersect_box(o, d, np.asarray(bbox[:3], F), np.asarray(bbox[3:], F))
@@ -168,7 +180,7 @@ def find_closest_hit(o, d, scene):
     # ---- nearest of the candidates, strict '<' in order (scene.adb:71-78)
     nearest = np.zeros(n, np.int32)                               # index 0 = hits(1)
     dist = np.full(n, INFINITY, F)
-    for idx, (hit, t) in enumerate([(s_hit, s_t), (b_hit, b_t), (None, None), (m_hit, m_t)]):
+    for idx, (hit, t) in enumerate([(s_hit, s_t), (b_hit, b_t), (f_hit, f_t), (m_hit, m_t)]):
         if hit is None:
             continue
         take = hit & (t < dist)
@@ -176,15 +188,18 @@ def find_closest_hit(o, d, scene):
         dist = np.where(take, t, dist)
 
     out = {}
-    sel = lambda a, b, c: np.where(nearest == 0, a, np.where(nearest == 1, b, c))
-    out["is_hit"] = sel(s_hit, b_hit, m_hit).astype(np.int32)
-    out["prim_type"] = sel(1, 0, 2).astype(np.int32)              # geometry.ads: Plane 0, Sphere 1, Triangle 2
-    out["prim_index"] = sel(min_i, plane, m_tri).astype(np.int32)
-    out["matId"] = sel(0, b_matid, 2).astype(np.int32)
-    out["mat"] = sel(s_mat, b_matid, 2).astype(np.int32)          # scene.adb:80-82
-    out["t"] = sel(s_t, b_t, m_t).astype(F)
-    out["normal"] = np.where((nearest == 0)[:, None], s_nrm, np.where((nearest == 1)[:, None], b_nrm, m_nrm)).astype(F)
-    out["tx"] = sel(F(0), F(0), m_tx).astype(F)
+    if f_hit is None:
+        f_hit, f_t = np.zeros(n, bool), np.zeros(n, F)
+    sel = lambda a, b, c, q=None: np.where(nearest == 0, a, np.where(nearest == 1, b, np.where(nearest == 2, c if q is None else q, c)))
+    out["is_hit"] = sel(s_hit, b_hit, m_hit, f_hit).astype(np.int32)
+    out["prim_type"] = sel(1, 0, 2, 3).astype(np.int32)           # geometry.ads: Plane 0, Sphere 1, Triangle 2, Quad 3
+    out["prim_index"] = sel(min_i, plane, m_tri, 0).astype(np.int32)
+    out["matId"] = sel(0, b_matid, 2, 0).astype(np.int32)
+    out["mat"] = sel(s_mat, b_matid, 2, 4).astype(np.int32)       # scene.adb:80-82; the flat light carries materials(4) (scene.adb:66)
+    out["t"] = sel(s_t, b_t, m_t, f_t).astype(F)
+    out["normal"] = np.where((nearest == 0)[:, None], s_nrm, np.where((nearest == 1)[:, None], b_nrm,
+                             np.where((nearest == 2)[:, None], np.asarray([0, -1, 0], F), m_nrm))).astype(F)
+    out["tx"] = sel(F(0), F(0), m_tx, F(0)).astype(F)
     out["ty"] = out["tx"].copy()
     return out
 

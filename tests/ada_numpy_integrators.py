@@ -103,6 +103,18 @@ def path_trace(kind, o, d, pixel, sample, seed, max_depth, scene, mats, light, s
     is_light = np.array([int(m["type"]) == MAT_LIGHT for m in mats])
     emit = np.array([light["intensity"] if (int(m["type"]) == MAT_LIGHT and int(m["light"]) >= 0) else (0, 0, 0) for m in mats], F)
     center, radius, area, intensity = light["center"].astype(F), F(light["radius"]), F(light["surfaceArea"]), light["intensity"].astype(F)
+    rect = int(light["shape"]) == 0                               # Light_Shape_Rect: AreaLight (lights.adb:47-90), else SphereLight
+
+    def light_sample(u1, u2, p):                                  # Lights.Sample -> (pos, pdf)
+        if rect:
+            return sh.area_light_sample(light["boxMin"].astype(F), light["boxMax"].astype(F), light["normal"].astype(F), area, u1, u2, p)
+        return sh.sphere_light_sample(center, radius, area, u1, u2, p, sincos)
+
+    def light_eval_pdf(p, ray_dir, hit_dist):                     # Lights.EvalPDF
+        if rect:                                                  # :81-85 PdfAtoW(AreaPDF, hitDist, max(dot(rayDir, -normal), 0))
+            cos_t = an._max(an._dot(ray_dir, -np.broadcast_to(light["normal"].astype(F), ray_dir.shape)), F(0.0))
+            return ((F(1.0) / area) * hit_dist * hit_dist / an._max(cos_t, sh.EPS_DIV)).astype(F)
+        return sh.sphere_light_eval_pdf(center, radius, area, p)
     levels = []                                                  # per level: (bounced, ended, end_value, explicit, throughput)
     rays = 0
     for level in range(max_depth):                               # recursion_level = max_depth - level > 0
@@ -123,7 +135,7 @@ def path_trace(kind, o, d, pixel, sample, seed, max_depth, scene, mats, light, s
             e = emit[mat[lightm]]
             if kind == PT_MIS:                                                               # :229-242
                 with np.errstate(all="ignore"):
-                    lgt = sh.sphere_light_eval_pdf(center, radius, area, o[li])
+                    lgt = light_eval_pdf(o[li], d[li], h["t"][lightm])
                     bs = prev_pdf[li]
                     w = np.where(prev_spec[li], F(1.0), bs * bs / (lgt * lgt + bs * bs)).astype(F)
                 e = _scale(w, e)
@@ -140,7 +152,7 @@ def path_trace(kind, o, d, pixel, sample, seed, max_depth, scene, mats, light, s
             hpos = ro + rd * t[:, None]
             with np.errstate(all="ignore"):
                 if kind != PT_STUPID:
-                    lpos, lpdf = sh.sphere_light_sample(center, radius, area, u[:, 0], u[:, 1], hpos, sincos)
+                    lpos, lpdf = light_sample(u[:, 0], u[:, 1], hpos)
                     sdir = an._normalize(lpos - hpos)
                     in_shadow = an.compute_shadow(hpos, lpos, scene)
                     rays += len(si)

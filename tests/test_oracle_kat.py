@@ -464,3 +464,28 @@ def test_integrators_against_independent_numpy_restatement(ob, oscene, kind, aa,
     bad = np.nonzero((_bits(acc) != _bits(want)).any(-1))
     assert len(bad[0]) == 0, "%d pixels differ, first at (y, x) = (%d, %d): %s vs %s" % (len(bad[0]), bad[0][0], bad[1][0], acc[bad[0][0], bad[1][0]], want[bad[0][0], bad[1][0]])
     assert (want > 0).any(-1).mean() > 0.05                            # (PT_STUPID finds the light rarely)
+
+
+@pytest.mark.parametrize("kind", ["PT_MIS", "PT_SHADOW", "PT_STUPID"])
+def test_integrators_rect_light_scene_against_numpy(ob, kind):
+    """the AreaLight variant of the scene (scene.adb:109-114, 130-136): IntersectFlatLight joins the candidates, Lights.Sample / EvalPDF
+    are the area light's -- oracle against the numpy restatement, every accumulator word and the ray count"""
+    import ada_numpy_integrators as ai
+    osc = ob.OracleScene()
+    d = osc.describe()
+    light = d["light"].copy(); light["shape"] = 0
+    light["intensity"] = 20.0
+    light["surfaceArea"] = (0.75 + 0.75) * (3.25 - 1.25)
+    fl = np.zeros(1, ob.flatlight_dt)
+    fl["boxMin"] = light["boxMin"]; fl["boxMax"] = light["boxMax"]; fl["normal"] = light["normal"]; fl["intensity"] = 20.0
+    osc.set_light(light); osc.set_flatlight(fl); osc.set_spheres(d["spheres"][:2])
+    d = osc.describe()
+    sc = {"spheres": d["spheres"], "cornell": d["cornell"][0], "pos": d["pos"], "nrm": d["nrm"], "tris": d["tris"], "bbox": d["bbox"],
+          "flatlight": {"boxMin": fl["boxMin"][0], "boxMax": fl["boxMax"][0]}}
+    w, h, seed = 48, 36, 777
+    acc, rays = ai.do_pass(getattr(ob, kind), w, h, 2, True, 8, seed, sc, d["materials"], d["light"][0],
+                           {"pos": d["camera"]["pos"][0], "matrix": d["camera"]["matrix"][0]}, ob.sincos_batch, ob.expon_batch)
+    want, want_rays = osc.render(ob.make_params(w, h, getattr(ob, kind), aa=1, max_depth=8, passes=2, seed=seed))
+    assert rays == want_rays
+    assert np.array_equal(_bits(acc), _bits(want))
+    assert (want > 0).any(-1).mean() > 0.05
